@@ -1,0 +1,11 @@
+"""Importable alias for the package directory ``ggllm.cpp_b200/`` (a dotted directory name cannot be
+imported with a plain ``import`` statement).  ``import ggllm_cpp_b200`` loads that directory as a package."""
+import importlib.util
+import os
+import sys
+
+_dir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "ggllm.cpp_b200")
+_spec = importlib.util.spec_from_file_location(__name__, os.path.join(_dir, "__init__.py"), submodule_search_locations=[_dir])
+_mod = importlib.util.module_from_spec(_spec)
+sys.modules[__name__] = _mod
+_spec.loader.exec_module(_mod)

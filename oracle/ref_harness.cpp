@@ -1,0 +1,62 @@
+// ref_harness.cpp -- thin C driver over the UNMODIFIED reference's public C API (libfalcon.h:149-335).
+//
+// TEST INFRASTRUCTURE ONLY.  Compiled (oracle/Makefile, target `ref`) together with the reference objects
+// into oracle/_ref/libfalcon_ref.so (CPU build) and oracle/_ref/libfalcon_hook.so (-DGGML_USE_CUBLAS build whose
+// ggml_cuda_* symbols are resolved by our libggml_b200.so).  It contains no arithmetic of its own: it
+// only calls falcon_init_backend / falcon_init_from_file / falcon_eval / falcon_get_logits, the same
+// sequence examples/falcon/falcon_main.cpp:146-159, 822-843 performs, so that Python (ctypes) does not have
+// to pass C++ structs by value.
+#include "libfalcon.h"
+#include "ggml.h"
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+extern "C" {
+
+// returns an opaque handle or NULL.  n_gpu_layers is ignored by the CPU build.
+void * refh_load(const char * path, int n_ctx, int n_batch, int n_gpu_layers, int logits_all) {
+    static bool backend_ready = false;
+    if (!backend_ready) { falcon_init_backend(); backend_ready = true; }
+    falcon_context_params p = falcon_context_default_params();
+    p.n_ctx = n_ctx;
+    p.n_batch = n_batch;
+    p.n_gpu_layers = n_gpu_layers;
+    p.seed = 1;
+    p.f16_kv = false;              // Falcon always runs an f32 KV cache (examples/falcon_common.cpp:786)
+    p.logits_all = logits_all != 0;
+    p.use_mmap = true;
+    return falcon_init_from_file(path, p);
+}
+
+// evaluates `n` tokens at position n_past; copies n_vocab (or n*n_vocab if the context was loaded with
+// logits_all) floats to `logits`.  Returns 0 on success (falcon_eval's convention, libfalcon.cpp:4566).
+int refh_eval(void * h, const int * tokens, int n, int n_past, int n_threads, int n_max_real_ctx, float * logits, int logits_all) {
+    falcon_context * ctx = (falcon_context *) h;
+    falcon_evaluation_config cfg;
+    cfg.n_tokens = n;
+    cfg.n_past = n_past;
+    cfg.n_threads = n_threads;
+    cfg.n_max_real_ctx = n_max_real_ctx;
+    int rc = falcon_eval(ctx, tokens, cfg);
+    if (rc != 0) return rc;
+    const int nv = falcon_n_vocab(ctx);
+    memcpy(logits, falcon_get_logits(ctx), sizeof(float) * (size_t) nv * (logits_all ? n : 1));
+    return 0;
+}
+
+int refh_n_vocab(void * h) { return falcon_n_vocab((falcon_context *) h); }
+void refh_free(void * h) { llama_free((falcon_context *) h); }
+
+// quantise a GGCC file with the reference's own quantiser driver (libfalcon.cpp:3533-3743); ftype = enum llama_ftype
+int refh_quantize(const char * in, const char * out, int ftype, int nthread) {
+    llama_model_quantize_params qp = llama_model_quantize_default_params();
+    qp.ftype = (enum llama_ftype) ftype;
+    qp.nthread = nthread;
+    return falcon_model_quantize(in, out, &qp);
+}
+
+// the reference's own timing table (libfalcon.cpp:4700-4714)
+void refh_print_timings(void * h) { falcon_print_timings((falcon_context *) h); }
+
+} // extern "C"
