@@ -1,0 +1,148 @@
+// c_api.cu -- part A of include/ggml_b200.h: the kernel-level C ABI.
+#include "kernels.h"
+#include "../../include/ggml_b200.h"
+#include <mutex>
+#include <cstring>
+
+struct b200_weight { WPlanes W; };
+struct b200_actq { ActQ A; void * base; size_t bytes; };
+
+static cudaStream_t g_own_stream = nullptr;
+static cudaStream_t g_stream = nullptr;
+static std::mutex g_mu;
+
+cudaStream_t b200_current_stream() { return g_stream; }
+
+extern "C" {
+
+int b200_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+int b200_init(int device) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    B200_CUDA_CHECK(cudaSetDevice(device));
+    if (!g_own_stream) {
+        B200_CUDA_CHECK(cudaStreamCreateWithFlags(&g_own_stream, cudaStreamNonBlocking));
+        g_stream = g_own_stream;
+    }
+    int sms = 0, major = 0;
+    B200_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    B200_CUDA_CHECK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
+    if (major != 10) { fprintf(stderr, "b200: device %d has compute capability %d.x; this library is sm_100a only\n", device, major); exit(1); }
+    return sms;
+}
+
+void b200_set_stream(void * s) { g_stream = s ? (cudaStream_t) s : g_own_stream; }
+void b200_synchronize(void) { B200_CUDA_CHECK(cudaStreamSynchronize(g_stream)); }
+
+void * b200_event_create(void) { cudaEvent_t e; B200_CUDA_CHECK(cudaEventCreate(&e)); return (void *) e; }
+void b200_event_destroy(void * e) { if (e) B200_CUDA_CHECK(cudaEventDestroy((cudaEvent_t) e)); }
+void b200_event_record(void * e, void * stream) { B200_CUDA_CHECK(cudaEventRecord((cudaEvent_t) e, stream ? (cudaStream_t) stream : g_stream)); }
+void b200_event_synchronize(void * e) { B200_CUDA_CHECK(cudaEventSynchronize((cudaEvent_t) e)); }
+float b200_event_elapsed_ms(void * a, void * b) { float ms = 0.f; B200_CUDA_CHECK(cudaEventElapsedTime(&ms, (cudaEvent_t) a, (cudaEvent_t) b)); return ms; }
+void b200_stream_synchronize(void * stream) { B200_CUDA_CHECK(cudaStreamSynchronize(stream ? (cudaStream_t) stream : g_stream)); }
+
+void * b200_malloc(size_t bytes) { void * p = nullptr; B200_CUDA_CHECK(cudaMalloc(&p, bytes ? bytes : 1)); return p; }
+void b200_free(void * p) { if (p) B200_CUDA_CHECK(cudaFree(p)); }
+void b200_memcpy_h2d(void * d, const void * s, size_t n) { B200_CUDA_CHECK(cudaMemcpyAsync(d, s, n, cudaMemcpyHostToDevice, g_stream)); B200_CUDA_CHECK(cudaStreamSynchronize(g_stream)); }
+void b200_memcpy_d2h(void * d, const void * s, size_t n) { B200_CUDA_CHECK(cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToHost, g_stream)); B200_CUDA_CHECK(cudaStreamSynchronize(g_stream)); }
+void b200_memset(void * p, int v, size_t n) { B200_CUDA_CHECK(cudaMemsetAsync(p, v, n, g_stream)); }
+void * b200_host_malloc(size_t bytes) {
+    if (getenv("GGML_CUDA_NO_PINNED") != nullptr) return nullptr;            // ggml-cuda.cu:2080
+    void * p = nullptr;
+    if (cudaMallocHost(&p, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }   // caller falls back to pageable (ggml-cuda.cu:2088-2096)
+    return p;
+}
+void b200_host_free(void * p) { if (p) B200_CUDA_CHECK(cudaFreeHost(p)); }
+
+b200_weight * b200_weight_upload(int type, int64_t K, int64_t M, const void * blocks) {
+    b200_weight * w = new b200_weight();
+    wplanes_upload(w->W, type, (int) K, (int) M, blocks, g_stream);
+    return w;
+}
+b200_weight * b200_weight_random(int type, int64_t K, int64_t M, uint64_t seed) {
+    b200_weight * w = new b200_weight();
+    wplanes_alloc_random(w->W, type, (int) K, (int) M, seed, g_stream);
+    return w;
+}
+void b200_weight_free(b200_weight * w) { if (w) { wplanes_free(w->W); delete w; } }
+size_t b200_weight_device_bytes(const b200_weight * w) { return w->W.bytes; }
+void b200_dequantize_rows(const b200_weight * w, const int32_t * rows_dev, int nrows, float * dst, int64_t dst_stride) {
+    launch_dequant_rows(w->W, rows_dev, nrows, dst, dst_stride, g_stream);
+}
+
+b200_actq * b200_actq_alloc(int wtype, int64_t K, int N) {
+    const int at = act_type_for(wtype);
+    B200_ASSERT(at >= 0);
+    b200_actq * a = new b200_actq();
+    a->bytes = actq_bytes(at, (int) K, N);
+    B200_CUDA_CHECK(cudaMalloc(&a->base, a->bytes));
+    actq_bind(a->A, at, (int) K, N, a->base);
+    return a;
+}
+void b200_actq_free(b200_actq * a) { if (a) { B200_CUDA_CHECK(cudaFree(a->base)); delete a; } }
+void b200_quantize_act(const float * x, int64_t x_stride, b200_actq * a) { launch_quantize_act(x, x_stride, a->A, g_stream); }
+void b200_actq_download(const b200_actq * a, int8_t * q, float * d, float * s, int16_t * bs) {
+    const ActQ & A = a->A; const int blk = act_block(A.type);
+    B200_CUDA_CHECK(cudaStreamSynchronize(g_stream));
+    if (q) B200_CUDA_CHECK(cudaMemcpy(q, A.q, (size_t) A.N * A.K, cudaMemcpyDeviceToHost));
+    if (d) B200_CUDA_CHECK(cudaMemcpy(d, A.d, (size_t) A.N * (A.K / blk) * 4, cudaMemcpyDeviceToHost));
+    if (s && A.s) B200_CUDA_CHECK(cudaMemcpy(s, A.s, (size_t) A.N * (A.K / 32) * 4, cudaMemcpyDeviceToHost));
+    if (bs) B200_CUDA_CHECK(cudaMemcpy(bs, A.bs, (size_t) A.N * (A.K / (A.type == T_Q8_K ? 16 : 32)) * 2, cudaMemcpyDeviceToHost));
+}
+
+int b200_mmv_max_n(void) { return 8; }
+
+void b200_mul_mat_vec_q(const b200_weight * w, const b200_actq * a, float * y, int64_t y_stride, int epilogue, const float * r1, const float * r2) {
+    MmvEpilogue e = { epilogue, r1, r2 };
+    launch_mmv(w->W, a->A, y, y_stride, e, g_stream);
+}
+
+// scratch for the one-shot b200_mul_mat (quantised activations, fp16 operand, GEMM workspace); grows on demand
+static void * g_scratch = nullptr; static size_t g_scratch_bytes = 0;
+static void * scratch(size_t bytes) {
+    if (bytes > g_scratch_bytes) {
+        if (g_scratch) { B200_CUDA_CHECK(cudaStreamSynchronize(g_stream)); B200_CUDA_CHECK(cudaFree(g_scratch)); }
+        g_scratch_bytes = round_up(bytes, 1 << 20);
+        B200_CUDA_CHECK(cudaMalloc(&g_scratch, g_scratch_bytes));
+    }
+    return g_scratch;
+}
+
+void b200_mul_mat(const b200_weight * w, const float * x, int64_t x_stride, int N, float * y, int64_t y_stride) {
+    const WPlanes & W = w->W;
+    if (W.type == T_F32 || W.type == T_F16) { launch_mmv_f(W, x, x_stride, N, y, y_stride, g_stream); return; }
+    const int at = act_type_for(W.type);
+    const size_t abytes = actq_bytes(at, W.K, N);
+    if (N <= b200_mmv_max_n()) {
+        ActQ A; actq_bind(A, at, W.K, N, scratch(abytes));
+        launch_quantize_act(x, x_stride, A, g_stream);
+        MmvEpilogue e = { EPI_NONE, nullptr, nullptr };
+        launch_mmv(W, A, y, y_stride, e, g_stream);
+    } else {
+        const size_t hbytes = round_up((size_t) N * W.K * 2, 256), wsb = mmq_gemm_workspace_bytes(W, N);
+        uint8_t * base = (uint8_t *) scratch(abytes + hbytes + wsb);
+        ActQ A; actq_bind(A, at, W.K, N, base);
+        launch_quantize_act(x, x_stride, A, g_stream);
+        __half * xh = (__half *) (base + abytes);
+        launch_actq_to_f16(A, xh, W.K, g_stream);
+        launch_mmq_gemm(W, xh, W.K, N, y, y_stride, 0, base + abytes + hbytes, wsb, g_stream);
+    }
+}
+
+void b200_layernorm(const float * x, int64_t xs, const float * g, const float * b, float * y, int64_t ys, int n, int rows) { launch_layernorm(x, xs, g, b, y, ys, n, rows, g_stream); }
+void b200_gelu(const float * x, float * y, int64_t n) { launch_gelu(x, y, n, g_stream); }
+void b200_add(const float * a, const float * b, float * y, int64_t n) { launch_add(a, b, y, n, g_stream); }
+void b200_rope_neox(float * x, int n_tok, int n_head, int head_dim, int64_t tok_stride, int n_past, int n_ctx_rope, int dyn, float alpha, int freq_base) {
+    launch_rope_neox(x, n_tok, n_head, head_dim, tok_stride, n_past, nullptr, rope_theta_scale_host(head_dim, n_ctx_rope, dyn, alpha, freq_base), g_stream);
+}
+void b200_attention(float * qkv, float * kc, float * vc, float * out, int n_head, int n_head_kv, int head_dim, int n_tok, int n_past, int n_ctx, int n_ctx_rope) {
+    AttnParams p = { n_head, n_head_kv, head_dim, n_tok, n_past, nullptr, n_ctx, (int64_t) (n_head + 2 * n_head_kv) * head_dim };
+    launch_rope_kv_append(qkv, kc, vc, p, rope_theta_scale_host(head_dim, n_ctx_rope ? n_ctx_rope : n_ctx, 1, 2.0f, 0), g_stream);   // libfalcon.cpp:2231-2234
+    launch_attention(qkv, kc, vc, out, (int64_t) n_head * head_dim, p, nullptr, g_stream);
+}
+
+} // extern "C"

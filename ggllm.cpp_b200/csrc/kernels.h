@@ -1,0 +1,63 @@
+// kernels.h -- internal launcher declarations (C++ linkage) shared by the C ABI, the ggml_cuda_* surface and the engine.
+#pragma once
+#include "formats.cuh"
+
+// ---- weights.cu
+size_t wplanes_layout(WPlanes & W, int type, int K, int M);
+void   wplanes_upload(WPlanes & W, int type, int K, int M, const void * host_raw, cudaStream_t stream);
+void   wplanes_from_device_raw(WPlanes & W, int type, int K, int M, const void * dev_raw, cudaStream_t stream);
+void   wplanes_alloc_random(WPlanes & W, int type, int K, int M, uint64_t seed, cudaStream_t stream);
+void   wplanes_free(WPlanes & W);
+void   launch_dequant_rows(const WPlanes & W, const int32_t * rows_dev, int nrows, float * dst, int64_t dst_stride, cudaStream_t stream);
+
+// ---- actquant.cu
+size_t actq_bytes(int act_type, int K, int N);
+void   actq_bind(ActQ & A, int act_type, int K, int N, void * base);          // carve a caller-provided buffer
+void   launch_quantize_act(const float * x, int64_t x_stride, const ActQ & A, cudaStream_t stream);
+void   launch_actq_to_f16(const ActQ & A, __half * dst, int64_t dst_stride, cudaStream_t stream);  // d*q -> fp16 (GEMM operand)
+
+// ---- mmv.cu : y[n][m] = sum_k W[m][k] * xq[n][k], N small (decode), integer dots on quantised activations
+enum { EPI_NONE = 0, EPI_GELU = 1, EPI_ADD2 = 2 };
+struct MmvEpilogue { int kind; const float * r1; const float * r2; };       // ADD2: y = (dot + r1[m]) + r2[m]
+void   launch_mmv(const WPlanes & W, const ActQ & A, float * y, int64_t y_stride, MmvEpilogue epi, cudaStream_t stream);
+void   launch_mmv_f(const WPlanes & W, const float * x, int64_t x_stride, int N, float * y, int64_t y_stride, cudaStream_t stream); // f16/f32 weights
+
+// ---- ops.cu
+void   launch_layernorm(const float * x, int64_t x_stride, const float * g, const float * b, float * y, int64_t y_stride,
+                        int n, int rows, cudaStream_t stream);              // y = norm(x)*g + b ; g,b may be null (plain ggml_norm)
+// [x = (ra + rb) + x, written back] ; A1 = Q(norm(x)*g1+b1) ; A2 = Q(norm(x)*g2+b2) (optional)
+void   launch_layernorm_q(float * x, int64_t x_stride, const float * ra, const float * rb, int64_t r_stride,
+                          const float * g1, const float * b1, const ActQ * A1,
+                          const float * g2, const float * b2, const ActQ * A2, int n, int rows, cudaStream_t stream);
+void   launch_gelu(const float * x, float * y, int64_t n, cudaStream_t stream);
+void   launch_add(const float * a, const float * b, float * y, int64_t n, cudaStream_t stream);
+void   launch_add3(const float * a, const float * b, const float * c, float * y, int64_t n, cudaStream_t stream);   // (a+b)+c
+void   launch_mul_bcast(const float * a, const float * b, float * y, int64_t n, int64_t nb, cudaStream_t stream);  // y[i] = a[i]*b[i%nb]
+void   launch_add_bcast(const float * a, const float * b, float * y, int64_t n, int64_t nb, cudaStream_t stream);
+void   launch_scale(const float * a, float s, float * y, int64_t n, cudaStream_t stream);
+struct RopeParams { int n_past; int head_dim; float theta_scale; };
+float  rope_theta_scale_host(int head_dim, int n_ctx_rope, int dynamic_mode, float ntk_alpha, int freq_base);
+// rotates x[t][h][head_dim] in place (token stride tok_stride, head stride head_dim), position = *n_past_dev + t (or n_past if dev ptr null)
+void   launch_rope_neox(float * x, int n_tok, int n_head, int head_dim, int64_t tok_stride, int n_past, const int * n_past_dev,
+                        float theta_scale, cudaStream_t stream);
+
+// ---- attention.cu
+struct AttnParams {
+    int n_head, n_head_kv, head_dim;
+    int n_tok;                  // new tokens (queries)
+    int n_past;                 // tokens already in the cache (host value; ignored if n_past_dev != null)
+    const int * n_past_dev;     // optional device scalar (CUDA-graph replay)
+    int n_ctx;                  // KV capacity (row count of the cache)
+    int64_t qkv_stride;         // floats between consecutive tokens in the fused QKV buffer
+};
+// fused: rope(Q), rope(K) -> K cache append, V cache append      (libfalcon.cpp:2229-2281)
+void   launch_rope_kv_append(float * qkv, float * k_cache, float * v_cache, const AttnParams & p, float theta_scale, cudaStream_t stream);
+// out[t][h*head_dim + i] = softmax(scale * Q K^T + causal mask) V   (libfalcon.cpp:2285-2366)
+void   launch_attention(const float * qkv, const float * k_cache, const float * v_cache, float * out, int64_t out_stride,
+                        const AttnParams & p, float * scratch, cudaStream_t stream);
+size_t attention_scratch_bytes(const AttnParams & p);
+
+// ---- gemm.cu : Y[n][m] = sum_k W[m][k] * X[n][k], N large (prompt), tcgen05 tensor cores
+void   launch_mmq_gemm(const WPlanes & W, const __half * X, int64_t x_stride, int N, float * Y, int64_t y_stride,
+                       int epi_gelu, void * workspace, size_t workspace_bytes, cudaStream_t stream);
+size_t mmq_gemm_workspace_bytes(const WPlanes & W, int N);

@@ -1,0 +1,198 @@
+// ops.cu -- the non-matmul operators of the Falcon graph, with the CPU oracle's numerics:
+//   LayerNorm  ggml_compute_forward_norm_f32 (ggml.c:10540-10599) + gamma/beta mul/add (libfalcon.cpp:2166-2185)
+//   GELU       fp16-LUT semantics (ggml.c:3461-3484)
+//   RoPE       NeoX mode with dynamic NTK alpha (ggml.c:12875-12898, 12957-12979)
+//   add / mul / scale glue (libfalcon.cpp:2399-2400; ggml-cuda.cu:181-206 add_f32/mul_f32/scale_f32)
+// None of these has a usable kernel in the reference backend (no LayerNorm, no GELU, RoPE mode 0 only).
+#include "kernels.h"
+#include "actquant.cuh"
+#include <cmath>
+
+// ---------------------------------------------------------------------------------------------- block reductions
+template <int NT> __device__ __forceinline__ double block_sum_d(double v, double * sh) {
+    v = warp_sum_d(v);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    __syncthreads();                       // protect sh reuse
+    if (l == 0) sh[w] = v;
+    __syncthreads();
+    double t = (l < NT / 32) ? sh[l] : 0.0;
+    t = warp_sum_d(t);
+    return t;                              // every thread gets the total
+}
+
+// ---------------------------------------------------------------------------------------------- LayerNorm
+// One CTA per row.  Sums in double like the CPU (ggml_float), everything else fp32 with separately rounded
+// multiply and add (no FMA) so the result is bit-identical to the oracle up to double-summation order.
+#define LN_THREADS 512
+__global__ void __launch_bounds__(LN_THREADS) layernorm_kernel(const float * __restrict__ x, int64_t x_stride, const float * __restrict__ g,
+                                                             const float * __restrict__ b, float * __restrict__ y, int64_t y_stride, int n) {
+    __shared__ double sh[LN_THREADS / 32];
+    const float * xr = x + (size_t) blockIdx.x * x_stride;
+    float * yr = y + (size_t) blockIdx.x * y_stride;
+    double s = 0.0;
+    for (int i = threadIdx.x; i < n; i += LN_THREADS) s += (double) xr[i];
+    const float mean = (float) (block_sum_d<LN_THREADS>(s, sh) / n);
+    double s2 = 0.0;
+    for (int i = threadIdx.x; i < n; i += LN_THREADS) { const float v = __fsub_rn(xr[i], mean); s2 += (double) __fmul_rn(v, v); }
+    const float var = (float) (block_sum_d<LN_THREADS>(s2, sh) / n);
+    const float scale = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(var, 1e-5f)));
+    for (int i = threadIdx.x; i < n; i += LN_THREADS) {
+        float v = __fmul_rn(__fsub_rn(xr[i], mean), scale);
+        if (g) v = __fmul_rn(v, g[i]);
+        if (b) v = __fadd_rn(v, b[i]);
+        yr[i] = v;
+    }
+}
+void launch_layernorm(const float * x, int64_t x_stride, const float * g, const float * b, float * y, int64_t y_stride, int n, int rows, cudaStream_t stream) {
+    if (rows <= 0) return;
+    layernorm_kernel<<<rows, LN_THREADS, 0, stream>>>(x, x_stride, g, b, y, y_stride, n);
+    B200_CUDA_CHECK(cudaGetLastError());
+}
+
+// Fused: [residual add] + normalise once + apply up to two (gamma, beta) pairs (Falcon-40B's ln_attn and ln_mlp read
+// the same input, libfalcon.cpp:2166-2188) + write each result directly as quantised activations for the following
+// mat-mul.  With ra/rb given the row is first updated to x = (ra + rb) + x and written back: the two residual adds
+// that close the previous layer (libfalcon.cpp:2399-2400), in that order.
+template <int ATYPE>
+__global__ void __launch_bounds__(LN_THREADS) layernorm_q_kernel(float * __restrict__ x, int64_t x_stride,
+        const float * __restrict__ ra, const float * __restrict__ rb, int64_t r_stride,
+        const float * __restrict__ g1, const float * __restrict__ b1, ActQ A1,
+        const float * __restrict__ g2, const float * __restrict__ b2, ActQ A2, int has2, int n) {
+    __shared__ double sh[LN_THREADS / 32];
+    extern __shared__ float vn[];                                     // the row: raw, then normalised
+    const int row = blockIdx.x;
+    float * xr = x + (size_t) row * x_stride;
+    double s = 0.0;
+    for (int i = threadIdx.x; i < n; i += LN_THREADS) {
+        float v = xr[i];
+        if (ra) { v = __fadd_rn(__fadd_rn(ra[(size_t) row * r_stride + i], rb[(size_t) row * r_stride + i]), v); xr[i] = v; }
+        vn[i] = v;
+        s += (double) v;
+    }
+    const float mean = (float) (block_sum_d<LN_THREADS>(s, sh) / n);
+    double s2 = 0.0;
+    for (int i = threadIdx.x; i < n; i += LN_THREADS) { const float v = __fsub_rn(vn[i], mean); s2 += (double) __fmul_rn(v, v); }
+    const float var = (float) (block_sum_d<LN_THREADS>(s2, sh) / n);
+    const float scale = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(var, 1e-5f)));
+    for (int i = threadIdx.x; i < n; i += LN_THREADS) vn[i] = __fmul_rn(__fsub_rn(vn[i], mean), scale);   // each thread rewrites only its own entries
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    // chunks of 8 values; a warp always works on 32 consecutive chunks = one 256-block (or eight 32-blocks)
+    for (int c0 = (threadIdx.x >> 5) * 32; c0 < n / 8; c0 += LN_THREADS) {
+        const int c = c0 + lane;
+        if (c < n / 8) {         // n % 256 == 0 for Q8_K, n % 32 == 0 otherwise: blocks never straddle the guard
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) v[j] = __fadd_rn(__fmul_rn(vn[c * 8 + j], g1[c * 8 + j]), b1[c * 8 + j]);
+            quantize_chunk8<ATYPE>(v, lane, A1, row, c * 8);
+            if (has2) {
+#pragma unroll
+                for (int j = 0; j < 8; j++) v[j] = __fadd_rn(__fmul_rn(vn[c * 8 + j], g2[c * 8 + j]), b2[c * 8 + j]);
+                quantize_chunk8<ATYPE>(v, lane, A2, row, c * 8);
+            }
+        }
+    }
+}
+void launch_layernorm_q(float * x, int64_t x_stride, const float * ra, const float * rb, int64_t r_stride,
+                        const float * g1, const float * b1, const ActQ * A1,
+                        const float * g2, const float * b2, const ActQ * A2, int n, int rows, cudaStream_t stream) {
+    if (rows <= 0) return;
+    const ActQ a2 = A2 ? *A2 : *A1;
+    B200_ASSERT(!A2 || A2->type == A1->type);
+    const size_t smem = (size_t) n * 4;
+#define LNQ(T) do { static bool set = false; if (!set) { B200_CUDA_CHECK(cudaFuncSetAttribute(layernorm_q_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); set = true; } \
+        layernorm_q_kernel<T><<<rows, LN_THREADS, smem, stream>>>(x, x_stride, ra, rb, r_stride, g1, b1, *A1, g2, b2, a2, A2 != nullptr, n); } while (0)
+    switch (A1->type) {
+        case T_Q8_0: LNQ(T_Q8_0); break;
+        case T_Q8_1: LNQ(T_Q8_1); break;
+        case T_Q8_K: LNQ(T_Q8_K); break;
+        default: B200_ASSERT(!"layernorm_q: bad activation type");
+    }
+#undef LNQ
+    B200_CUDA_CHECK(cudaGetLastError());
+}
+
+// ---------------------------------------------------------------------------------------------- elementwise
+__device__ __forceinline__ float gelu_ref(float v) {      // table_gelu_f16[f16(v)] (ggml.c:3476-3484, table 4281-4290)
+    const float f = __half2float(__float2half_rn(v));
+    const float gl = 0.5f * f * (1.0f + tanhf(0.79788456080286535587989211986876f * f * (1.0f + 0.044715f * f * f)));
+    return __half2float(__float2half_rn(gl));
+}
+__global__ void gelu_kernel(const float * __restrict__ x, float * __restrict__ y, int64_t n) {
+    for (int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t) gridDim.x * blockDim.x) y[i] = gelu_ref(x[i]);
+}
+__global__ void add_kernel(const float * __restrict__ a, const float * __restrict__ b, float * __restrict__ y, int64_t n) {
+    for (int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t) gridDim.x * blockDim.x) y[i] = __fadd_rn(a[i], b[i]);
+}
+__global__ void add3_kernel(const float * __restrict__ a, const float * __restrict__ b, const float * __restrict__ c, float * __restrict__ y, int64_t n) {
+    for (int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t) gridDim.x * blockDim.x) y[i] = __fadd_rn(__fadd_rn(a[i], b[i]), c[i]);
+}
+__global__ void mul_bcast_kernel(const float * __restrict__ a, const float * __restrict__ b, float * __restrict__ y, int64_t n, int64_t nb) {
+    for (int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t) gridDim.x * blockDim.x) y[i] = __fmul_rn(a[i], b[i % nb]);
+}
+__global__ void add_bcast_kernel(const float * __restrict__ a, const float * __restrict__ b, float * __restrict__ y, int64_t n, int64_t nb) {
+    for (int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t) gridDim.x * blockDim.x) y[i] = __fadd_rn(a[i], b[i % nb]);
+}
+__global__ void scale_kernel(const float * __restrict__ a, float s, float * __restrict__ y, int64_t n) {
+    for (int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t) gridDim.x * blockDim.x) y[i] = __fmul_rn(a[i], s);
+}
+static unsigned ew_grid(int64_t n) { int64_t g = (n + 255) / 256; return (unsigned) (g < 1 ? 1 : (g > 148 * 16 ? 148 * 16 : g)); }
+void launch_gelu(const float * x, float * y, int64_t n, cudaStream_t s) { gelu_kernel<<<ew_grid(n), 256, 0, s>>>(x, y, n); B200_CUDA_CHECK(cudaGetLastError()); }
+void launch_add(const float * a, const float * b, float * y, int64_t n, cudaStream_t s) { add_kernel<<<ew_grid(n), 256, 0, s>>>(a, b, y, n); B200_CUDA_CHECK(cudaGetLastError()); }
+void launch_add3(const float * a, const float * b, const float * c, float * y, int64_t n, cudaStream_t s) { add3_kernel<<<ew_grid(n), 256, 0, s>>>(a, b, c, y, n); B200_CUDA_CHECK(cudaGetLastError()); }
+void launch_mul_bcast(const float * a, const float * b, float * y, int64_t n, int64_t nb, cudaStream_t s) { mul_bcast_kernel<<<ew_grid(n), 256, 0, s>>>(a, b, y, n, nb); B200_CUDA_CHECK(cudaGetLastError()); }
+void launch_add_bcast(const float * a, const float * b, float * y, int64_t n, int64_t nb, cudaStream_t s) { add_bcast_kernel<<<ew_grid(n), 256, 0, s>>>(a, b, y, n, nb); B200_CUDA_CHECK(cudaGetLastError()); }
+void launch_scale(const float * a, float sc, float * y, int64_t n, cudaStream_t s) { scale_kernel<<<ew_grid(n), 256, 0, s>>>(a, sc, y, n); B200_CUDA_CHECK(cudaGetLastError()); }
+
+// ---------------------------------------------------------------------------------------------- RoPE
+// theta_scale is computed on the host exactly as the CPU does (powf in fp32, ggml.c:12875-12898) and passed in.
+float rope_theta_scale_host(int head_dim, int n_ctx_rope, int dynamic_mode, float ntk_alpha, int freq_base) {
+    const float fb = (float) (freq_base ? freq_base : 10000);
+    float alpha = 1.0f;
+    if (dynamic_mode) {
+        if (n_ctx_rope >= 2048) alpha = powf(((n_ctx_rope / 2048) - 1) * ntk_alpha + 1, head_dim / (head_dim - 2.0));
+    } else if (ntk_alpha != 0.0f) alpha = powf(ntk_alpha, head_dim / (head_dim - 2.0));
+    return powf(alpha * fb, -2.0f / head_dim);
+}
+// pair i of a head at position p: theta = p * theta_scale^i built by repeated fp32 multiplication, as the CPU loop does
+__device__ __forceinline__ void rope_pair(float * v, int half, int i, int p, float theta_scale) {
+    float theta = (float) p;
+    for (int k = 0; k < i; k++) theta = __fmul_rn(theta, theta_scale);
+    const float c = cosf(theta), s = sinf(theta);
+    const float x0 = v[i], x1 = v[i + half];
+    v[i] = __fsub_rn(__fmul_rn(x0, c), __fmul_rn(x1, s));
+    v[i + half] = __fadd_rn(__fmul_rn(x0, s), __fmul_rn(x1, c));
+}
+__global__ void rope_neox_kernel(float * __restrict__ x, int n_head, int head_dim, int64_t tok_stride, int n_past, const int * __restrict__ n_past_dev, float theta_scale) {
+    const int t = blockIdx.y, h = blockIdx.x, i = threadIdx.x;
+    if (h >= n_head || i >= head_dim / 2) return;
+    const int p = (n_past_dev ? *n_past_dev : n_past) + t;
+    rope_pair(x + (size_t) t * tok_stride + (size_t) h * head_dim, head_dim / 2, i, p, theta_scale);
+}
+void launch_rope_neox(float * x, int n_tok, int n_head, int head_dim, int64_t tok_stride, int n_past, const int * n_past_dev, float theta_scale, cudaStream_t stream) {
+    if (n_tok <= 0) return;
+    dim3 grid((unsigned) n_head, (unsigned) n_tok);
+    rope_neox_kernel<<<grid, head_dim / 2, 0, stream>>>(x, n_head, head_dim, tok_stride, n_past, n_past_dev, theta_scale);
+    B200_CUDA_CHECK(cudaGetLastError());
+}
+
+// fused RoPE(Q) + RoPE(K) + K append + V append (libfalcon.cpp:2229-2281): one CTA per (token, head slot)
+__global__ void rope_kv_append_kernel(float * __restrict__ qkv, float * __restrict__ kc, float * __restrict__ vc, AttnParams p, float theta_scale) {
+    const int t = blockIdx.y, slot = blockIdx.x, i = threadIdx.x, D = p.head_dim, half = D / 2;
+    const int n_past = p.n_past_dev ? *p.n_past_dev : p.n_past;
+    const int pos = n_past + t;
+    float * v = qkv + (size_t) t * p.qkv_stride + (size_t) slot * D;             // slots: Q heads | K heads | V heads
+    if (slot < p.n_head + p.n_head_kv) rope_pair(v, half, i, pos, theta_scale);
+    if (slot >= p.n_head) {
+        const bool is_k = slot < p.n_head + p.n_head_kv;
+        const int kvh = slot - p.n_head - (is_k ? 0 : p.n_head_kv);
+        float * dst = (is_k ? kc : vc) + ((size_t) pos * p.n_head_kv + kvh) * D;
+        dst[i] = v[i]; dst[i + half] = v[i + half];
+    }
+}
+void launch_rope_kv_append(float * qkv, float * k_cache, float * v_cache, const AttnParams & p, float theta_scale, cudaStream_t stream) {
+    if (p.n_tok <= 0) return;
+    dim3 grid((unsigned) (p.n_head + 2 * p.n_head_kv), (unsigned) p.n_tok);
+    rope_kv_append_kernel<<<grid, p.head_dim / 2, 0, stream>>>(qkv, k_cache, v_cache, p, theta_scale);
+    B200_CUDA_CHECK(cudaGetLastError());
+}

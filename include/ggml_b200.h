@@ -1,0 +1,160 @@
+/*
+ * ggml_b200.h -- C ABI of libggml_b200.so, the B200 (sm_100a) quantized-inference backend for ggllm.cpp.
+ *
+ * Plain C: pointers, sizes and ggml type ids (enum ggml_type, ggml.h:241-262) only.  No torch / C++ types.
+ * Pointers named *_dev are CUDA device pointers on the current device; everything else is host memory.
+ * Errors follow the reference backend's convention (ggml-cuda.cu:22-51, ggml.h:204-210): CUDA failures print
+ * to stderr and exit(1), contract violations abort(); there are no error codes to check.
+ * There is NO CPU fallback: every entry point needs a CUDA device.
+ *
+ * Three layers are exported:
+ *   1. b200_*            kernel-level operators (this file, part A): what ggml_cuda_op_* do for one graph node
+ *                        (ggml-cuda.cu:2153-2518) but device-resident and with the CPU oracle's numerics.
+ *   2. b200_falcon_*     the Falcon eval path (part B): loader upload + layer-range partition + falcon_eval,
+ *                        i.e. the "rewired" libfalcon offload (libfalcon.cpp:1552-1959, 2011-2588, 4566).
+ *   3. ggml_cuda_*       the reference's own operator surface (ggml-cuda.h:31-60), declared in
+ *                        ggml_b200_cuda_surface.h, so that ggml.c / libfalcon.cpp built with -DGGML_USE_CUBLAS
+ *                        link against this library unchanged.
+ */
+#ifndef GGML_B200_H
+#define GGML_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ========================================= part A: kernel-level operators ================================= */
+
+/* Replaces ggml_init_cublas (ggml-cuda.cu:1982-2041).  Selects `device`, creates the backend stream.
+ * Returns the number of SMs.  Idempotent per device. */
+int    b200_init(int device);
+int    b200_device_count(void);
+/* Run all subsequent b200_* work on this cudaStream_t (NULL = the backend's own stream). */
+void   b200_set_stream(void * cuda_stream);
+void   b200_synchronize(void);
+
+/* CUDA-event timing on a stream (NULL = the backend stream): what bench.py times kernels with */
+void * b200_event_create(void);
+void   b200_event_destroy(void * ev);
+void   b200_event_record(void * ev, void * cuda_stream);
+void   b200_event_synchronize(void * ev);
+float  b200_event_elapsed_ms(void * ev_start, void * ev_stop);
+void   b200_stream_synchronize(void * cuda_stream);
+
+/* Raw device memory helpers so that C / ctypes callers can stage buffers without another CUDA binding. */
+void * b200_malloc(size_t bytes);
+void   b200_free(void * p_dev);
+void   b200_memcpy_h2d(void * dst_dev, const void * src, size_t bytes);
+void   b200_memcpy_d2h(void * dst, const void * src_dev, size_t bytes);
+void   b200_memset(void * p_dev, int value, size_t bytes);
+/* pinned host memory: ggml_cuda_host_malloc / ggml_cuda_host_free (ggml-cuda.cu:2079-2103); may return NULL */
+void * b200_host_malloc(size_t bytes);
+void   b200_host_free(void * p);
+
+/* ---- weights.  Replaces ggml_cuda_transform_tensor (ggml-cuda.cu:3030-3073): `blocks` is the tensor's raw
+ * data exactly as stored in a GGML/GGCC file: M rows of K/blk blocks (block_q4_0 .. block_q6_K, or f16/f32 rows).
+ * The device copy is re-laid out in planes (DESIGN.md "HBM layout"); the caller may free `blocks` on return. */
+typedef struct b200_weight b200_weight;
+b200_weight * b200_weight_upload(int ggml_type, int64_t K, int64_t M, const void * blocks);
+/* well-formed pseudo-random blocks generated on the device (throughput runs on 40B/180B-sized synthetic models) */
+b200_weight * b200_weight_random(int ggml_type, int64_t K, int64_t M, uint64_t seed);
+void          b200_weight_free(b200_weight * w);      /* ggml_cuda_free_data, ggml-cuda.cu:3075-3092 */
+size_t        b200_weight_device_bytes(const b200_weight * w);
+/* dst[r][0..K) = dequantised row rows[r] (rows_dev == NULL: rows 0..nrows-1).  Bit-exact with
+ * dequantize_row_q* (ggml.c:1509-1619, k_quants.c:344-877); this is ggml_get_rows (ggml.c:11975-12002). */
+void          b200_dequantize_rows(const b200_weight * w, const int32_t * rows_dev, int nrows, float * dst_dev, int64_t dst_stride);
+
+/* ---- quantised activations: the CPU mat-mul's INIT pass (ggml.c:11462-11476): rows quantised to the weight
+ * type's vec_dot_type (Q8_0 / Q8_1 / Q8_K).  Codes and scales are bit-exact with the CPU on an x86 host. */
+typedef struct b200_actq b200_actq;
+b200_actq * b200_actq_alloc(int weight_ggml_type, int64_t K, int N);
+void        b200_actq_free(b200_actq * a);
+void        b200_quantize_act(const float * x_dev, int64_t x_stride, b200_actq * a);
+/* test hook: copy out codes q[N*K], scales d[N*K/blk], Q8_1 sums s[N*K/32] (or NULL), block sums bs (or NULL) */
+void        b200_actq_download(const b200_actq * a, int8_t * q, float * d, float * s, int16_t * bs);
+
+/* ---- y[n][m] = sum_k W[m][k] x[n][k].  Replaces ggml_cuda_mul_mat (ggml-cuda.cu:2931-2951):
+ * N == 1..b200_mmv_max_n(): fused dequantise + integer-dot mat-vec (replaces dequantize_mul_mat_vec*,
+ *                            ggml-cuda.cu:475-845, 1121-1171)
+ * larger N               : tcgen05 tensor-core GEMM with fused dequantisation (replaces to_fp16_cuda +
+ *                            float_to_half + cublasGemmEx, ggml-cuda.cu:2353-2403)
+ * x/y are fp32 device buffers with row strides in floats. */
+void   b200_mul_mat(const b200_weight * w, const float * x_dev, int64_t x_stride, int N, float * y_dev, int64_t y_stride);
+/* the two halves separately; epilogue: 0 none, 1 GELU (fp16-LUT semantics), 2 y = (dot + r1) + r2 */
+void   b200_mul_mat_vec_q(const b200_weight * w, const b200_actq * a, float * y_dev, int64_t y_stride,
+                          int epilogue, const float * r1_dev, const float * r2_dev);
+int    b200_mmv_max_n(void);
+
+/* ---- the other operators of the Falcon graph, CPU-oracle numerics */
+/* y = norm(x) * g + b per row of n values (g, b may be NULL = plain ggml_norm, ggml.c:10540-10599) */
+void   b200_layernorm(const float * x_dev, int64_t x_stride, const float * g_dev, const float * b_dev,
+                      float * y_dev, int64_t y_stride, int n, int rows);
+void   b200_gelu(const float * x_dev, float * y_dev, int64_t n);                        /* ggml.c:3461-3484 */
+void   b200_add(const float * a_dev, const float * b_dev, float * y_dev, int64_t n);   /* ggml.c:8312- */
+/* NeoX RoPE (mode 2) with dynamic NTK (ggml.c:12875-12898, 12957-12979) on x[n_tok][n_head][head_dim], in place */
+void   b200_rope_neox(float * x_dev, int n_tok, int n_head, int head_dim, int64_t tok_stride, int n_past,
+                      int n_ctx_rope, int dynamic_mode, float ntk_alpha, int freq_base);
+/* RoPE(Q,K) + KV append + causal multi-query attention for one layer (libfalcon.cpp:2229-2366).
+ * qkv_dev: [n_tok][(n_head + 2 n_head_kv) * head_dim] (rotated in place like ggml_rope_inplace);
+ * k/v cache: [n_ctx][n_head_kv][head_dim] f32; out: [n_tok][n_head * head_dim]. */
+void   b200_attention(float * qkv_dev, float * k_cache_dev, float * v_cache_dev, float * out_dev,
+                      int n_head, int n_head_kv, int head_dim, int n_tok, int n_past, int n_ctx, int n_ctx_rope);
+
+/* ========================================= part B: Falcon eval path ====================================== */
+
+typedef struct b200_falcon b200_falcon;
+
+typedef struct {
+    int32_t n_vocab, n_embd, n_head, n_head_kv, n_layer;
+    int32_t falcon_type;      /* 7 | 40: selects the single- or dual-LayerNorm layer (libfalcon.cpp:1578-1593, 2177) */
+    int32_t n_ctx;            /* KV capacity (falcon_context_params.n_ctx, libfalcon.h:91) */
+    int32_t n_batch;          /* largest n_tokens of one eval (libfalcon.h:92) */
+    /* layer-range pipeline (replaces tensor_split / n_gpu_layers, libfalcon.h:93-97): this process owns layers
+     * [layer_first, layer_last) of the model; rank/world describe its place in the NCCL pipeline. */
+    int32_t layer_first, layer_last;
+    int32_t rank, world;
+} b200_falcon_params;
+
+/* Create the device-resident model shell (KV cache, activation arena, CUDA graphs).  Weights are attached
+ * afterwards, tensor by tensor, under the reference's GGCC tensor names (libfalcon.cpp:1764-1861), e.g.
+ * "transformer.h.3.mlp.dense_h_to_4h.weight".  Tensors of layers outside [layer_first, layer_last) are ignored. */
+b200_falcon * b200_falcon_create(const b200_falcon_params * params);
+void          b200_falcon_set_tensor(b200_falcon * f, const char * name, int ggml_type, int n_dims,
+                                     const int64_t * ne, const void * data);
+/* random-init tensor of the named shape generated on the device (synthetic throughput models) */
+void          b200_falcon_set_tensor_random(b200_falcon * f, const char * name, int ggml_type, uint64_t seed);
+/* load every tensor of a GGCC v10 file (format: libfalcon.cpp:770-973).  Returns 0 on success. */
+int           b200_falcon_load_ggcc(b200_falcon * f, const char * path);
+/* hparams of a GGCC file without loading it (fills n_vocab..falcon_type); returns 0 on success */
+int           b200_ggcc_read_hparams(const char * path, b200_falcon_params * out);
+void          b200_falcon_free(b200_falcon * f);
+size_t        b200_falcon_weight_bytes(const b200_falcon * f);   /* algorithmic bytes of the resident quantised matrices */
+
+/* NCCL pipeline plumbing (world > 1): rank 0 creates the id, every rank passes the same 128 bytes. */
+void          b200_nccl_unique_id(void * id128);
+void          b200_falcon_init_pipeline(b200_falcon * f, const void * id128);
+
+/* falcon_eval (libfalcon.cpp:4566): n_tokens token ids at position n_past.  Host buffers in and out:
+ * token ids H2D and logits D2H are part of the call.  logits: n_vocab floats of the last token, or
+ * n_tokens * n_vocab if all_logits (falcon_context_params.logits_all).  n_ctx_rope = the rope's 4th parameter
+ * (n_max_real_ctx ? that : n_ctx, libfalcon.cpp:2229-2230); 0 = use n_ctx.
+ * In a pipeline every rank calls it; only the last rank's `logits` are written.  Returns 0 on success. */
+int           b200_falcon_eval(b200_falcon * f, const int32_t * tokens, int n_tokens, int n_past, int n_ctx_rope,
+                               float * logits, int all_logits);
+/* device-resident decode step for throughput measurement: token id already on the device, logits stay on the
+ * device (b200_falcon_logits_dev).  Same kernels/graph as b200_falcon_eval minus the two PCIe copies. */
+void          b200_falcon_decode_dev(b200_falcon * f, const int32_t * token_dev, int n_past, int n_ctx_rope);
+const float * b200_falcon_logits_dev(const b200_falcon * f);
+/* the cudaStream_t the eval path runs on (for event timing) */
+void *        b200_falcon_stream(b200_falcon * f);
+/* number of kernel launches (graph nodes) issued by the most recent eval on this rank */
+int           b200_falcon_last_launches(const b200_falcon * f);
+/* CUDA-event time (ms) of the most recent eval's device work on this rank */
+float         b200_falcon_last_ms(const b200_falcon * f);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GGML_B200_H */

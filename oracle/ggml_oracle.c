@@ -917,6 +917,15 @@ static const float *as_f32(const orc_tensor *t) { return (const float *)t->data;
 
 int orc_falcon_eval(orc_model *m, const int32_t *tokens, int N, int n_past, int n_ctx_rope,
                     float *logits, int all_logits, int nthreads) {
+    return orc_falcon_eval_range(m, tokens, N, n_past, n_ctx_rope, logits, all_logits, nthreads, 0, m->n_layer, NULL, NULL);
+}
+
+/* The same eval restricted to layers [layer_first, layer_last): the unit of the layer-range pipeline.
+ * layer_first > 0: the residual stream [N][n_embd] comes from resid_in instead of the embedding lookup;
+ * layer_last < n_layer: no final norm / lm_head, the residual stream is written to resid_out instead. */
+int orc_falcon_eval_range(orc_model *m, const int32_t *tokens, int N, int n_past, int n_ctx_rope,
+                          float *logits, int all_logits, int nthreads, int layer_first, int layer_last,
+                          const float *resid_in, float *resid_out) {
     const int E = m->n_embd, H = m->n_head, HKV = m->n_head_kv, D = E / H, QKV = (H + 2 * HKV) * D, FF = 4 * E;
     const int group = H / HKV, T = n_past + N;
     if (T > m->n_ctx) return -1;
@@ -925,9 +934,10 @@ int orc_falcon_eval(orc_model *m, const int32_t *tokens, int N, int n_past, int 
           *att = (float *)malloc(sizeof(float) * (size_t)N * E), *ao = (float *)malloc(sizeof(float) * (size_t)N * E),
           *up = (float *)malloc(sizeof(float) * (size_t)N * FF), *dn = (float *)malloc(sizeof(float) * (size_t)N * E),
           *sc = (float *)malloc(sizeof(float) * (size_t)T);
-    for (int t = 0; t < N; t++) get_row(&m->tok_embeddings, tokens[t], inp + (size_t)t * E);   /* libfalcon.cpp:2120 */
+    if (layer_first == 0) for (int t = 0; t < N; t++) get_row(&m->tok_embeddings, tokens[t], inp + (size_t)t * E);   /* libfalcon.cpp:2120 */
+    else memcpy(inp, resid_in, sizeof(float) * (size_t)N * E);
     const float kq_scale = 1.0f / sqrtf((float)D);           /* libfalcon.cpp:2313-2317 */
-    for (int il = 0; il < m->n_layer; il++) {
+    for (int il = layer_first; il < layer_last; il++) {
         const orc_layer *L = &m->layers[il];
         for (int t = 0; t < N; t++) {                        /* libfalcon.cpp:2166-2188 */
             orc_layernorm(inp + (size_t)t * E, as_f32(&L->ln_mlp_g), as_f32(&L->ln_mlp_b), xm + (size_t)t * E, E);
@@ -966,8 +976,9 @@ int orc_falcon_eval(orc_model *m, const int32_t *tokens, int N, int n_past, int 
         for (size_t i = 0; i < (size_t)N * E; i++) { float c = dn[i] + ao[i]; inp[i] = c + inp[i]; }   /* :2399-2400 */
     }
     const int first = all_logits ? 0 : N - 1;
-    for (int t = first; t < N; t++) orc_layernorm(inp + (size_t)t * E, as_f32(&m->ln_f_g), as_f32(&m->ln_f_b), xa + (size_t)t * E, E);  /* :2422-2431 */
-    orc_mul_mat(m->lm_head.type, m->lm_head.data, E, m->n_vocab, xa + (size_t)first * E, N - first, logits, nthreads);  /* :2440 */
+    if (layer_last < m->n_layer) memcpy(resid_out, inp, sizeof(float) * (size_t)N * E);
+    else for (int t = first; t < N; t++) orc_layernorm(inp + (size_t)t * E, as_f32(&m->ln_f_g), as_f32(&m->ln_f_b), xa + (size_t)t * E, E);  /* :2422-2431 */
+    if (layer_last >= m->n_layer) orc_mul_mat(m->lm_head.type, m->lm_head.data, E, m->n_vocab, xa + (size_t)first * E, N - first, logits, nthreads);  /* :2440 */
     free(inp); free(xa); free(xm); free(qkv); free(att); free(ao); free(up); free(dn); free(sc);
     return 0;
 }

@@ -97,6 +97,10 @@ typedef struct {
  * (configuration.n_max_real_ctx ? that : n_ctx, libfalcon.cpp:2229-2230).  Returns 0 on success. */
 int orc_falcon_eval(orc_model *m, const int32_t *tokens, int N, int n_past, int n_ctx_rope,
                     float *logits, int all_logits, int nthreads);
+/* layers [layer_first, layer_last) only: residual in (layer_first > 0) / residual out (layer_last < n_layer) */
+int orc_falcon_eval_range(orc_model *m, const int32_t *tokens, int N, int n_past, int n_ctx_rope,
+                          float *logits, int all_logits, int nthreads, int layer_first, int layer_last,
+                          const float *resid_in, float *resid_out);
 
 #ifdef __cplusplus
 }

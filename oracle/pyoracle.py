@@ -74,6 +74,8 @@ class _Orc:
         L.orc_rope_theta_scale.restype = C.c_float
         L.orc_rope_theta_scale.argtypes = [C.c_int, C.c_int, C.c_int, C.c_float, C.c_int]
         L.orc_falcon_eval.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int]
+        L.orc_falcon_eval_range.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int,
+                                            C.c_int, C.c_int, C.c_void_p, C.c_void_p]
 
     def quantize(self, t, x):
         """x: float32 [..., k] -> uint8 [..., row_bytes] (quantize_row_q*_reference, row by row)."""
@@ -222,6 +224,19 @@ class OrcFalcon:
         rc = self.orc.L.orc_falcon_eval(C.byref(self.m), _fp(tokens), n, n_past, n_ctx_rope or self.m.n_ctx, _fp(out), int(all_logits), nthreads)
         assert rc == 0
         return out
+
+    def eval_range(self, tokens, n_past, layer_first, layer_last, resid_in=None, n_ctx_rope=None, all_logits=False, nthreads=8):
+        """one pipeline stage: returns the residual stream [N][n_embd] if layer_last < n_layer, else the logits"""
+        tokens = np.ascontiguousarray(tokens, dtype=np.int32)
+        n = tokens.size
+        is_last = layer_last >= self.m.n_layer
+        out = np.zeros((n if all_logits else 1, self.m.n_vocab), dtype=np.float32)
+        resid = np.zeros((n, self.m.n_embd), dtype=np.float32)
+        rin = np.ascontiguousarray(resid_in, dtype=np.float32) if resid_in is not None else None
+        rc = self.orc.L.orc_falcon_eval_range(C.byref(self.m), _fp(tokens), n, n_past, n_ctx_rope or self.m.n_ctx, _fp(out), int(all_logits),
+                                              nthreads, layer_first, layer_last, _fp(rin) if rin is not None else None, _fp(resid))
+        assert rc == 0
+        return out if is_last else resid
 
 
 # ----------------------------------------------------------------------------------------------- ref

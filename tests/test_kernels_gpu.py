@@ -1,0 +1,219 @@
+"""-m gpu parity tests of the kernel-level C ABI (include/ggml_b200.h part A) against the oracle.
+
+Bars: bit-exact for integer/byte work (block dequantisation, activation codes + scales); mat-vec = exact integer
+block dots, so only fp32 summation order differs from the CPU -> |err| <= 2e-5 * sum_k |w_k x_k| (stated per test);
+float ops (LayerNorm, GELU, RoPE, softmax/attention) within the tolerances written next to each assert.
+"""
+import numpy as np
+import pytest
+import pyoracle as po
+
+pytestmark = pytest.mark.gpu
+
+ALL_TYPES = po.WEIGHT_TYPES
+
+
+def _weights(orc, t, M, K, seed, scale=0.05):
+    rng = np.random.default_rng(seed)
+    w = (scale * rng.standard_normal((M, K))).astype(np.float32)
+    return orc.quantize(t, w)
+
+
+@pytest.mark.parametrize("t", ALL_TYPES + [po.F16, po.F32])
+def test_dequantize_bit_exact(gpu, orc, t):
+    """device planar repack + dequant_elem == dequantize_row_q* bit for bit (ggml.c:1509-1619, k_quants.c:344-877)"""
+    M, K = 37, 1024
+    wq = _weights(orc, t, M, K, seed=t)
+    W = gpu.Weight(t, K, M, wq)
+    got = W.dequantize()
+    want = orc.dequantize(t, wq, K)
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    rows = np.array([5, 0, 36, 5], np.int32)      # ggml_get_rows with repeats
+    assert np.array_equal(W.dequantize(rows).view(np.uint32), want[rows].view(np.uint32))
+
+
+def test_dequantize_unaligned_rows(gpu, orc):
+    """K = 4544 (Falcon-7B): Q4_0 rows are 2556 B, not a multiple of 16 -- the planar layout must still be exact"""
+    M, K = 19, 4544
+    wq = _weights(orc, po.Q4_0, M, K, seed=3)
+    got = gpu.Weight(po.Q4_0, K, M, wq).dequantize()
+    assert np.array_equal(got.view(np.uint32), orc.dequantize(po.Q4_0, wq, K).view(np.uint32))
+
+
+@pytest.mark.parametrize("t", [po.Q4_0, po.Q4_1, po.Q4_K])
+def test_activation_quantization_bit_exact(gpu, orc, t):
+    """codes, scales and block sums == quantize_row_q8_0 (x86 body) / q8_1 / q8_K_reference"""
+    N, K = 5, 2048
+    rng = np.random.default_rng(11)
+    x = rng.standard_normal((N, K)).astype(np.float32) * np.array([1, 10, 0.01, 100, 1], np.float32)[:, None]
+    x[4, :256] = 0.0                      # an all-zero block
+    x[4, 300] = -x[4, 301]                # +/- tie on the block maximum: first one wins
+    xd = gpu.DevBuf(src=x)
+    A = gpu.ActQ(t, K, N)
+    A.quantize(xd.ptr)
+    q, d, s, bs = A.download()
+    ref = orc.quantize_act(t, x)
+    at = po.VEC_DOT_TYPE[t]
+    bb, blk = po.BLOCK_BYTES[at], po.BLOCK_ELEMS[at]
+    r = ref.reshape(N, K // blk, bb)
+    if at == po.Q8_K:
+        assert np.array_equal(d.view(np.uint32), r[:, :, 0:4].copy().view(np.uint32).reshape(N, -1))
+        assert np.array_equal(q, r[:, :, 4:260].copy().view(np.int8).reshape(N, K))
+        rbs = r[:, :, 260:292].copy().view(np.int16).reshape(N, -1)
+        nz = np.repeat(d != 0, 16, axis=1)              # the reference leaves bsums of all-zero blocks unwritten
+        assert np.array_equal(bs[nz], rbs[nz]) and np.all(bs[~nz] == 0)
+    elif at == po.Q8_0:
+        dref = r[:, :, 0:2].copy().view(np.float16).astype(np.float32).reshape(N, -1)
+        assert np.array_equal(d, dref)
+        assert np.array_equal(q, r[:, :, 2:34].copy().view(np.int8).reshape(N, K))
+        assert np.array_equal(bs, q.reshape(N, -1, 32).astype(np.int32).sum(-1).astype(np.int16))
+    else:
+        assert np.array_equal(d.view(np.uint32), r[:, :, 0:4].copy().view(np.uint32).reshape(N, -1))
+        assert np.array_equal(s.view(np.uint32), r[:, :, 4:8].copy().view(np.uint32).reshape(N, -1))
+        assert np.array_equal(q, r[:, :, 8:40].copy().view(np.int8).reshape(N, K))
+
+
+def _mmv_check(gpu, orc, t, M, K, N, seed, epi=0):
+    rng = np.random.default_rng(seed)
+    wq = _weights(orc, t, M, K, seed)
+    x = rng.standard_normal((N, K)).astype(np.float32)
+    W = gpu.Weight(t, K, M, wq)
+    xd, yd = gpu.DevBuf(src=x), gpu.DevBuf(N * M * 4)
+    gpu.lib().b200_mul_mat(W.h, xd.ptr, K, N, yd.ptr, M)
+    got = yd.download(np.float32, (N, M))
+    want = orc.mul_mat(t, wq, K, M, x)
+    # |sum_k w x| error budget: fp32 reassociation of K/32 (or K/256) exactly-computed block terms
+    wd = np.abs(orc.dequantize(t, wq, K))
+    budget = 2e-5 * (wd @ np.abs(x).T).T + 1e-6
+    err = np.abs(got - want)
+    assert np.all(err <= budget), (po.TYPE_NAMES[t], float(err.max()), float(budget[err.argmax() // M, err.argmax() % M]))
+    return got, want
+
+
+@pytest.mark.parametrize("t", ALL_TYPES)
+def test_mat_vec_all_types(gpu, orc, t):
+    _mmv_check(gpu, orc, t, M=301, K=2048, N=1, seed=100 + t)
+
+
+@pytest.mark.parametrize("t,K,M", [(po.Q4_K, 8192, 1024), (po.Q4_0, 4544, 263), (po.Q3_K, 8192, 130), (po.Q6_K, 1024, 65), (po.Q4_K, 32768, 96)])
+def test_mat_vec_model_shapes(gpu, orc, t, K, M):
+    _mmv_check(gpu, orc, t, M=M, K=K, N=1, seed=7)
+
+
+@pytest.mark.parametrize("t", [po.Q4_0, po.Q4_K, po.Q5_1])
+def test_mat_vec_small_batch(gpu, orc, t):
+    _mmv_check(gpu, orc, t, M=200, K=1024, N=5, seed=9)
+
+
+@pytest.mark.parametrize("t", [po.F16, po.F32])
+def test_mat_vec_float_weights(gpu, orc, t):
+    rng = np.random.default_rng(5)
+    M, K, N = 77, 1000 if t == po.F32 else 1024, 2
+    w = (0.05 * rng.standard_normal((M, K))).astype(np.float32)
+    wq = orc.quantize(t, w)
+    x = rng.standard_normal((N, K)).astype(np.float32)
+    W = gpu.Weight(t, K, M, wq)
+    xd, yd = gpu.DevBuf(src=x), gpu.DevBuf(N * M * 4)
+    gpu.lib().b200_mul_mat(W.h, xd.ptr, K, N, yd.ptr, M)
+    got = yd.download(np.float32, (N, M))
+    want = orc.mul_mat(t, wq, K, M, x)
+    assert np.allclose(got, want, rtol=0, atol=2e-5 * np.abs(w).sum(1).max())
+
+
+def test_mat_vec_gelu_and_residual_epilogues(gpu, orc):
+    t, M, K = po.Q4_K, 300, 1024
+    rng = np.random.default_rng(21)
+    wq = _weights(orc, t, M, K, 21, scale=0.2)
+    x = rng.standard_normal((1, K)).astype(np.float32)
+    r1, r2 = rng.standard_normal(M).astype(np.float32), rng.standard_normal(M).astype(np.float32)
+    W = gpu.Weight(t, K, M, wq)
+    xd, yd = gpu.DevBuf(src=x), gpu.DevBuf(M * 4)
+    A = gpu.ActQ(t, K, 1)
+    A.quantize(xd.ptr)
+    base = orc.mul_mat(t, wq, K, M, x)[0]
+    gpu.lib().b200_mul_mat_vec_q(W.h, A.h, yd.ptr, M, 1, None, None)
+    got = yd.download(np.float32, (M,))
+    want = orc.gelu(base)
+    # GELU goes through fp16: allow one fp16 ulp where the fp32 dot differs in its last bits
+    assert np.all(np.abs(got - want) <= np.maximum(np.abs(want) * 2.0 ** -10, 1e-7))
+    assert np.mean(got == want) > 0.98
+    r1d, r2d = gpu.DevBuf(src=r1), gpu.DevBuf(src=r2)
+    gpu.lib().b200_mul_mat_vec_q(W.h, A.h, yd.ptr, M, 2, r1d.ptr, r2d.ptr)
+    got = yd.download(np.float32, (M,))
+    assert np.allclose(got, (base + r1) + r2, rtol=0, atol=1e-5)
+
+
+def test_layernorm(gpu, orc):
+    """double-accumulated LayerNorm (ggml.c:10568-10595): bit-exact except where the parallel double sum rounds differently"""
+    rng = np.random.default_rng(2)
+    rows, n = 6, 8192
+    x = (rng.standard_normal((rows, n)) * 3 + 0.5).astype(np.float32)
+    g = (1 + 0.1 * rng.standard_normal(n)).astype(np.float32)
+    b = (0.01 * rng.standard_normal(n)).astype(np.float32)
+    xd, gd, bd, yd = gpu.DevBuf(src=x), gpu.DevBuf(src=g), gpu.DevBuf(src=b), gpu.DevBuf(rows * n * 4)
+    gpu.lib().b200_layernorm(xd.ptr, n, gd.ptr, bd.ptr, yd.ptr, n, n, rows)
+    got = yd.download(np.float32, (rows, n))
+    want = orc.layernorm(x, g, b)
+    assert np.allclose(got, want, rtol=0, atol=1e-6)           # tolerance: 1 ulp of O(1..8) values
+    assert np.mean(got == want) > 0.99
+    gpu.lib().b200_layernorm(xd.ptr, n, None, None, yd.ptr, n, n, rows)
+    assert np.allclose(yd.download(np.float32, (rows, n)), orc.norm(x), rtol=0, atol=1e-6)
+
+
+def test_gelu(gpu, orc):
+    x = np.linspace(-12, 12, 100001).astype(np.float32)
+    xd, yd = gpu.DevBuf(src=x), gpu.DevBuf(x.nbytes)
+    gpu.lib().b200_gelu(xd.ptr, yd.ptr, x.size)
+    got, want = yd.download(np.float32, x.shape), orc.gelu(x)
+    # fp16-LUT semantics: equal except where device tanhf and glibc tanhf straddle an fp16 rounding boundary (1 fp16 ulp)
+    assert np.all(np.abs(got - want) <= np.maximum(np.abs(want) * 2.0 ** -10, 6e-8))
+    assert np.mean(got == want) > 0.999
+
+
+@pytest.mark.parametrize("n_ctx_rope,n_past", [(64, 0), (2048, 1234), (8192, 8000)])
+def test_rope_neox_ntk(gpu, orc, n_ctx_rope, n_past):
+    rng = np.random.default_rng(4)
+    n_tok, n_head, hd = 3, 9, 64
+    x = rng.standard_normal((n_tok, n_head, hd)).astype(np.float32)
+    xd = gpu.DevBuf(src=x)
+    gpu.lib().b200_rope_neox(xd.ptr, n_tok, n_head, hd, n_head * hd, n_past, n_ctx_rope, 1, 2.0, 0)
+    got = xd.download(np.float32, x.shape)
+    want = orc.rope_neox(x, n_past, n_ctx_rope)
+    # tolerance: device vs glibc cosf/sinf differ by <= 2 ulp on arguments up to n_past radians
+    assert np.allclose(got, want, rtol=0, atol=3e-6 * np.abs(x).max())
+
+
+@pytest.mark.parametrize("n_head,n_head_kv,n_tok,n_past", [(4, 2, 1, 0), (4, 2, 1, 37), (8, 1, 1, 200), (16, 8, 5, 11), (4, 2, 7, 0)])
+def test_attention(gpu, orc, n_head, n_head_kv, n_tok, n_past):
+    """rope + KV append + causal GQA attention vs a numpy restatement built from the oracle's rope and softmax"""
+    rng = np.random.default_rng(6)
+    hd, n_ctx = 64, 256
+    QKV = (n_head + 2 * n_head_kv) * hd
+    kc = np.zeros((n_ctx, n_head_kv, hd), np.float32)
+    vc = np.zeros_like(kc)
+    kc[:n_past] = rng.standard_normal((n_past, n_head_kv, hd)).astype(np.float32)
+    vc[:n_past] = rng.standard_normal((n_past, n_head_kv, hd)).astype(np.float32)
+    qkv = rng.standard_normal((n_tok, QKV)).astype(np.float32)
+    qd, kd, vd, od = gpu.DevBuf(src=qkv), gpu.DevBuf(src=kc), gpu.DevBuf(src=vc), gpu.DevBuf(n_tok * n_head * hd * 4)
+    gpu.lib().b200_attention(qd.ptr, kd.ptr, vd.ptr, od.ptr, n_head, n_head_kv, hd, n_tok, n_past, n_ctx, n_ctx)
+    got = od.download(np.float32, (n_tok, n_head, hd))
+    # oracle
+    q3 = qkv.reshape(n_tok, -1, hd)
+    q = orc.rope_neox(q3[:, :n_head], n_past, n_ctx)
+    k = orc.rope_neox(q3[:, n_head:n_head + n_head_kv], n_past, n_ctx)
+    kc[n_past:n_past + n_tok] = k
+    vc[n_past:n_past + n_tok] = q3[:, n_head + n_head_kv:]
+    assert np.allclose(kd.download(np.float32, kc.shape), kc, rtol=0, atol=1e-5)
+    assert np.array_equal(vd.download(np.float32, vc.shape), vc)
+    want = np.zeros_like(got)
+    grp = n_head // n_head_kv
+    for t in range(n_tok):
+        T = n_past + t + 1
+        for h in range(n_head):
+            s = (kc[:T, h // grp] @ q[t, h]).astype(np.float32) * np.float32(0.125)
+            p = orc.soft_max(s[None, :])[0]
+            want[t, h] = p @ vc[:T, h // grp]
+    # tolerance: the exp LUT rounds (s - max) to fp16, so a 1e-6 difference in a score can move one probability
+    # by one fp16 ulp (2^-11 relative); outputs are O(1) averages of V
+    assert np.allclose(got, want, rtol=0, atol=2e-3)
+    assert np.median(np.abs(got - want)) < 2e-6
