@@ -22,7 +22,7 @@ PART_A = ["b200_event_create", "b200_event_destroy", "b200_event_record", "b200_
 PART_B = ["b200_falcon_create", "b200_falcon_set_tensor", "b200_falcon_set_tensor_random", "b200_falcon_load_ggcc",
           "b200_ggcc_read_hparams", "b200_falcon_free", "b200_falcon_weight_bytes", "b200_nccl_unique_id",
           "b200_falcon_init_pipeline", "b200_falcon_eval", "b200_falcon_decode_dev", "b200_falcon_logits_dev",
-          "b200_falcon_last_launches", "b200_falcon_last_ms", "b200_falcon_stream"]
+          "b200_falcon_last_launches", "b200_falcon_last_ms", "b200_falcon_stream", "b200_falcon_profile_matvec"]
 
 
 def build(verbose=False):
@@ -64,7 +64,7 @@ def lib():
             "b200_nccl_unique_id": (None, [vp]), "b200_falcon_init_pipeline": (None, [vp, vp]),
             "b200_falcon_eval": (i32, [vp, vp, i32, i32, i32, vp, i32]), "b200_falcon_decode_dev": (None, [vp, vp, i32, i32]),
             "b200_falcon_logits_dev": (vp, [vp]), "b200_falcon_last_launches": (i32, [vp]), "b200_falcon_last_ms": (f32, [vp]),
-            "b200_falcon_stream": (vp, [vp]),
+            "b200_falcon_stream": (vp, [vp]), "b200_falcon_profile_matvec": (f32, [vp, i32, vp, vp]),
         }
         for name, (res, args) in sig.items():
             fn = getattr(L, name)
@@ -270,6 +270,12 @@ class Falcon:
 
     def last_ms(self):
         return self.L.b200_falcon_last_ms(self.h)
+
+    def profile_matvec(self, reps=3):
+        """-> (total ms, launches, algorithmic bytes) of every resident mat-vec launched back to back"""
+        n, by = C.c_int(0), C.c_size_t(0)
+        ms = self.L.b200_falcon_profile_matvec(self.h, reps, C.byref(n), C.byref(by))
+        return ms, n.value, by.value
 
     def init_pipeline(self, id_bytes):
         buf = (C.c_char * 128).from_buffer_copy(id_bytes)

@@ -467,4 +467,40 @@ int b200_falcon_last_launches(const b200_falcon * f) { return f->launches; }
 float b200_falcon_last_ms(const b200_falcon * f) { return f->last_ms; }
 void * b200_falcon_stream(b200_falcon * f) { return (void *) f->s_main; }
 
+// Times the dominant kernel in isolation on the model's own matrices: every local quantised mat-vec (4 per layer +
+// lm_head) launched back to back on the eval stream, `reps` passes, CUDA events around the whole region.  Each
+// launch reads a different matrix and one pass touches weight_bytes >> L2, so every launch streams cold HBM.
+// Returns the total milliseconds; *n_launches and *bytes describe the region (bytes = algorithmic weight bytes).
+float b200_falcon_profile_matvec(b200_falcon * f, int reps, int * n_launches, size_t * bytes) {
+    B200_ASSERT(f->act_type >= 0);
+    ensure_actq(f);
+    cudaStream_t st = f->s_main;
+    ActQ xe = f->xm, xff = f->xup; xe.N = 1; xff.N = 1;
+    B200_CUDA_CHECK(cudaMemsetAsync(f->inp, 0, (size_t) f->E * 4, st));
+    launch_quantize_act(f->inp, f->E, xe, st);
+    B200_CUDA_CHECK(cudaMemsetAsync(f->up, 0, (size_t) f->FF * 4, st));
+    launch_quantize_act(f->up, f->FF, xff, st);
+    MmvEpilogue e = { EPI_NONE, nullptr, nullptr };
+    int n = 0; size_t b = 0;
+    auto pass = [&](bool count) {
+        for (auto & L : f->layers) {
+            launch_mmv(L.wqkv, xe, f->qkv, f->QKV, e, st); launch_mmv(L.wo, xe, f->ao, f->E, e, st);
+            launch_mmv(L.up, xe, f->up, f->FF, e, st); launch_mmv(L.down, xff, f->dn, f->E, e, st);
+            if (count) { n += 4; b += algorithmic_bytes(L.wqkv.type, L.wqkv.K, L.wqkv.M) + algorithmic_bytes(L.wo.type, L.wo.K, L.wo.M)
+                                    + algorithmic_bytes(L.up.type, L.up.K, L.up.M) + algorithmic_bytes(L.down.type, L.down.K, L.down.M); }
+        }
+        if (f->last && f->lm_head.p[0]) { launch_mmv(f->lm_head, xe, f->logits, f->V, e, st);
+            if (count) { n += 1; b += algorithmic_bytes(f->lm_head.type, f->lm_head.K, f->lm_head.M); } }
+    };
+    pass(false);                                                       // warm-up
+    B200_CUDA_CHECK(cudaEventRecord(f->e_t0, st));
+    for (int r = 0; r < reps; r++) pass(r == 0);
+    B200_CUDA_CHECK(cudaEventRecord(f->e_t1, st));
+    B200_CUDA_CHECK(cudaStreamSynchronize(st));
+    float ms = 0.f; B200_CUDA_CHECK(cudaEventElapsedTime(&ms, f->e_t0, f->e_t1));
+    if (n_launches) *n_launches = n * reps;
+    if (bytes) *bytes = b * (size_t) reps;
+    return ms;
+}
+
 } // extern "C"

@@ -12,7 +12,11 @@
 
 #define B200_MAX_PLANES 4
 
-struct PlaneSpec { int src_off; int bytes; };     // where the plane's bytes live inside one source block
+// where a plane's bytes come from inside one source block.  kind 0: `bytes` copied verbatim from src_off;
+// kind 1 (Q4_K/Q5_K scales): the 12-byte packed 6-bit (scale,min) field at src_off is expanded losslessly into
+// 16 bytes, {sc[2p], sc[2p+1], min[2p], min[2p+1]} for p = 0..3 (get_scale_min_k4, k_quants.c:264-271), so that a
+// lane fetches the four values of its sub-block pair with one 32-bit load and feeds them straight to dp2a.
+struct PlaneSpec { int src_off; int bytes; int kind; };
 struct TypeSpec {
     int blk_elems;      // weights per block (32 legacy, 256 K-quants, 1 for f16/f32)
     int blk_bytes;      // bytes per source block
@@ -32,8 +36,8 @@ static inline TypeSpec type_spec(int t) {
         case T_Q8_0: return {32, 34, 2, {{2, 32}, {0, 2}}};                          // qs | d
         case T_Q2_K: return {256, 84, 3, {{16, 64}, {0, 16}, {80, 4}}};              // qs | scales | d,dmin
         case T_Q3_K: return {256, 110, 4, {{32, 64}, {0, 32}, {96, 12}, {108, 2}}};  // qs | hmask | scales | d
-        case T_Q4_K: return {256, 144, 2, {{16, 128}, {0, 16}}};                     // qs | d,dmin,scales[12]
-        case T_Q5_K: return {256, 176, 3, {{48, 128}, {16, 32}, {0, 16}}};           // qs | qh | d,dmin,scales[12]
+        case T_Q4_K: return {256, 144, 3, {{16, 128}, {4, 16, 1}, {0, 4}}};          // qs | scales+mins (expanded) | d,dmin
+        case T_Q5_K: return {256, 176, 4, {{48, 128}, {16, 32}, {4, 16, 1}, {0, 4}}}; // qs | qh | scales+mins (expanded) | d,dmin
         case T_Q6_K: return {256, 210, 4, {{0, 128}, {128, 64}, {192, 16}, {208, 2}}}; // ql | qh | scales | d
     }
     return {0, 0, 0, {}};
@@ -115,11 +119,12 @@ __device__ inline float dequant_elem(const WPlanes & W, size_t row, int e) {
     }
     const int b = e >> 8, i = e & 255;
     if (t == T_Q4_K || t == T_Q5_K) {
-        const uint8_t * hdr = W.p[t == T_Q4_K ? 1 : 2] + row * W.stride[t == T_Q4_K ? 1 : 2] + b * 16;
-        const float d = f16_bits_to_f32(reinterpret_cast<const uint16_t *>(hdr)[0]);
-        const float dmin = f16_bits_to_f32(reinterpret_cast<const uint16_t *>(hdr)[1]);
+        const int ps = t == T_Q4_K ? 1 : 2;                       // plane of the expanded scales; d,dmin follow in the next plane
+        const uint8_t * sm = W.p[ps] + row * W.stride[ps] + b * 16;
+        const uint16_t * dd = reinterpret_cast<const uint16_t *>(W.p[ps + 1] + row * W.stride[ps + 1] + b * 4);
+        const float d = f16_bits_to_f32(dd[0]), dmin = f16_bits_to_f32(dd[1]);
         const int sub = i >> 5, l = i & 31, pair = sub >> 1;
-        int sc, mn; unpack_sm6(sub, hdr + 4, sc, mn);
+        const int sc = sm[4 * pair + (sub & 1)], mn = sm[4 * pair + 2 + (sub & 1)];
         const uint8_t byte = (W.p[0] + row * W.stride[0])[b * 128 + pair * 32 + l];
         int code = (sub & 1) ? (byte >> 4) : (byte & 0xF);
         if (t == T_Q5_K) code += (((W.p[1] + row * W.stride[1])[b * 32 + l] >> sub) & 1) ? 16 : 0;

@@ -7,15 +7,20 @@
 // differs from the CPU (which itself differs between its scalar and AVX2 bodies).
 //
 // Shape of the kernel (HBM-bound; see DESIGN.md "mmv"):
-//   * persistent grid of min(SMs*k, rows) CTAs; warp w of the grid owns rows w, w+W, ...
-//   * the activation codes (K bytes) are staged once per CTA into shared memory by a 1-D TMA bulk copy
-//     (cp.async.bulk + mbarrier); scales/block sums (tiny) by ordinary loads
-//   * every lane streams 16-byte pieces of the quant plane with ld.global.nc.L1::no_allocate, U pieces in
-//     flight before the first use; consecutive lanes read consecutive 16 B => 512 B per warp-instruction
-//   * lane-local dp4a accumulation, one warp-shuffle reduction per row, lane 0 stores (+ fused epilogue)
+//   * one persistent CTA of 16 warps per SM; CTA c owns a contiguous, balanced range of rows, its warps pull rows
+//     from a shared-memory counter (results do not depend on which warp computes a row: deterministic)
+//   * weights never touch registers on their way in: lane 0 of every warp keeps a ring of S "units" (CH blocks of
+//     a row, ~3-5 KB over all planes) in flight with 1-D TMA bulk copies (cp.async.bulk + mbarrier complete_tx);
+//     16 warps x S stages = 100-200 KB of HBM reads in flight per SM
+//   * the activation codes (K bytes) are staged once per CTA by another TMA bulk copy; scales / block sums (tiny)
+//     by ordinary loads
+//   * a lane reads 16-byte pieces of the unit from shared memory (consecutive lanes -> consecutive 16 B, conflict
+//     free), dp4a against the activation codes, one fp32 multiply-accumulate per (sub-)block
+//   * one warp-shuffle reduction per row, lane 0 stores (+ fused GELU / residual epilogue)
 #include "kernels.h"
 
-#define MMV_THREADS 256
+#define MMV_THREADS 512
+__host__ __device__ constexpr size_t round_up16(size_t v) { return (v + 15) / 16 * 16; }
 
 struct XS {                 // activation row in shared memory
     const int8_t * q; const float * d; const float * s; const int16_t * bs;
@@ -29,52 +34,55 @@ __device__ __forceinline__ uint4 lds16(const int8_t * p) { return *reinterpret_c
 template <int TYPE> struct MV;
 
 // ---------------------------------------------------------------- Q4_K  (k_quants.c:1999-2055)
+// sum_j sc_j * (q4 . q8)_j and sum_j min_j * bsums_j as two dp2a over the expanded scale plane {sc0, sc1, m0, m1}
+__device__ __forceinline__ int dp2a_lo_us(int pair16, uint32_t bytes, int c) { int d; asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(pair16), "r"(bytes), "r"(c)); return d; }
+__device__ __forceinline__ int dp2a_hi_us(int pair16, uint32_t bytes, int c) { int d; asm("dp2a.hi.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(pair16), "r"(bytes), "r"(c)); return d; }
+__device__ __forceinline__ int pack16(int lo, int hi) { return (lo & 0xffff) | (hi << 16); }
+
 template <> struct MV<T_Q4_K> {
     static constexpr int PPB = 8;                // 16-byte pieces per 256-weight block
-    struct Regs { uint4 q, h; };
-    __device__ static Regs load(const WPlanes & W, size_t row, int b, int pc) {
+    static constexpr int CH = 32, NPL = 3;       // blocks per unit, planes
+    __host__ __device__ static constexpr int pb(int p) { return p == 0 ? 128 : p == 1 ? 16 : p == 2 ? 4 : 0; }
+    static constexpr int O1 = CH * 128, O2 = O1 + CH * 16;
+    struct Regs { uint4 q; uint32_t sm, dd; };
+    __device__ static Regs load(const uint8_t * sb, int b, int pc) {
         Regs r;
-        r.q = ldg_stream_v4(W.p[0] + row * W.stride[0] + (size_t) b * 128 + pc * 16);
-        r.h = ldg_v4(W.p[1] + row * W.stride[1] + (size_t) b * 16);
+        r.q = *reinterpret_cast<const uint4 *>(sb + b * 128 + pc * 16);
+        r.sm = *reinterpret_cast<const uint32_t *>(sb + O1 + b * 16 + (pc >> 1) * 4);
+        r.dd = *reinterpret_cast<const uint32_t *>(sb + O2 + b * 4);
         return r;
     }
-    __device__ static void scales(const uint4 h, int p, int & sc0, int & m0, int & sc1, int & m1) {
-        // 6-bit (scale,min) pairs 2p and 2p+1 of the 12-byte field held in h.y h.z h.w (get_scale_min_k4)
-        if (p < 2) {
-            const int sh = 16 * p;
-            sc0 = (h.y >> sh) & 63; sc1 = (h.y >> (sh + 8)) & 63;
-            m0 = (h.z >> sh) & 63;  m1 = (h.z >> (sh + 8)) & 63;
-        } else {
-            const int sh = 16 * (p - 2);
-            const uint32_t a = h.w >> sh, lo = h.y >> sh, hi = h.z >> sh;
-            sc0 = (a & 0xF) | (((lo >> 6) & 3) << 4);        sc1 = ((a >> 8) & 0xF) | (((lo >> 14) & 3) << 4);
-            m0 = ((a >> 4) & 0xF) | (((hi >> 6) & 3) << 4);  m1 = ((a >> 12) & 0xF) | (((hi >> 14) & 3) << 4);
-        }
+    __device__ static float finish(int il, int ih, uint32_t sm, uint32_t dd, int b, int pc, const XS & x) {
+        const int p = pc >> 1, half = pc & 1;
+        const int isum = dp2a_lo_us(pack16(il, ih), sm, 0);
+        const int msum = dp2a_hi_us(pack16(x.bs[b * 16 + 4 * p + half], x.bs[b * 16 + 4 * p + 2 + half]), sm, 0);
+        const float xd = x.d[b];
+        const float2 dm = __half22float2(*reinterpret_cast<const __half2 *>(&dd));
+        return (dm.x * xd) * (float) isum - (dm.y * xd) * (float) msum;
     }
     __device__ static float dot(const Regs & r, int b, int pc, const XS & x) {
-        const int p = pc >> 1, half = pc & 1;
-        const int e0 = b * 256 + 64 * p + 16 * half;                     // low nibbles: e0.., high nibbles: e0+32..
+        const int e0 = b * 256 + 64 * (pc >> 1) + 16 * (pc & 1);          // low nibbles: e0.., high nibbles: e0+32..
         const uint4 xl = lds16(x.q + e0), xh = lds16(x.q + e0 + 32);
         const int il = dot16_u(r.q.x & 0x0F0F0F0F, r.q.y & 0x0F0F0F0F, r.q.z & 0x0F0F0F0F, r.q.w & 0x0F0F0F0F, xl);
-        const int ih = dot16_u((r.q.x >> 4) & 0x0F0F0F0F, (r.q.y >> 4) & 0x0F0F0F0F, (r.q.z >> 4) & 0x0F0F0F0F, (r.q.w >> 4) & 0x0F0F0F0F, xh);
-        int sc0, m0, sc1, m1; scales(r.h, p, sc0, m0, sc1, m1);
-        const int isum = sc0 * il + sc1 * ih;
-        const int msum = m0 * x.bs[b * 16 + 4 * p + half] + m1 * x.bs[b * 16 + 4 * p + 2 + half];
-        const float xd = x.d[b];
-        const float d = f16_bits_to_f32((uint16_t) (r.h.x & 0xffff)), dmin = f16_bits_to_f32((uint16_t) (r.h.x >> 16));
-        return (d * xd) * (float) isum - (dmin * xd) * (float) msum;
+        // high nibbles stay in place (x16): the dot is an exact multiple of 16
+        const int ih = dot16_u(r.q.x & 0xF0F0F0F0, r.q.y & 0xF0F0F0F0, r.q.z & 0xF0F0F0F0, r.q.w & 0xF0F0F0F0, xh) >> 4;
+        return finish(il, ih, r.sm, r.dd, b, pc, x);
     }
 };
 
 // ---------------------------------------------------------------- Q5_K  (k_quants.c:2340-2400)
 template <> struct MV<T_Q5_K> {
     static constexpr int PPB = 8;
-    struct Regs { uint4 q, qh, h; };
-    __device__ static Regs load(const WPlanes & W, size_t row, int b, int pc) {
+    static constexpr int CH = 16, NPL = 4;
+    __host__ __device__ static constexpr int pb(int p) { return p == 0 ? 128 : p == 1 ? 32 : p == 2 ? 16 : 4; }
+    static constexpr int O1 = CH * 128, O2 = O1 + CH * 32, O3 = O2 + CH * 16;
+    struct Regs { uint4 q, qh; uint32_t sm, dd; };
+    __device__ static Regs load(const uint8_t * sb, int b, int pc) {
         Regs r;
-        r.q = ldg_stream_v4(W.p[0] + row * W.stride[0] + (size_t) b * 128 + pc * 16);
-        r.qh = ldg_v4(W.p[1] + row * W.stride[1] + (size_t) b * 32 + (pc & 1) * 16);
-        r.h = ldg_v4(W.p[2] + row * W.stride[2] + (size_t) b * 16);
+        r.q = *reinterpret_cast<const uint4 *>(sb + b * 128 + pc * 16);
+        r.qh = *reinterpret_cast<const uint4 *>(sb + O1 + b * 32 + (pc & 1) * 16);
+        r.sm = *reinterpret_cast<const uint32_t *>(sb + O2 + b * 16 + (pc >> 1) * 4);
+        r.dd = *reinterpret_cast<const uint32_t *>(sb + O3 + b * 4);
         return r;
     }
     __device__ static float dot(const Regs & r, int b, int pc, const XS & x) {
@@ -88,25 +96,28 @@ template <> struct MV<T_Q5_K> {
         const int ih = dot16_u(HI5(r.q.x, r.qh.x), HI5(r.q.y, r.qh.y), HI5(r.q.z, r.qh.z), HI5(r.q.w, r.qh.w), xh);
 #undef LO5
 #undef HI5
-        int sc0, m0, sc1, m1; MV<T_Q4_K>::scales(r.h, p, sc0, m0, sc1, m1);
-        const int isum = sc0 * il + sc1 * ih;
-        const int msum = m0 * x.bs[b * 16 + 4 * p + half] + m1 * x.bs[b * 16 + 4 * p + 2 + half];
+        // 5-bit codes: |il| can reach 16*31*127 > int16, so the scale products are plain 32-bit multiplies here
+        const int isum = (int) (r.sm & 0xff) * il + (int) ((r.sm >> 8) & 0xff) * ih;
+        const int msum = dp2a_hi_us(pack16(x.bs[b * 16 + 4 * p + half], x.bs[b * 16 + 4 * p + 2 + half]), r.sm, 0);
         const float xd = x.d[b];
-        const float d = f16_bits_to_f32((uint16_t) (r.h.x & 0xffff)), dmin = f16_bits_to_f32((uint16_t) (r.h.x >> 16));
-        return (d * xd) * (float) isum - (dmin * xd) * (float) msum;
+        const float2 dm = __half22float2(*reinterpret_cast<const __half2 *>(&r.dd));
+        return (dm.x * xd) * (float) isum - (dm.y * xd) * (float) msum;
     }
 };
 
 // ---------------------------------------------------------------- Q6_K  (k_quants.c:2748-2789)
 template <> struct MV<T_Q6_K> {
     static constexpr int PPB = 8;
+    static constexpr int CH = 16, NPL = 4;
+    __host__ __device__ static constexpr int pb(int p) { return p == 0 ? 128 : p == 1 ? 64 : p == 2 ? 16 : 2; }
+    static constexpr int O1 = CH * 128, O2 = O1 + CH * 64, O3 = O2 + CH * 16;
     struct Regs { uint4 ql, qh, sc; uint32_t d; };
-    __device__ static Regs load(const WPlanes & W, size_t row, int b, int pc) {
+    __device__ static Regs load(const uint8_t * sb, int b, int pc) {
         Regs r;
-        r.ql = ldg_stream_v4(W.p[0] + row * W.stride[0] + (size_t) b * 128 + pc * 16);            // = n*64 + c*16
-        r.qh = ldg_stream_v4(W.p[1] + row * W.stride[1] + (size_t) b * 64 + (pc >> 2) * 32 + (pc & 1) * 16);
-        r.sc = ldg_v4(W.p[2] + row * W.stride[2] + (size_t) b * 16);
-        r.d = ldg_u16(W.p[3] + row * W.stride[3] + (size_t) b * 2);
+        r.ql = *reinterpret_cast<const uint4 *>(sb + b * 128 + pc * 16);                          // = n*64 + c*16
+        r.qh = *reinterpret_cast<const uint4 *>(sb + O1 + b * 64 + (pc >> 2) * 32 + (pc & 1) * 16);
+        r.sc = *reinterpret_cast<const uint4 *>(sb + O2 + b * 16);
+        r.d = *reinterpret_cast<const uint16_t *>(sb + O3 + b * 2);
         return r;
     }
     __device__ static float dot(const Regs & r, int b, int pc, const XS & x) {
@@ -131,14 +142,17 @@ template <> struct MV<T_Q6_K> {
 // ---------------------------------------------------------------- Q3_K  (k_quants.c:1684-1745)
 template <> struct MV<T_Q3_K> {
     static constexpr int PPB = 4;                // 16 bytes of qs = 64 weights
+    static constexpr int CH = 32, NPL = 4;
+    __host__ __device__ static constexpr int pb(int p) { return p == 0 ? 64 : p == 1 ? 32 : p == 2 ? 12 : 2; }
+    static constexpr int O1 = CH * 64, O2 = O1 + CH * 32, O3 = O2 + CH * 12;
     struct Regs { uint4 q, hm; uint32_t s0, s1, s2, d; };
-    __device__ static Regs load(const WPlanes & W, size_t row, int b, int pc) {
+    __device__ static Regs load(const uint8_t * sb, int b, int pc) {
         Regs r;
-        r.q = ldg_stream_v4(W.p[0] + row * W.stride[0] + (size_t) b * 64 + pc * 16);              // = n*32 + c*16
-        r.hm = ldg_stream_v4(W.p[1] + row * W.stride[1] + (size_t) b * 32 + (pc & 1) * 16);
-        const uint8_t * s = W.p[2] + row * W.stride[2] + (size_t) b * 12;
-        r.s0 = ldg_u32(s); r.s1 = ldg_u32(s + 4); r.s2 = ldg_u32(s + 8);
-        r.d = ldg_u16(W.p[3] + row * W.stride[3] + (size_t) b * 2);
+        r.q = *reinterpret_cast<const uint4 *>(sb + b * 64 + pc * 16);                            // = n*32 + c*16
+        r.hm = *reinterpret_cast<const uint4 *>(sb + O1 + b * 32 + (pc & 1) * 16);
+        const uint32_t * s = reinterpret_cast<const uint32_t *>(sb + O2 + b * 12);
+        r.s0 = s[0]; r.s1 = s[1]; r.s2 = s[2];
+        r.d = *reinterpret_cast<const uint16_t *>(sb + O3 + b * 2);
         return r;
     }
     __device__ static float dot(const Regs & r, int b, int pc, const XS & x) {
@@ -165,12 +179,15 @@ template <> struct MV<T_Q3_K> {
 // ---------------------------------------------------------------- Q2_K  (k_quants.c:1267-1305)
 template <> struct MV<T_Q2_K> {
     static constexpr int PPB = 4;
+    static constexpr int CH = 32, NPL = 3;
+    __host__ __device__ static constexpr int pb(int p) { return p == 0 ? 64 : p == 1 ? 16 : p == 2 ? 4 : 0; }
+    static constexpr int O1 = CH * 64, O2 = O1 + CH * 16;
     struct Regs { uint4 q, sc; uint32_t dm; };
-    __device__ static Regs load(const WPlanes & W, size_t row, int b, int pc) {
+    __device__ static Regs load(const uint8_t * sb, int b, int pc) {
         Regs r;
-        r.q = ldg_stream_v4(W.p[0] + row * W.stride[0] + (size_t) b * 64 + pc * 16);
-        r.sc = ldg_v4(W.p[1] + row * W.stride[1] + (size_t) b * 16);
-        r.dm = ldg_u32(W.p[2] + row * W.stride[2] + (size_t) b * 4);
+        r.q = *reinterpret_cast<const uint4 *>(sb + b * 64 + pc * 16);
+        r.sc = *reinterpret_cast<const uint4 *>(sb + O1 + b * 16);
+        r.dm = *reinterpret_cast<const uint32_t *>(sb + O2 + b * 4);
         return r;
     }
     __device__ static float dot(const Regs & r, int b, int pc, const XS & x) {
@@ -198,11 +215,14 @@ __device__ __forceinline__ uint32_t spread4(uint32_t bits4) { return ((bits4 & 0
 
 template <> struct MV<T_Q4_0> {
     static constexpr int PPB = 1;
+    static constexpr int CH = 256, NPL = 2;
+    __host__ __device__ static constexpr int pb(int p) { return p == 0 ? 16 : p == 1 ? 2 : p == 2 ? 0 : 0; }
+    static constexpr int O1 = CH * 16;
     struct Regs { uint4 q; uint32_t d; };
-    __device__ static Regs load(const WPlanes & W, size_t row, int b, int) {
+    __device__ static Regs load(const uint8_t * sb, int b, int) {
         Regs r;
-        r.q = ldg_stream_v4(W.p[0] + row * W.stride[0] + (size_t) b * 16);
-        r.d = ldg_u16(W.p[1] + row * W.stride[1] + (size_t) b * 2);
+        r.q = *reinterpret_cast<const uint4 *>(sb + b * 16);
+        r.d = *reinterpret_cast<const uint16_t *>(sb + O1 + b * 2);
         return r;
     }
     __device__ static float dot(const Regs & r, int b, int, const XS & x) {
@@ -215,11 +235,14 @@ template <> struct MV<T_Q4_0> {
 };
 template <> struct MV<T_Q4_1> {
     static constexpr int PPB = 1;
+    static constexpr int CH = 256, NPL = 2;
+    __host__ __device__ static constexpr int pb(int p) { return p == 0 ? 16 : p == 1 ? 4 : p == 2 ? 0 : 0; }
+    static constexpr int O1 = CH * 16;
     struct Regs { uint4 q; uint32_t dm; };
-    __device__ static Regs load(const WPlanes & W, size_t row, int b, int) {
+    __device__ static Regs load(const uint8_t * sb, int b, int) {
         Regs r;
-        r.q = ldg_stream_v4(W.p[0] + row * W.stride[0] + (size_t) b * 16);
-        r.dm = ldg_u32(W.p[1] + row * W.stride[1] + (size_t) b * 4);
+        r.q = *reinterpret_cast<const uint4 *>(sb + b * 16);
+        r.dm = *reinterpret_cast<const uint32_t *>(sb + O1 + b * 4);
         return r;
     }
     __device__ static float dot(const Regs & r, int b, int, const XS & x) {
@@ -231,12 +254,15 @@ template <> struct MV<T_Q4_1> {
 };
 template <> struct MV<T_Q5_0> {
     static constexpr int PPB = 1;
+    static constexpr int CH = 128, NPL = 3;
+    __host__ __device__ static constexpr int pb(int p) { return p == 0 ? 16 : p == 1 ? 4 : p == 2 ? 2 : 0; }
+    static constexpr int O1 = CH * 16, O2 = O1 + CH * 4;
     struct Regs { uint4 q; uint32_t qh, d; };
-    __device__ static Regs load(const WPlanes & W, size_t row, int b, int) {
+    __device__ static Regs load(const uint8_t * sb, int b, int) {
         Regs r;
-        r.q = ldg_stream_v4(W.p[0] + row * W.stride[0] + (size_t) b * 16);
-        r.qh = ldg_u32(W.p[1] + row * W.stride[1] + (size_t) b * 4);
-        r.d = ldg_u16(W.p[2] + row * W.stride[2] + (size_t) b * 2);
+        r.q = *reinterpret_cast<const uint4 *>(sb + b * 16);
+        r.qh = *reinterpret_cast<const uint32_t *>(sb + O1 + b * 4);
+        r.d = *reinterpret_cast<const uint16_t *>(sb + O2 + b * 2);
         return r;
     }
     __device__ static int idot(const uint4 q, uint32_t qh, int b, const XS & x) {
@@ -254,12 +280,15 @@ template <> struct MV<T_Q5_0> {
 };
 template <> struct MV<T_Q5_1> {
     static constexpr int PPB = 1;
+    static constexpr int CH = 128, NPL = 3;
+    __host__ __device__ static constexpr int pb(int p) { return p == 0 ? 16 : p == 1 ? 4 : p == 2 ? 4 : 0; }
+    static constexpr int O1 = CH * 16, O2 = O1 + CH * 4;
     struct Regs { uint4 q; uint32_t qh, dm; };
-    __device__ static Regs load(const WPlanes & W, size_t row, int b, int) {
+    __device__ static Regs load(const uint8_t * sb, int b, int) {
         Regs r;
-        r.q = ldg_stream_v4(W.p[0] + row * W.stride[0] + (size_t) b * 16);
-        r.qh = ldg_u32(W.p[1] + row * W.stride[1] + (size_t) b * 4);
-        r.dm = ldg_u32(W.p[2] + row * W.stride[2] + (size_t) b * 4);
+        r.q = *reinterpret_cast<const uint4 *>(sb + b * 16);
+        r.qh = *reinterpret_cast<const uint32_t *>(sb + O1 + b * 4);
+        r.dm = *reinterpret_cast<const uint32_t *>(sb + O2 + b * 4);
         return r;
     }
     __device__ static float dot(const Regs & r, int b, int, const XS & x) {
@@ -269,11 +298,14 @@ template <> struct MV<T_Q5_1> {
 };
 template <> struct MV<T_Q8_0> {
     static constexpr int PPB = 2;                // 16 int8 weights per piece
+    static constexpr int CH = 128, NPL = 2;
+    __host__ __device__ static constexpr int pb(int p) { return p == 0 ? 32 : p == 1 ? 2 : p == 2 ? 0 : 0; }
+    static constexpr int O1 = CH * 32;
     struct Regs { uint4 q; uint32_t d; };
-    __device__ static Regs load(const WPlanes & W, size_t row, int b, int pc) {
+    __device__ static Regs load(const uint8_t * sb, int b, int pc) {
         Regs r;
-        r.q = ldg_stream_v4(W.p[0] + row * W.stride[0] + (size_t) b * 32 + pc * 16);
-        r.d = ldg_u16(W.p[1] + row * W.stride[1] + (size_t) b * 2);
+        r.q = *reinterpret_cast<const uint4 *>(sb + b * 32 + pc * 16);
+        r.d = *reinterpret_cast<const uint16_t *>(sb + O1 + b * 2);
         return r;
     }
     __device__ static float dot(const Regs & r, int b, int pc, const XS & x) {
@@ -291,64 +323,122 @@ __device__ __forceinline__ float gelu_f16lut(float v) {
     return __half2float(__float2half_rn(g));
 }
 
-template <int TYPE, int U>
-__global__ void __launch_bounds__(MMV_THREADS) mmv_kernel(const WPlanes W, const ActQ A, float * __restrict__ y, int64_t y_stride, const MmvEpilogue epi) {
+// ------------------------------------------------------------------------------------------------ the kernel
+// Work unit = CH consecutive blocks of one weight row (about 4-5 KB over all planes).  Every warp owns a ring of
+// `S` unit buffers in shared memory; its lane 0 keeps S units in flight with 1-D TMA bulk copies (one per plane)
+// that complete on the stage's mbarrier.  With 16 warps x 2-3 stages an SM has 100-200 KB of weight bytes in
+// flight without spending a single register on them -- that, not occupancy, is what hides HBM latency here.
+template <int TYPE> struct UnitGeom {
+    static constexpr int NPL = MV<TYPE>::NPL;
+    __host__ __device__ static constexpr int plane_bytes(int p) { return MV<TYPE>::pb(p); }
+    __host__ __device__ static constexpr int off(int p) {            // byte offset of plane p inside a stage
+        int o = 0;
+        for (int q = 0; q < p; q++) o += (MV<TYPE>::CH * MV<TYPE>::pb(q) + 15) / 16 * 16;
+        return o;
+    }
+    static constexpr int META = off(NPL);                        // (row, chunk) of the unit a stage holds
+    static constexpr int STAGE = META + 16;
+};
+
+template <int TYPE>
+__global__ void __launch_bounds__(MMV_THREADS, 1) mmv_kernel(const WPlanes W, const ActQ A, float * __restrict__ y, int64_t y_stride,
+                                                             const MmvEpilogue epi, const int S) {
     using T = MV<TYPE>;
-    extern __shared__ __align__(16) uint8_t smem[];
+    using G = UnitGeom<TYPE>;
+    constexpr int WARPS = MMV_THREADS / 32;
+    extern __shared__ __align__(128) uint8_t smem[];
     const int n = blockIdx.y;                                   // activation row (column of Y)
     const int K = W.K, ablk = TYPE >= T_Q2_K ? 256 : 32;
     const int nd = K / ablk, nbs = TYPE >= T_Q2_K ? K / 16 : K / 32;
-    uint64_t * bar = reinterpret_cast<uint64_t *>(smem);
-    int8_t * xq = reinterpret_cast<int8_t *>(smem + 16);
-    float * xd = reinterpret_cast<float *>(smem + 16 + K);
-    float * xs = xd + nd;                                       // Q8_1 only (nd entries), otherwise unused
+    // layout: [x barrier + next-row counter | stage barriers (WARPS*S) | x codes | x scales | stages]
+    uint64_t * xbar = reinterpret_cast<uint64_t *>(smem);
+    int * next_row = reinterpret_cast<int *>(smem + 8);
+    uint64_t * bars = reinterpret_cast<uint64_t *>(smem + 16);
+    int8_t * xq = reinterpret_cast<int8_t *>(smem + 16 + round_up16(WARPS * S * 8));
+    float * xd = reinterpret_cast<float *>(xq + K);
+    float * xs = xd + nd;                                       // Q8_1 only (nd entries)
     int16_t * xbs = reinterpret_cast<int16_t *>((TYPE == T_Q4_1 || TYPE == T_Q5_1) ? (xs + nd) : xs);
+    uint8_t * stages = reinterpret_cast<uint8_t *>(xbs) + round_up16(nbs * 2);
+    stages = smem + (((stages - smem) + 127) / 128) * 128;
 
-    if (threadIdx.x == 0) {
-        mbar_init(bar, 1);
-        mbar_fence_init();
-        mbar_expect_tx(bar, (uint32_t) K);
-        tma_load_1d(xq, A.q + (size_t) n * K, (uint32_t) K, bar);      // activation tile: global -> shared via TMA
-    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint64_t * my_bars = bars + warp * S;
+    uint8_t * my_stages = stages + (size_t) warp * S * G::STAGE;
+
+    // rows [row0, row1) belong to this CTA (balanced to +-1 row); warps pull rows from a shared-memory counter
+    const int per = W.M / gridDim.x, rem = W.M % gridDim.x;
+    const int row0 = blockIdx.x * per + min((int) blockIdx.x, rem), row1 = row0 + per + ((int) blockIdx.x < rem ? 1 : 0);
+    const int UPR = (W.nb + T::CH - 1) / T::CH;                 // units per row
+
+    if (threadIdx.x == 0) { mbar_init(xbar, 1); *next_row = row0; }
+    if (lane == 0) for (int s = 0; s < S; s++) mbar_init(my_bars + s, 1);
+    mbar_fence_init();
+    __syncthreads();
+
+    // producer state (lane 0 only): the row/chunk of the next unit to issue
+    int p_row = -1, p_chunk = 0, issued = 0;
+    // consumer state: what the ring holds, in issue order (all lanes track it identically through shuffles)
+    auto issue = [&]() -> bool {                                // lane 0: claim + issue the next unit; false when out of rows
+        if (p_row < 0 || p_chunk == UPR) { p_row = atomicAdd(next_row, 1); p_chunk = 0; }
+        if (p_row >= row1) { p_row = row1; p_chunk = UPR; return false; }
+        const int st = issued % S;
+        const int b0 = p_chunk * T::CH, nblk = min(T::CH, W.nb - b0);
+        uint32_t bytes = 0;
+#pragma unroll
+        for (int p = 0; p < G::NPL; p++) bytes += (uint32_t) ((nblk * G::plane_bytes(p) + 15) / 16 * 16);
+        // (row, chunk) for the consumer side: written before the arrive so that its release ordering covers it
+        reinterpret_cast<int *>(my_stages + (size_t) st * G::STAGE + G::META)[0] = p_row;
+        reinterpret_cast<int *>(my_stages + (size_t) st * G::STAGE + G::META)[1] = p_chunk;
+        mbar_expect_tx(my_bars + st, bytes);
+#pragma unroll
+        for (int p = 0; p < G::NPL; p++)
+            tma_load_1d(my_stages + (size_t) st * G::STAGE + G::off(p), W.p[p] + (size_t) p_row * W.stride[p] + (size_t) b0 * G::plane_bytes(p),
+                        (uint32_t) ((nblk * G::plane_bytes(p) + 15) / 16 * 16), my_bars + st);
+        p_chunk++; issued++;
+        return true;
+    };
+    if (lane == 0) for (int s = 0; s < S; s++) if (!issue()) break;      // weights start streaming before x is even staged
+
+    // activation tile: codes by TMA, scales / block sums (tiny) by ordinary loads
+    if (threadIdx.x == 0) { mbar_expect_tx(xbar, (uint32_t) K); tma_load_1d(xq, A.q + (size_t) n * K, (uint32_t) K, xbar); }
     for (int i = threadIdx.x; i < nd; i += MMV_THREADS) {
         xd[i] = A.d[(size_t) n * nd + i];
         if (TYPE == T_Q4_1 || TYPE == T_Q5_1) xs[i] = A.s[(size_t) n * nd + i];
     }
     for (int i = threadIdx.x; i < nbs; i += MMV_THREADS) xbs[i] = A.bs[(size_t) n * nbs + i];
-    __syncthreads();                                            // barrier init + scale arrays visible
+    __syncthreads();
+    mbar_wait(xbar, 0);
     const XS x = { xq, xd, xs, xbs };
 
-    const int lane = threadIdx.x & 31;
-    const int warps_per_cta = MMV_THREADS / 32;
-    const int gw = blockIdx.x * warps_per_cta + (threadIdx.x >> 5), nw = gridDim.x * warps_per_cta;
-    const int P = W.nb * T::PPB;                                // 16-byte pieces per row
-    bool staged = false;
-
-    for (int row = gw; row < W.M; row += nw) {
-        float acc = 0.f;
-        for (int g0 = 0; g0 < P; g0 += 32 * U) {
-            typename T::Regs regs[U];
-#pragma unroll
-            for (int u = 0; u < U; u++) {
-                const int g = g0 + u * 32 + lane;
-                if (g < P) regs[u] = T::load(W, (size_t) row, g / T::PPB, g % T::PPB);
-            }
-            if (!staged) { mbar_wait(bar, 0); staged = true; }  // first weight loads are already in flight
-#pragma unroll
-            for (int u = 0; u < U; u++) {
-                const int g = g0 + u * 32 + lane;
-                if (g < P) acc += T::dot(regs[u], g / T::PPB, g % T::PPB, x);
-            }
+    int n_issued = __shfl_sync(0xffffffffu, issued, 0);
+    float acc = 0.f;
+    for (int u = 0; u < n_issued; u++) {
+        const int st = u % S;
+        mbar_wait(my_bars + st, (uint32_t) ((u / S) & 1));
+        const uint8_t * sb = my_stages + (size_t) st * G::STAGE;
+        const int row = reinterpret_cast<const int *>(sb + G::META)[0], chunk = reinterpret_cast<const int *>(sb + G::META)[1];
+        const int b0 = chunk * T::CH, nblk = min(T::CH, W.nb - b0);
+        const int P = nblk * T::PPB;
+#pragma unroll 4
+        for (int g = lane; g < P; g += 32) {
+            const typename T::Regs r = T::load(sb, g / T::PPB, g % T::PPB);
+            acc += T::dot(r, b0 + g / T::PPB, g % T::PPB, x);
         }
-        acc = warp_sum(acc);
-        if (lane == 0) {
-            float v = acc;
-            if (epi.kind == EPI_GELU) v = gelu_f16lut(v);
-            else if (epi.kind == EPI_ADD2) v = (v + epi.r1[(size_t) n * y_stride + row]) + epi.r2[(size_t) n * y_stride + row];
-            y[(size_t) n * y_stride + row] = v;
+        __syncwarp();                                           // every lane is done with this stage
+        int more = 0;
+        if (lane == 0) more = issue() ? 1 : 0;                  // refill it
+        n_issued += __shfl_sync(0xffffffffu, more, 0);
+        if (chunk == UPR - 1) {
+            const float v0 = warp_sum(acc);
+            if (lane == 0) {
+                float v = v0;
+                if (epi.kind == EPI_GELU) v = gelu_f16lut(v);
+                else if (epi.kind == EPI_ADD2) v = (v + epi.r1[(size_t) n * y_stride + row]) + epi.r2[(size_t) n * y_stride + row];
+                y[(size_t) n * y_stride + row] = v;
+            }
+            acc = 0.f;
         }
     }
-    if (!staged) mbar_wait(bar, 0);                             // never exit with a bulk copy still landing in our smem
 }
 
 static int g_num_sms = 0;
@@ -357,35 +447,45 @@ static int num_sms() {
     return g_num_sms;
 }
 
-template <int TYPE, int U>
+template <int TYPE>
 static void launch_typed(const WPlanes & W, const ActQ & A, float * y, int64_t y_stride, MmvEpilogue epi, cudaStream_t stream) {
+    using G = UnitGeom<TYPE>;
+    constexpr int WARPS = MMV_THREADS / 32;
     const int K = W.K, ablk = TYPE >= T_Q2_K ? 256 : 32;
-    const size_t smem = 16 + (size_t) K + (size_t) (K / ablk) * 4 * ((TYPE == T_Q4_1 || TYPE == T_Q5_1) ? 2 : 1) + (size_t) (TYPE >= T_Q2_K ? K / 16 : K / 32) * 2 + 16;
+    const size_t xbytes = (size_t) K + (size_t) (K / ablk) * 4 * ((TYPE == T_Q4_1 || TYPE == T_Q5_1) ? 2 : 1) + round_up16((size_t) (TYPE >= T_Q2_K ? K / 16 : K / 32) * 2);
+    int S = 4;                                                  // deepest ring that fits next to the activation tile
+    size_t smem = 0;
+    for (; S >= 1; S--) {
+        smem = 16 + round_up16((size_t) WARPS * S * 8) + xbytes + 256 + (size_t) WARPS * S * G::STAGE;
+        if (smem <= 220 * 1024) break;
+    }
+    B200_ASSERT(S >= 1);
     static bool attr_set = false;
-    if (!attr_set) { B200_CUDA_CHECK(cudaFuncSetAttribute(mmv_kernel<TYPE, U>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr_set = true; }
-    const int warps = MMV_THREADS / 32;
-    int ctas = num_sms() * 4;                                   // persistent: 4 CTAs x 256 threads per SM when shared memory allows
-    const int need = (W.M + warps - 1) / warps;
-    if (ctas > need) ctas = need;
+    if (!attr_set) { B200_CUDA_CHECK(cudaFuncSetAttribute(mmv_kernel<TYPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr_set = true; }
+    int ctas = num_sms();                                       // one persistent CTA per SM
+    if (ctas > W.M) ctas = W.M;
     dim3 grid((unsigned) ctas, (unsigned) A.N);
-    mmv_kernel<TYPE, U><<<grid, MMV_THREADS, smem, stream>>>(W, A, y, y_stride, epi);
+    mmv_kernel<TYPE><<<grid, MMV_THREADS, smem, stream>>>(W, A, y, y_stride, epi, S);
     B200_CUDA_CHECK(cudaGetLastError());
 }
 
+bool launch_mmv_fast(const WPlanes & W, const ActQ & A, float * y, int64_t y_stride, MmvEpilogue e, cudaStream_t stream);   // mmv_fast.cu
+
 void launch_mmv(const WPlanes & W, const ActQ & A, float * y, int64_t y_stride, MmvEpilogue epi, cudaStream_t stream) {
     B200_ASSERT(A.K == W.K && A.type == act_type_for(W.type));
-    B200_ASSERT(W.K % 32 == 0 && W.K <= 190 * 1024);
+    if (!getenv("B200_MMV_GENERIC") && launch_mmv_fast(W, A, y, y_stride, epi, stream)) return;
+    B200_ASSERT(W.K % 32 == 0 && W.K <= 96 * 1024);
     switch (W.type) {
-        case T_Q4_K: launch_typed<T_Q4_K, 4>(W, A, y, y_stride, epi, stream); break;
-        case T_Q5_K: launch_typed<T_Q5_K, 2>(W, A, y, y_stride, epi, stream); break;
-        case T_Q6_K: launch_typed<T_Q6_K, 2>(W, A, y, y_stride, epi, stream); break;
-        case T_Q3_K: launch_typed<T_Q3_K, 2>(W, A, y, y_stride, epi, stream); break;
-        case T_Q2_K: launch_typed<T_Q2_K, 2>(W, A, y, y_stride, epi, stream); break;
-        case T_Q4_0: launch_typed<T_Q4_0, 4>(W, A, y, y_stride, epi, stream); break;
-        case T_Q4_1: launch_typed<T_Q4_1, 4>(W, A, y, y_stride, epi, stream); break;
-        case T_Q5_0: launch_typed<T_Q5_0, 4>(W, A, y, y_stride, epi, stream); break;
-        case T_Q5_1: launch_typed<T_Q5_1, 4>(W, A, y, y_stride, epi, stream); break;
-        case T_Q8_0: launch_typed<T_Q8_0, 4>(W, A, y, y_stride, epi, stream); break;
+        case T_Q4_K: launch_typed<T_Q4_K>(W, A, y, y_stride, epi, stream); break;
+        case T_Q5_K: launch_typed<T_Q5_K>(W, A, y, y_stride, epi, stream); break;
+        case T_Q6_K: launch_typed<T_Q6_K>(W, A, y, y_stride, epi, stream); break;
+        case T_Q3_K: launch_typed<T_Q3_K>(W, A, y, y_stride, epi, stream); break;
+        case T_Q2_K: launch_typed<T_Q2_K>(W, A, y, y_stride, epi, stream); break;
+        case T_Q4_0: launch_typed<T_Q4_0>(W, A, y, y_stride, epi, stream); break;
+        case T_Q4_1: launch_typed<T_Q4_1>(W, A, y, y_stride, epi, stream); break;
+        case T_Q5_0: launch_typed<T_Q5_0>(W, A, y, y_stride, epi, stream); break;
+        case T_Q5_1: launch_typed<T_Q5_1>(W, A, y, y_stride, epi, stream); break;
+        case T_Q8_0: launch_typed<T_Q8_0>(W, A, y, y_stride, epi, stream); break;
         default: B200_ASSERT(!"launch_mmv: unsupported weight type");
     }
 }

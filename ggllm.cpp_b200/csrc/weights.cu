@@ -31,7 +31,12 @@ __global__ void repack_kernel(const uint8_t * __restrict__ src, WPlanes W, TypeS
     for (int p = 0; p < ts.n_planes; p++) {
         uint8_t * d = W.p[p] + (size_t) (row0 + r) * W.stride[p] + (size_t) b * ts.plane[p].bytes;
         const uint8_t * f = s + ts.plane[p].src_off;
-        for (int i = 0; i < ts.plane[p].bytes; i++) d[i] = f[i];
+        if (ts.plane[p].kind == 1) {                      // expand the 6-bit (scale, min) pairs, see PlaneSpec
+            for (int pr = 0; pr < 4; pr++) {
+                int s0, m0, s1, m1; unpack_sm6(2 * pr, f, s0, m0); unpack_sm6(2 * pr + 1, f, s1, m1);
+                d[4 * pr] = (uint8_t) s0; d[4 * pr + 1] = (uint8_t) s1; d[4 * pr + 2] = (uint8_t) m0; d[4 * pr + 3] = (uint8_t) m1;
+            }
+        } else for (int i = 0; i < ts.plane[p].bytes; i++) d[i] = f[i];
     }
 }
 
@@ -100,6 +105,7 @@ __global__ void fill_random_kernel(WPlanes W, TypeSpec ts, uint64_t seed) {
             const int nbytes = ts.plane[p].bytes;
             for (int i = 0; i < nbytes; i += 4) {
                 uint32_t v = mix32(seed ^ (((uint64_t) idx * 8 + p) << 20) ^ (uint64_t) i);
+                if (ts.plane[p].kind == 1) v &= 0x3f3f3f3fu;         // expanded 6-bit scales / mins
                 for (int k = 0; k < 4 && i + k < nbytes; k++) d[i + k] = (uint8_t) (v >> (8 * k));
             }
         }
@@ -118,8 +124,8 @@ __global__ void fill_random_kernel(WPlanes W, TypeSpec ts, uint64_t seed) {
             case T_Q5_1: put16(2, 0, d16); put16(2, 2, m16); break;
             case T_Q2_K: put16(2, 0, d16); put16(2, 2, d16); break;
             case T_Q3_K: put16(3, 0, d16); break;
-            case T_Q4_K: put16(1, 0, d16); put16(1, 2, d16); break;
-            case T_Q5_K: put16(2, 0, d16); put16(2, 2, d16); break;
+            case T_Q4_K: put16(2, 0, d16); put16(2, 2, d16); break;
+            case T_Q5_K: put16(3, 0, d16); put16(3, 2, d16); break;
             case T_Q6_K: put16(3, 0, d16); break;
             case T_F16: put16(0, 0, __half_as_ushort(__float2half_rn(dsm * 10.f - 0.02f))); break;
             case T_F32: *reinterpret_cast<float *>(W.p[0] + (size_t) r * W.stride[0] + (size_t) b * 4) = dsm * 10.f - 0.02f; break;

@@ -118,3 +118,23 @@ def read_ggcc(path, mmap=True):
         tensors[name] = (t, ne, buf[off:off + nbytes])
         off += nbytes
     return hp, tensors
+
+
+def random_blocks(ggml_type, n_rows, k, rng):
+    """n_rows x k weights as well-formed pseudo-random blocks of `ggml_type` (uniform quant bytes, sane fp16 scales):
+    the host twin of b200_weight_random, for files the reference has to load."""
+    per, bsz = BLOCK[ggml_type]
+    nb = n_rows * (k // per)
+    if ggml_type == 0:
+        return (0.02 * rng.standard_normal((n_rows, k))).astype(np.float32)
+    if ggml_type == 1:
+        return (0.02 * rng.standard_normal((n_rows, k))).astype(np.float16)
+    raw = rng.integers(0, 256, size=(nb, bsz), dtype=np.uint8)
+    unit = 1e-4 if per == 256 else 2e-3
+    d = (unit * (1.0 + 2.0 * rng.random(nb))).astype(np.float16).view(np.uint16)
+    lo, hi = (d & 0xff).astype(np.uint8), (d >> 8).astype(np.uint8)
+    # byte offsets of the fp16 scale fields inside one block (ggml.c:879-916, k_quants.h:20-74)
+    offs = {2: [0], 3: [0, 2], 6: [0], 7: [0, 2], 8: [0], 10: [80, 82], 11: [108], 12: [0, 2], 13: [0, 2], 14: [208]}[ggml_type]
+    for o in offs:
+        raw[:, o], raw[:, o + 1] = lo, hi
+    return raw.reshape(n_rows, -1)

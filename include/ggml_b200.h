@@ -149,6 +149,10 @@ void          b200_falcon_decode_dev(b200_falcon * f, const int32_t * token_dev,
 const float * b200_falcon_logits_dev(const b200_falcon * f);
 /* the cudaStream_t the eval path runs on (for event timing) */
 void *        b200_falcon_stream(b200_falcon * f);
+/* roofline probe: every resident quantised mat-vec of this rank (4 per layer + lm_head) launched back to back,
+ * `reps` passes, timed with CUDA events on the eval stream.  Returns total ms; fills the launch count and the
+ * algorithmic weight bytes streamed in that region. */
+float         b200_falcon_profile_matvec(b200_falcon * f, int reps, int * n_launches, size_t * bytes);
 /* number of kernel launches (graph nodes) issued by the most recent eval on this rank */
 int           b200_falcon_last_launches(const b200_falcon * f);
 /* CUDA-event time (ms) of the most recent eval's device work on this rank */

@@ -10,6 +10,8 @@ def main():
     L = b.lib()
     types = [int(t) for t in sys.argv[1].split(",")] if len(sys.argv) > 1 else [12, 2, 11, 14]
     shapes = [(8192, 9216), (8192, 8192), (8192, 32768), (32768, 8192), (8192, 65024)]
+    if len(sys.argv) > 2:
+        shapes = [tuple(int(v) for v in sh.split("x")) for sh in sys.argv[2].split(",")]
     e0, e1 = L.b200_event_create(), L.b200_event_create()
     for t in types:
         for K, M in shapes:
