@@ -1,0 +1,34 @@
+"""-m gpu: the drop-in boundary.  The UNMODIFIED reference (ggml.c + libfalcon.cpp compiled with -DGGML_USE_CUBLAS into
+oracle/_ref/libfalcon_hook.so, ggml_cuda_* symbols left undefined) is loaded on top of libggml_b200.so, so its own
+loader (ggml_cuda_transform_tensor, libfalcon.cpp:1251), graph builder and executor hook (ggml_cuda_compute_forward,
+ggml.c:15779-15790) drive our kernels.  Logits are compared with the oracle's CPU restatement."""
+import os
+import numpy as np
+import pytest
+import pyoracle as po
+from helpers import TINY_40B, TINY_7B, synth_model, ggcc
+
+pytestmark = pytest.mark.gpu
+HOOK = os.path.join(po.HERE, "_ref", "libfalcon_hook.so")
+
+
+@pytest.mark.skipif(not os.path.exists(HOOK), reason="oracle/_ref/libfalcon_hook.so not present (built where /root/reference exists)")
+@pytest.mark.parametrize("hp,wt,ftype", [(TINY_40B, po.Q4_K, 15), (TINY_7B, po.Q4_0, 2)])
+def test_reference_eval_runs_on_our_operator_surface(gpu, tmp_path, hp, wt, ftype):
+    tensors = synth_model(hp, wt, seed=1234)
+    path = str(tmp_path / "m.ggcc")
+    ggcc.write_ggcc(path, hp, tensors, ftype=ftype)
+    gpu.lib()                                      # libggml_b200.so is in the global symbol scope (RTLD_GLOBAL)
+    ref = po.RefFalcon(path, n_ctx=64, n_batch=16, logits_all=True, hook=True, n_gpu_layers=99)
+    o = po.OrcFalcon(hp, tensors, n_ctx=64)
+    prompt = np.array([11] + list(range(100, 111)), np.int32)          # 12 tokens: the N > 8 (GEMM) branch of the hook
+    got, want = ref.eval(prompt, 0, n_threads=2), o.eval(prompt, 0, all_logits=True)
+    S = np.abs(want).max()
+    assert np.abs(got - want).max() <= 3e-2 * S and np.median(np.abs(got - want)) <= 5e-3 * S
+    tight = []
+    for i in range(4):                                                  # decode: the mat-vec branch
+        tok = np.array([200 + i], np.int32)
+        g, w = ref.eval(tok, 12 + i, n_threads=2), o.eval(tok, 12 + i, all_logits=True)
+        assert np.abs(g - w).max() <= 3e-2 * S and np.median(np.abs(g - w)) <= 5e-3 * S
+        tight.append(np.median(np.abs(g - w)) <= 2e-5 * S)
+    ref.close()
