@@ -12,6 +12,8 @@ static cudaStream_t g_stream = nullptr;
 static std::mutex g_mu;
 
 cudaStream_t b200_current_stream() { return g_stream; }
+void launch_gemm_simt(const WPlanes & W, const __half * X, int64_t x_stride, int N, float * Y, int64_t y_stride, int epi_gelu, cudaStream_t stream);
+bool launch_gemm_tc(const WPlanes & W, const __half * X, int64_t x_stride, int N, float * Y, int64_t y_stride, int epi_gelu, cudaStream_t stream);
 
 extern "C" {
 
@@ -131,6 +133,11 @@ void b200_mul_mat(const b200_weight * w, const float * x, int64_t x_stride, int 
         launch_actq_to_f16(A, xh, W.K, g_stream);
         launch_mmq_gemm(W, xh, W.K, N, y, y_stride, 0, base + abytes + hbytes, wsb, g_stream);
     }
+}
+
+int b200_mul_mat_f16(const b200_weight * w, const void * x_f16, int64_t x_stride, int N, float * y, int64_t y_stride, int epi_gelu, int impl) {
+    if (impl == 0) { launch_gemm_simt(w->W, (const __half *) x_f16, x_stride, N, y, y_stride, epi_gelu, g_stream); return 1; }
+    return launch_gemm_tc(w->W, (const __half *) x_f16, x_stride, N, y, y_stride, epi_gelu, g_stream) ? 1 : 0;
 }
 
 void b200_layernorm(const float * x, int64_t xs, const float * g, const float * b, float * y, int64_t ys, int n, int rows) { launch_layernorm(x, xs, g, b, y, ys, n, rows, g_stream); }

@@ -1,0 +1,291 @@
+// gemm_tc.cu -- prompt mat-mat on the 5th-generation tensor cores: Y[n][m] = sum_k fp16(W[m][k]) * X[n][k].
+//
+// Replaces the reference's prompt path (ggml-cuda.cu:2353-2403): dequantise the WHOLE weight matrix to an fp16
+// temporary (to_fp16_cuda, 2 B/weight written and re-read = 4.6x the quantised bytes), convert activations
+// (float_to_half + stream sync), cublasGemmEx, per call.  Here the quantised blocks are the only thing read from
+// HBM; a tile is dequantised once, straight into the shared-memory operand layout of tcgen05.mma, and used for every
+// token of the batch (up to 512 accumulator columns live in TMEM).
+//
+// One CTA = one 128-row tile of W over the full K and ALL N tokens (N <= 512):
+//   warp 0      : TMA producer of the activation tile  B[N x 64] fp16 (cp.async.bulk.tensor.2d, SWIZZLE_128B), ring of SB stages
+//   warp 1      : allocates TMEM (512 columns), single elected thread issues tcgen05.mma.cta_group::1.kind::f16
+//                 (M = 128, N <= 256 per instruction, K = 16), tcgen05.commit releases the smem stages
+//   warps 2..9  : dequant producers: 2 threads per weight row, 32 weights each per 64-wide K block, written as
+//                 8 halves per 16-byte chunk into the K-major SWIZZLE_128B layout (chunk c of row r at c ^ (r & 7)),
+//                 fence.proxy.async, mbarrier arrive; ring of SA stages.  After the main loop the same warps are the
+//                 epilogue: tcgen05.ld 32x32b.x32 -> (GELU) -> coalesced fp32 stores.
+// Operands: A = weights (K-major smem), B = activations (K-major smem), D = fp32 in TMEM, lane = weight row.
+#include "kernels.h"
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
+namespace {
+
+constexpr int BM = 128, BK = 64, SA = 4, SB = 2;
+constexpr int N_MAX = 512;
+constexpr int PRODUCER_THREADS = 256, THREADS = 64 + PRODUCER_THREADS;
+constexpr int A_STAGE = BM * BK * 2;                       // 16 KB
+
+__device__ __forceinline__ void mbar_arrive(uint64_t * bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t * bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16(uint32_t tmem_c, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 :: "r"(tmem_c), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void * smem_dst, const CUtensorMap * map, int c0, int c1, uint64_t * bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 :: "r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): 8-row groups 1024 B apart
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t) ((smem_addr & 0x3FFFF) >> 4);           // start address, 16-byte units
+    d |= (uint64_t) 1 << 16;                                // leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t) (1024 >> 4) << 32;                      // stride byte offset between 8-row groups
+    d |= (uint64_t) 1 << 46;                                // descriptor version (Blackwell)
+    d |= (uint64_t) 2 << 61;                                // SWIZZLE_128B
+    return d;
+}
+__device__ __forceinline__ uint32_t instr_desc_f16(int n) {  // cute::UMMA::InstrDescriptor: f16 x f16 -> f32, both K-major, M = 128
+    return (1u << 4) | ((uint32_t) (n >> 3) << 17) | ((uint32_t) (BM >> 4) << 24);
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]),
+                   "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                   "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+    const __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<const uint32_t *>(&h);
+}
+
+// ---- dequantisation of one thread's share of a 64-wide K block: segments [16h, 16h+16) and [32+16h, 32+16h+16) of the block,
+//      returned as 4 chunks of 8 halves: lo0, lo1 (first segment), hi0, hi1 (second segment)
+struct Chunks { uint4 c[4]; };
+
+// generic: element-wise through the bit-exact dequantiser (any type)
+__device__ __forceinline__ Chunks dequant_generic(const WPlanes & W, size_t row, int k0, int h) {
+    Chunks o;
+#pragma unroll
+    for (int s = 0; s < 2; s++)
+#pragma unroll
+        for (int c = 0; c < 2; c++) {
+            const int e = k0 + 32 * s + 16 * h + 8 * c;
+            float v[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) v[i] = dequant_elem(W, row, e + i);
+            o.c[2 * s + c] = make_uint4(pack_h2(v[0], v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
+        }
+    return o;
+}
+// Q4_K: w = (d*sc)*q - dmin*m, computed in fp32 exactly like dequantize_row_q4_K (k_quants.c:607-631), one rounding to fp16
+struct RawQ4K { uint4 q; uint32_t sm, dd; };
+__device__ __forceinline__ RawQ4K load_q4k(const WPlanes & W, size_t row, int kb, int h) {
+    RawQ4K r;
+    const int b = kb >> 2, p = kb & 3;
+    r.q = ldg_stream_v4(W.p[0] + row * W.stride[0] + (size_t) b * 128 + p * 32 + h * 16);
+    r.sm = ldg_u32(W.p[1] + row * W.stride[1] + (size_t) b * 16 + p * 4);
+    r.dd = ldg_u32(W.p[2] + row * W.stride[2] + (size_t) b * 4);
+    return r;
+}
+__device__ __forceinline__ Chunks dequant_q4k(const RawQ4K & r) {
+    const float2 dm = __half22float2(*reinterpret_cast<const __half2 *>(&r.dd));
+    const float d0 = __fmul_rn(dm.x, (float) (r.sm & 0xff)), d1 = __fmul_rn(dm.x, (float) ((r.sm >> 8) & 0xff));
+    const float m0 = __fmul_rn(dm.y, (float) ((r.sm >> 16) & 0xff)), m1 = __fmul_rn(dm.y, (float) (r.sm >> 24));
+    const uint32_t w[4] = { r.q.x, r.q.y, r.q.z, r.q.w };
+    float lo[16], hi[16];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const uint32_t byte = (w[i] >> (8 * j)) & 0xff;
+            lo[4 * i + j] = __fsub_rn(__fmul_rn(d0, (float) (byte & 0xF)), m0);
+            hi[4 * i + j] = __fsub_rn(__fmul_rn(d1, (float) (byte >> 4)), m1);
+        }
+    Chunks o;
+    o.c[0] = make_uint4(pack_h2(lo[0], lo[1]), pack_h2(lo[2], lo[3]), pack_h2(lo[4], lo[5]), pack_h2(lo[6], lo[7]));
+    o.c[1] = make_uint4(pack_h2(lo[8], lo[9]), pack_h2(lo[10], lo[11]), pack_h2(lo[12], lo[13]), pack_h2(lo[14], lo[15]));
+    o.c[2] = make_uint4(pack_h2(hi[0], hi[1]), pack_h2(hi[2], hi[3]), pack_h2(hi[4], hi[5]), pack_h2(hi[6], hi[7]));
+    o.c[3] = make_uint4(pack_h2(hi[8], hi[9]), pack_h2(hi[10], hi[11]), pack_h2(hi[12], hi[13]), pack_h2(hi[14], hi[15]));
+    return o;
+}
+
+struct GemmArgs {
+    WPlanes W;
+    float * Y; int64_t y_stride;
+    int N, NT;            // tokens; tokens rounded up to 16 (accumulator columns used)
+    int box_rows;         // rows of one TMA box of the activation tile (<= 256)
+    int epi_gelu;
+};
+
+template <int TYPE>
+__global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap xmap, const GemmArgs a) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t * smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t) 1023);
+    const int b_stage = a.box_rows * (a.NT > 256 ? 2 : 1) * 128;          // bytes of one activation stage
+    uint8_t * sA = smem;                                                   // SA stages of 16 KB
+    uint8_t * sB = smem + SA * A_STAGE;                                    // SB stages
+    uint64_t * bars = reinterpret_cast<uint64_t *>(sB + SB * b_stage);
+    uint64_t * a_full = bars, * a_empty = bars + SA, * b_full = bars + 2 * SA, * b_empty = bars + 2 * SA + SB, * acc_full = bars + 2 * SA + 2 * SB;
+    uint32_t * tmem_slot = reinterpret_cast<uint32_t *>(acc_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.x * BM;
+    const int KB = a.W.K / BK;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < SA; s++) { mbar_init(a_full + s, PRODUCER_THREADS); mbar_init(a_empty + s, 1); }
+        for (int s = 0; s < SB; s++) { mbar_init(b_full + s, 1); mbar_init(b_empty + s, 1); }
+        mbar_init(acc_full, 1);
+        mbar_fence_init();
+    }
+    if (warp == 1) {                                                       // TMEM: all 512 columns, one CTA per SM
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer: activation tile [NT x 64] of K block kb =====
+        if (lane == 0) {
+            for (int kb = 0; kb < KB; kb++) {
+                const int s = kb % SB;
+                if (kb >= SB) mbar_wait(b_empty + s, (uint32_t) ((kb / SB - 1) & 1));
+                mbar_expect_tx(b_full + s, (uint32_t) b_stage);
+                tma_load_2d(sB + (size_t) s * b_stage, &xmap, kb * BK, 0, b_full + s);
+                if (a.NT > 256) tma_load_2d(sB + (size_t) s * b_stage + a.box_rows * 128, &xmap, kb * BK, 256, b_full + s);
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            const int n0 = a.NT > 256 ? 256 : a.NT, n1 = a.NT > 256 ? a.NT - 256 : 0;
+            const uint32_t id0 = instr_desc_f16(n0), id1 = instr_desc_f16(n1 > 0 ? n1 : 16);
+            for (int kb = 0; kb < KB; kb++) {
+                const int sa = kb % SA, sb = kb % SB;
+                mbar_wait(a_full + sa, (uint32_t) ((kb / SA) & 1));
+                mbar_wait(b_full + sb, (uint32_t) ((kb / SB) & 1));
+                tc_fence_after();
+                const uint32_t a_addr = smem_u32(sA + (size_t) sa * A_STAGE), b_addr = smem_u32(sB + (size_t) sb * b_stage);
+#pragma unroll
+                for (int k = 0; k < BK / 16; k++) {
+                    const uint64_t da = umma_desc(a_addr + k * 32);
+                    tc_mma_f16(tmem_base, da, umma_desc(b_addr + k * 32), id0, (kb | k) != 0);
+                    if (n1 > 0) tc_mma_f16(tmem_base + 256, da, umma_desc(b_addr + a.box_rows * 128 + k * 32), id1, (kb | k) != 0);
+                }
+                tc_commit(a_empty + sa);                                   // stages are free once these MMAs have read them
+                tc_commit(b_empty + sb);
+            }
+            tc_commit(acc_full);
+        }
+    } else {
+        // ===== dequant producers (2 threads per weight row) =====
+        const int t = threadIdx.x - 64, r = t >> 1, h = t & 1;
+        const size_t row = (size_t) min(m0 + r, a.W.M - 1);                // rows past M are computed from row M-1 and never stored
+        uint8_t * my_row = nullptr;
+        RawQ4K raw;
+        if (TYPE == T_Q4_K) raw = load_q4k(a.W, row, 0, h);
+        for (int kb = 0; kb < KB; kb++) {
+            const int s = kb % SA;
+            Chunks ch;
+            if (TYPE == T_Q4_K) {
+                ch = dequant_q4k(raw);
+                if (kb + 1 < KB) raw = load_q4k(a.W, row, kb + 1, h);      // next block's bytes are in flight while this one is stored
+            } else ch = dequant_generic(a.W, row, kb * BK, h);
+            if (kb >= SA) mbar_wait(a_empty + s, (uint32_t) ((kb / SA - 1) & 1));
+            my_row = sA + (size_t) s * A_STAGE + r * 128;
+            const int sw = r & 7;
+            *reinterpret_cast<uint4 *>(my_row + (((2 * h) ^ sw) << 4)) = ch.c[0];          // elements 16h .. 16h+7
+            *reinterpret_cast<uint4 *>(my_row + (((2 * h + 1) ^ sw) << 4)) = ch.c[1];      //          16h+8 .. 16h+15
+            *reinterpret_cast<uint4 *>(my_row + (((4 + 2 * h) ^ sw) << 4)) = ch.c[2];      // elements 32+16h ..
+            *reinterpret_cast<uint4 *>(my_row + (((5 + 2 * h) ^ sw) << 4)) = ch.c[3];
+            fence_proxy_async();                                           // generic-proxy stores -> visible to the tensor core (async proxy)
+            mbar_arrive(a_full + s);
+        }
+        // ===== epilogue: TMEM -> registers -> global =====
+        mbar_wait(acc_full, 0);
+        tc_fence_after();
+        const int q = warp & 3;                                            // TMEM lane quarter this warp may access
+        const int half_id = (warp - 2) >> 2;                               // two warps share a quarter: even / odd 32-column chunks
+        const int m = m0 + q * 32 + lane;
+        const int nchunks = (a.NT + 31) / 32;
+        for (int c = half_id; c < nchunks; c += 2) {
+            uint32_t v[32];
+            tmem_ld32(tmem_base + ((uint32_t) (q * 32) << 16) + (uint32_t) (c * 32), v);
+            if (m < a.W.M) {
+#pragma unroll
+                for (int j = 0; j < 32; j++) {
+                    const int n = c * 32 + j;
+                    if (n < a.N) {
+                        float y = __uint_as_float(v[j]);
+                        if (a.epi_gelu) { const float f = __half2float(__float2half_rn(y));
+                            y = __half2float(__float2half_rn(0.5f * f * (1.0f + tanhf(0.79788456080286535587989211986876f * f * (1.0f + 0.044715f * f * f))))); }
+                        a.Y[(size_t) n * a.y_stride + m] = y;              // a warp writes 32 consecutive m: 128 B per store
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(512) : "memory");
+}
+
+PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
+    static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+    if (!fn) {
+        cudaDriverEntryPointQueryResult q;
+        void * p = nullptr;
+        B200_CUDA_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+        B200_ASSERT(q == cudaDriverEntryPointSuccess && p);
+        fn = (PFN_cuTensorMapEncodeTiled_v12000) p;
+    }
+    return fn;
+}
+
+template <int TYPE>
+void launch_typed(const CUtensorMap & map, const GemmArgs & a, size_t smem, cudaStream_t stream) {
+    static bool set = false;
+    if (!set) { B200_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<TYPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); set = true; }
+    gemm_tc_kernel<TYPE><<<(a.W.M + BM - 1) / BM, THREADS, smem, stream>>>(map, a);
+    B200_CUDA_CHECK(cudaGetLastError());
+}
+
+} // namespace
+
+// X: fp16 [N][x_stride] (x_stride >= K, multiple of 8), Y: fp32 [N][y_stride].  N <= 512, K % 64 == 0.
+bool launch_gemm_tc(const WPlanes & W, const __half * X, int64_t x_stride, int N, float * Y, int64_t y_stride, int epi_gelu, cudaStream_t stream) {
+    if (N > N_MAX || W.K % BK != 0 || (x_stride % 8) != 0 || ((uintptr_t) X & 15) != 0) return false;
+    GemmArgs a;
+    a.W = W; a.Y = Y; a.y_stride = y_stride; a.N = N; a.NT = (N + 15) / 16 * 16; a.epi_gelu = epi_gelu;
+    a.box_rows = a.NT > 256 ? 256 : a.NT;
+    CUtensorMap map;
+    const cuuint64_t gdim[2] = { (cuuint64_t) W.K, (cuuint64_t) N };
+    const cuuint64_t gstr[1] = { (cuuint64_t) x_stride * 2 };
+    const cuuint32_t box[2] = { (cuuint32_t) BK, (cuuint32_t) a.box_rows };
+    const cuuint32_t estr[2] = { 1, 1 };
+    const CUresult rc = get_encode()(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void *) X, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (rc != CUDA_SUCCESS) { fprintf(stderr, "b200: cuTensorMapEncodeTiled failed (%d)\n", (int) rc); exit(1); }
+    const size_t b_stage = (size_t) a.box_rows * (a.NT > 256 ? 2 : 1) * 128;
+    const size_t smem = 1024 + (size_t) SA * A_STAGE + SB * b_stage + 256;
+    switch (W.type) {
+        case T_Q4_K: launch_typed<T_Q4_K>(map, a, smem, stream); break;
+        default:     launch_typed<-1>(map, a, smem, stream); break;        // generic element-wise dequantiser
+    }
+    return true;
+}

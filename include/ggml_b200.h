@@ -86,6 +86,11 @@ void   b200_mul_mat(const b200_weight * w, const float * x_dev, int64_t x_stride
 void   b200_mul_mat_vec_q(const b200_weight * w, const b200_actq * a, float * y_dev, int64_t y_stride,
                           int epilogue, const float * r1_dev, const float * r2_dev);
 int    b200_mmv_max_n(void);
+/* the GEMM half alone, on fp16 activations x[n][k] already on the device (what b200_mul_mat does after quantising):
+ * impl 1 = tcgen05 tensor-core kernel (returns 0 if the shape is not covered: N > 512 or K % 64 != 0),
+ * impl 0 = CUDA-core kernel with identical operand rounding (the test reference for impl 1). */
+int    b200_mul_mat_f16(const b200_weight * w, const void * x_f16_dev, int64_t x_stride, int N, float * y_dev, int64_t y_stride,
+                        int epilogue_gelu, int impl);
 
 /* ---- the other operators of the Falcon graph, CPU-oracle numerics */
 /* y = norm(x) * g + b per row of n values (g, b may be NULL = plain ggml_norm, ggml.c:10540-10599) */

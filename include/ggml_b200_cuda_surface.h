@@ -47,6 +47,7 @@ typedef struct {                                       /* ggml-cuda.h:16-27 */
 } GPUStatus;
 #endif
 
+#ifndef GGML_B200_SURFACE_TYPES_ONLY   /* oracle/abi_check.cpp compares just the types with the reference's */
 /* ggml-cuda.h:31  pointer to a static struct, never freed by the caller */
 const GPUStatus * ggml_cuda_get_system_gpu_status(void);
 /* ggml-cuda.h:33  check_only: has init finished? (non-blocking); otherwise initialise (idempotent).  Called from a
@@ -79,6 +80,7 @@ void   ggml_cuda_assign_buffers(struct ggml_tensor * tensor);
 void   ggml_cuda_assign_buffers_no_scratch(struct ggml_tensor * tensor);
 /* ggml-cuda.h:60  THE operator hook (called by every worker thread, ggml.c:15779-15790): true = handled */
 bool   ggml_cuda_compute_forward(struct ggml_compute_params * params, struct ggml_tensor * tensor);
+#endif /* GGML_B200_SURFACE_TYPES_ONLY */
 
 #ifdef __cplusplus
 }

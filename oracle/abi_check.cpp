@@ -32,8 +32,7 @@ namespace ours {
 #undef GGML_CUDA_MAX_DEVICES
 #define ggml_tensor_extra_gpu ggml_tensor_extra_gpu_ours
 #define GPUStatus GPUStatus_ours
-#define ggml_cuda_get_system_gpu_status ggml_cuda_get_system_gpu_status_ours
-#define ggml_cuda_print_gpu_status ggml_cuda_print_gpu_status_ours
+#define GGML_B200_SURFACE_TYPES_ONLY
 #include "../include/ggml_b200_cuda_surface.h"
 #undef GPUStatus
 #undef ggml_tensor_extra_gpu

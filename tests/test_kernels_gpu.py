@@ -217,3 +217,27 @@ def test_attention(gpu, orc, n_head, n_head_kv, n_tok, n_past):
     # by one fp16 ulp (2^-11 relative); outputs are O(1) averages of V
     assert np.allclose(got, want, rtol=0, atol=2e-3)
     assert np.median(np.abs(got - want)) < 2e-6
+
+
+@pytest.mark.parametrize("t,M,K,N,gelu", [(po.Q4_K, 256, 512, 40, 0), (po.Q4_K, 1000, 1024, 300, 0), (po.Q4_K, 384, 2048, 512, 1),
+                                          (po.Q4_0, 200, 256, 17, 0), (po.Q6_K, 128, 512, 64, 0), (po.Q4_K, 128, 8192, 9, 0), (po.Q4_K, 640, 1024, 512, 0)])
+def test_tensor_core_gemm_matches_cuda_core_gemm(gpu, orc, t, M, K, N, gelu):
+    """tcgen05 kernel vs the CUDA-core kernel on identical fp16 operands: only the fp32 accumulation order differs.
+    Then both against the exact fp64 product of the fp16-rounded operands."""
+    rng = np.random.default_rng(M + K + N)
+    wq = _weights(orc, t, M, K, seed=3)
+    xh = rng.standard_normal((N, K)).astype(np.float16)
+    W = gpu.Weight(t, K, M, wq)
+    xd, y0, y1 = gpu.DevBuf(src=xh), gpu.DevBuf(N * M * 4), gpu.DevBuf(N * M * 4)
+    y1.zero()
+    assert gpu.lib().b200_mul_mat_f16(W.h, xd.ptr, K, N, y0.ptr, M, gelu, 0) == 1
+    assert gpu.lib().b200_mul_mat_f16(W.h, xd.ptr, K, N, y1.ptr, M, gelu, 1) == 1
+    a, b = y0.download(np.float32, (N, M)), y1.download(np.float32, (N, M))
+    wd = orc.dequantize(t, wq, K).astype(np.float16).astype(np.float64)
+    exact = xh.astype(np.float64) @ wd.T
+    budget = 3e-6 * (np.abs(xh.astype(np.float64)) @ np.abs(wd).T) + 1e-6
+    if gelu:
+        exact = orc.gelu(exact.astype(np.float32)).astype(np.float64)
+        budget = np.maximum(budget, np.abs(exact) * 2.0 ** -9 + 1e-6)        # fp16 rounding of the GELU input and of its output
+    assert np.all(np.abs(b - exact) <= budget), float(np.abs(b - exact).max())
+    assert np.all(np.abs(a - exact) <= budget), float(np.abs(a - exact).max())
