@@ -149,7 +149,10 @@ void b200_rope_neox(float * x, int n_tok, int n_head, int head_dim, int64_t tok_
 void b200_attention(float * qkv, float * kc, float * vc, float * out, int n_head, int n_head_kv, int head_dim, int n_tok, int n_past, int n_ctx, int n_ctx_rope) {
     AttnParams p = { n_head, n_head_kv, head_dim, n_tok, n_past, nullptr, n_ctx, (int64_t) (n_head + 2 * n_head_kv) * head_dim };
     launch_rope_kv_append(qkv, kc, vc, p, rope_theta_scale_host(head_dim, n_ctx_rope ? n_ctx_rope : n_ctx, 1, 2.0f, 0), g_stream);   // libfalcon.cpp:2231-2234
-    launch_attention(qkv, kc, vc, out, (int64_t) n_head * head_dim, p, nullptr, g_stream);
+    if (n_tok > 1) {
+        float * sc = (float *) scratch(attention_prefill_scratch_bytes(n_head, n_tok, n_past + n_tok));
+        launch_attention_prefill(qkv, kc, vc, out, (int64_t) n_head * head_dim, p, sc, g_stream);
+    } else launch_attention(qkv, kc, vc, out, (int64_t) n_head * head_dim, p, nullptr, g_stream);
 }
 
 } // extern "C"

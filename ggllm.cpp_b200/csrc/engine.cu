@@ -68,6 +68,7 @@ struct b200_falcon {
     void * actq_mem = nullptr; ActQ xa{}, xm{}, xatt{}, xup{}, xf{};
     __half * xh_a = nullptr, * xh_b = nullptr;      // fp16 GEMM operands, one per branch
     void * gemm_ws_a = nullptr, * gemm_ws_b = nullptr; size_t gemm_ws_bytes = 0;
+    float * attn_scratch = nullptr;
     int32_t * tokens_dev = nullptr; int * n_past_dev = nullptr;
     int32_t * tokens_h = nullptr; int * n_past_h = nullptr; float * logits_h = nullptr; size_t logits_h_floats = 0;
     cudaStream_t s_main = nullptr, s_mlp = nullptr;
@@ -309,7 +310,7 @@ void b200_falcon_free(b200_falcon * f) {
     wplanes_free(f->tok_emb); wplanes_free(f->lm_head);
     cudaFree(f->lnf_g); cudaFree(f->lnf_b); cudaFree(f->k_cache); cudaFree(f->v_cache);
     cudaFree(f->inp); cudaFree(f->qkv); cudaFree(f->att); cudaFree(f->ao); cudaFree(f->up); cudaFree(f->dn); cudaFree(f->logits);
-    cudaFree(f->actq_mem); cudaFree(f->xh_a); cudaFree(f->xh_b); cudaFree(f->gemm_ws_a); cudaFree(f->gemm_ws_b);
+    cudaFree(f->attn_scratch); cudaFree(f->actq_mem); cudaFree(f->xh_a); cudaFree(f->xh_b); cudaFree(f->gemm_ws_a); cudaFree(f->gemm_ws_b);
     cudaFree(f->tokens_dev); cudaFree(f->n_past_dev);
     cudaFreeHost(f->tokens_h); cudaFreeHost(f->n_past_h); cudaFreeHost(f->logits_h);
     for (int i = 0; i < 2; i++) if (f->graph[i]) cudaGraphExecDestroy(f->graph[i]);
@@ -370,7 +371,10 @@ static void enqueue_eval(b200_falcon * f, int N, int n_past, float theta_scale, 
         AttnParams ap = { f->H, f->HKV, f->D, N, n_past, graph_mode ? f->n_past_dev : nullptr, f->hp.n_ctx, (int64_t) f->QKV };
         const size_t kvoff = (size_t) l * f->hp.n_ctx * f->HKV * f->D;
         launch_rope_kv_append(f->qkv, f->k_cache + kvoff, f->v_cache + kvoff, ap, theta_scale, sa);             // :2229-2281
-        launch_attention(f->qkv, f->k_cache + kvoff, f->v_cache + kvoff, f->att, E, ap, nullptr, sa);           // :2285-2366
+        if (N > 1 && !graph_mode) {
+            if (!f->attn_scratch) B200_CUDA_CHECK(cudaMalloc(&f->attn_scratch, attention_prefill_scratch_bytes(f->H, f->hp.n_batch, f->hp.n_ctx)));
+            launch_attention_prefill(f->qkv, f->k_cache + kvoff, f->v_cache + kvoff, f->att, E, ap, f->attn_scratch, sa); f->launches++;
+        } else launch_attention(f->qkv, f->k_cache + kvoff, f->v_cache + kvoff, f->att, E, ap, nullptr, sa);     // :2285-2366
         launch_quantize_act(f->att, E, xatt, sa);
         f->launches += 3;
         mm(f, L.wo, xatt, N, f->ao, E, EPI_NONE, nullptr, nullptr, f->xh_a, f->gemm_ws_a, sa);                  // :2370

@@ -127,6 +127,8 @@ struct GemmArgs {
     int N, NT;            // tokens; tokens rounded up to 16 (accumulator columns used)
     int box_rows;         // rows of one TMA box of the activation tile (<= 256)
     int epi_gelu;
+    int ksplit;           // K is split over gridDim.y CTAs; > 1: partial tiles are added into a zeroed Y with atomics
+                          // (ksplit == 2 keeps the result deterministic: 0 + a + b is the same in either order)
 };
 
 template <int TYPE>
@@ -142,7 +144,8 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.x * BM;
-    const int KB = a.W.K / BK;
+    const int KBT = a.W.K / BK;                                            // K blocks in total; this CTA owns [kb0, kb0 + KB)
+    const int kb0 = (int) ((int64_t) KBT * blockIdx.y / a.ksplit), KB = (int) ((int64_t) KBT * (blockIdx.y + 1) / a.ksplit) - kb0;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < SA; s++) { mbar_init(a_full + s, PRODUCER_THREADS); mbar_init(a_empty + s, 1); }
@@ -166,8 +169,8 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
                 const int s = kb % SB;
                 if (kb >= SB) mbar_wait(b_empty + s, (uint32_t) ((kb / SB - 1) & 1));
                 mbar_expect_tx(b_full + s, (uint32_t) b_stage);
-                tma_load_2d(sB + (size_t) s * b_stage, &xmap, kb * BK, 0, b_full + s);
-                if (a.NT > 256) tma_load_2d(sB + (size_t) s * b_stage + a.box_rows * 128, &xmap, kb * BK, 256, b_full + s);
+                tma_load_2d(sB + (size_t) s * b_stage, &xmap, (kb0 + kb) * BK, 0, b_full + s);
+                if (a.NT > 256) tma_load_2d(sB + (size_t) s * b_stage + a.box_rows * 128, &xmap, (kb0 + kb) * BK, 256, b_full + s);
             }
         }
     } else if (warp == 1) {
@@ -198,14 +201,14 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
         const size_t row = (size_t) min(m0 + r, a.W.M - 1);                // rows past M are computed from row M-1 and never stored
         uint8_t * my_row = nullptr;
         RawQ4K raw;
-        if (TYPE == T_Q4_K) raw = load_q4k(a.W, row, 0, h);
+        if (TYPE == T_Q4_K) raw = load_q4k(a.W, row, kb0, h);
         for (int kb = 0; kb < KB; kb++) {
             const int s = kb % SA;
             Chunks ch;
             if (TYPE == T_Q4_K) {
                 ch = dequant_q4k(raw);
-                if (kb + 1 < KB) raw = load_q4k(a.W, row, kb + 1, h);      // next block's bytes are in flight while this one is stored
-            } else ch = dequant_generic(a.W, row, kb * BK, h);
+                if (kb + 1 < KB) raw = load_q4k(a.W, row, kb0 + kb + 1, h);      // next block's bytes are in flight while this one is stored
+            } else ch = dequant_generic(a.W, row, (kb0 + kb) * BK, h);
             if (kb >= SA) mbar_wait(a_empty + s, (uint32_t) ((kb / SA - 1) & 1));
             my_row = sA + (size_t) s * A_STAGE + r * 128;
             const int sw = r & 7;
@@ -234,7 +237,8 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
                         float y = __uint_as_float(v[j]);
                         if (a.epi_gelu) { const float f = __half2float(__float2half_rn(y));
                             y = __half2float(__float2half_rn(0.5f * f * (1.0f + tanhf(0.79788456080286535587989211986876f * f * (1.0f + 0.044715f * f * f))))); }
-                        a.Y[(size_t) n * a.y_stride + m] = y;              // a warp writes 32 consecutive m: 128 B per store
+                        if (a.ksplit > 1) atomicAdd(a.Y + (size_t) n * a.y_stride + m, y);
+                        else a.Y[(size_t) n * a.y_stride + m] = y;         // a warp writes 32 consecutive m: 128 B per store
                     }
                 }
             }
@@ -261,7 +265,7 @@ template <int TYPE>
 void launch_typed(const CUtensorMap & map, const GemmArgs & a, size_t smem, cudaStream_t stream) {
     static bool set = false;
     if (!set) { B200_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<TYPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); set = true; }
-    gemm_tc_kernel<TYPE><<<(a.W.M + BM - 1) / BM, THREADS, smem, stream>>>(map, a);
+    gemm_tc_kernel<TYPE><<<dim3((a.W.M + BM - 1) / BM, a.ksplit), THREADS, smem, stream>>>(map, a);
     B200_CUDA_CHECK(cudaGetLastError());
 }
 
@@ -273,6 +277,10 @@ bool launch_gemm_tc(const WPlanes & W, const __half * X, int64_t x_stride, int N
     GemmArgs a;
     a.W = W; a.Y = Y; a.y_stride = y_stride; a.N = N; a.NT = (N + 15) / 16 * 16; a.epi_gelu = epi_gelu;
     a.box_rows = a.NT > 256 ? 256 : a.NT;
+    // fewer than ~100 row tiles cannot fill 148 SMs: split K in two (deterministic, see GemmArgs::ksplit)
+    const int tiles = (W.M + BM - 1) / BM;
+    a.ksplit = (tiles < 100 && !epi_gelu && W.K / BK >= 8 && !getenv("B200_GEMM_NOSPLIT")) ? 2 : 1;
+    if (a.ksplit > 1) B200_CUDA_CHECK(cudaMemsetAsync(Y, 0, ((size_t) (N - 1) * y_stride + W.M) * sizeof(float), stream));
     CUtensorMap map;
     const cuuint64_t gdim[2] = { (cuuint64_t) W.K, (cuuint64_t) N };
     const cuuint64_t gstr[1] = { (cuuint64_t) x_stride * 2 };

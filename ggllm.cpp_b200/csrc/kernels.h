@@ -56,6 +56,10 @@ void   launch_rope_kv_append(float * qkv, float * k_cache, float * v_cache, cons
 void   launch_attention(const float * qkv, const float * k_cache, const float * v_cache, float * out, int64_t out_stride,
                         const AttnParams & p, float * scratch, cudaStream_t stream);
 size_t attention_scratch_bytes(const AttnParams & p);
+// N > 1 (prompt): tiled two-kernel version with a score scratch matrix (attention_prefill.cu)
+size_t attention_prefill_scratch_bytes(int n_head, int n_tok, int T);
+void   launch_attention_prefill(const float * qkv, const float * k_cache, const float * v_cache, float * out, int64_t out_stride,
+                                const AttnParams & p, float * scratch, cudaStream_t stream);
 
 // ---- gemm.cu : Y[n][m] = sum_k W[m][k] * X[n][k], N large (prompt), tcgen05 tensor cores
 void   launch_mmq_gemm(const WPlanes & W, const __half * X, int64_t x_stride, int N, float * Y, int64_t y_stride,

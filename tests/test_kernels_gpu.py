@@ -183,13 +183,14 @@ def test_rope_neox_ntk(gpu, orc, n_ctx_rope, n_past):
     assert np.allclose(got, want, rtol=0, atol=3e-6 * np.abs(x).max())
 
 
-@pytest.mark.parametrize("n_head,n_head_kv,n_tok,n_past", [(4, 2, 1, 0), (4, 2, 1, 37), (8, 1, 1, 200), (16, 8, 5, 11), (4, 2, 7, 0)])
+@pytest.mark.parametrize("n_head,n_head_kv,n_tok,n_past", [(4, 2, 1, 0), (4, 2, 1, 37), (8, 1, 1, 200), (16, 8, 5, 11), (4, 2, 7, 0),
+                                                           (32, 2, 40, 90), (71, 1, 3, 60), (16, 8, 100, 0)])
 def test_attention(gpu, orc, n_head, n_head_kv, n_tok, n_past):
     """rope + KV append + causal GQA attention vs a numpy restatement built from the oracle's rope and softmax"""
     rng = np.random.default_rng(6)
     hd, n_ctx = 64, 256
     QKV = (n_head + 2 * n_head_kv) * hd
-    kc = np.zeros((n_ctx, n_head_kv, hd), np.float32)
+    kc = np.zeros((n_ctx, n_head_kv, hd), np.float32)   # decode (n_tok == 1) and prefill (n_tok > 1) kernels
     vc = np.zeros_like(kc)
     kc[:n_past] = rng.standard_normal((n_past, n_head_kv, hd)).astype(np.float32)
     vc[:n_past] = rng.standard_normal((n_past, n_head_kv, hd)).astype(np.float32)
