@@ -220,17 +220,37 @@ def main():
     e2e_s = time.perf_counter() - t0
     clocks = sampler.stop()
 
+    # ---- N > 1 only: strictly autoregressive single stream.  The two regions above are teacher-forced, so rank r can
+    # start token i+1 while rank r+1 still works on token i (what falcon_perplexity-style scoring allows).  Generation
+    # cannot: the next token id exists only after the last stage has produced logits.  Here the last rank "samples"
+    # (argmax) and broadcasts the token id to everybody before the next step may start.
+    auto_ms = None
+    if dist is not None:
+        import torch
+        tok = torch.zeros(1, dtype=torch.int32, device="cuda")
+        n_auto = min(args.steps, 32)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(n_auto):
+            lg = f.eval(np.array([int(tok.item()) % hp["n_vocab"]], np.int32), pos, rope)
+            if rank == world - 1:
+                tok[0] = int(np.argmax(lg[0]))
+            dist.broadcast(tok, src=world - 1)
+            pos += 1
+        barrier()
+        auto_ms = (time.perf_counter() - t0) * 1e3 / n_auto
+
     # ---- dominant kernel alone (roofline): every resident mat-vec back to back, CUDA events
     mv_ms, mv_n, mv_bytes = f.profile_matvec(reps=3)
 
     if dist is not None:
         import torch
-        t = torch.tensor([dev_ms, e2e_s * 1e3, t_wall * 1e3, mv_ms], device="cuda")
+        t = torch.tensor([dev_ms, e2e_s * 1e3, t_wall * 1e3, auto_ms], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dev_ms, e2e_ms, wall_ms, mv_ms = [float(v) for v in t.tolist()]
-        agg = torch.tensor([float(mv_bytes), float(mv_n), float(f.weight_bytes()), float(launches)], device="cuda", dtype=torch.float64)
+        dev_ms, e2e_ms, wall_ms, auto_ms = [float(v) for v in t.tolist()]
+        agg = torch.tensor([float(f.weight_bytes()), float(launches)], device="cuda", dtype=torch.float64)
         dist.all_reduce(agg, op=dist.ReduceOp.SUM)
-        mv_bytes, mv_n, weight_bytes, launches = [float(v) for v in agg.tolist()]
+        weight_bytes, launches = [float(v) for v in agg.tolist()]      # the roofline probe stays per GPU (rank 0's own matrices)
     else:
         e2e_ms, wall_ms, weight_bytes = e2e_s * 1e3, t_wall * 1e3, float(f.weight_bytes())
     if rank != 0:
@@ -241,6 +261,10 @@ def main():
     kv_bytes = hp["n_layer"] * 2 * (pos - args.steps) * hp["n_head_kv"] * 64 * 4
     step_bytes = weight_bytes + kv_bytes
     ach = mv_bytes / (mv_ms / 1e3) / 1e9
+    if auto_ms is not None:
+        config["decode_dependency"] = ("value / e2e: teacher-forced token ids, so consecutive tokens overlap across pipeline stages; "
+                                       "autoregressive_tok_s: strict single stream (last rank broadcasts the argmax token before the next step)")
+        config["autoregressive_tok_s"] = 1e3 / auto_ms
     out = {"metric": METRIC, "value": value, "unit": "tok/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": warmup,
            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong" if world > 1 else "weak", "vs_baseline": None,
            "dtype": "int8 x int4 block dots (dp4a), fp32 accumulate; f32 KV/attention", "data": "synthetic", "config": config,
@@ -253,8 +277,8 @@ def main():
                         "launches_timed": int(mv_n), "avg_launch_us": mv_ms * 1e3 / max(mv_n, 1), "algorithmic_bytes_per_launch": mv_bytes / max(mv_n, 1),
                         "how": "all resident mat-vecs (4 per layer + lm_head) launched back to back x3 on the eval stream, CUDA events around the region; "
                                "each launch reads a different matrix, one pass = 23.2 GB >> L2",
-                        "step_achieved_GBs": step_bytes * value / 1e9, "step_frac": step_bytes * value / 1e9 / peak,
-                        "step_bytes": step_bytes, "step_roofline_tok_s": peak * 1e9 / step_bytes},
+                        "step_achieved_GBs_per_gpu": step_bytes * value / 1e9 / world, "step_frac": step_bytes * value / 1e9 / world / peak,
+                        "step_bytes": step_bytes, "step_roofline_tok_s_per_gpu": peak * 1e9 / step_bytes},
            "wall_ms_per_step": wall_ms / args.steps}
     if world == 1 and not args.no_cpu_baseline:
         try:
