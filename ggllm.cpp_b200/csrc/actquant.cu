@@ -31,6 +31,7 @@ void actq_bind(ActQ & A, int t, int K, int N, void * base) {
 
 template <int TYPE>
 __global__ void __launch_bounds__(256) quantize_act_kernel(const float * __restrict__ x, int64_t x_stride, ActQ A) {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const int lane = threadIdx.x & 31;
     const int64_t chunk = ((int64_t) blockIdx.x * blockDim.x + threadIdx.x);     // index of this lane's 8-value chunk
     const int64_t chunks_per_row = A.K / 8;

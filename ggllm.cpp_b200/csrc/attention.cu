@@ -26,6 +26,8 @@ __device__ __forceinline__ float exp_f16lut(float v) {      // table_exp_f16[f16
 __global__ void __launch_bounds__(ATT_THREADS) attention_kernel(const float * __restrict__ qkv, const float * __restrict__ kc, const float * __restrict__ vc,
                                                                float * __restrict__ out, int64_t out_stride, AttnParams p) {
     extern __shared__ __align__(16) float sm[];
+    trace_begin(p.trace);
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // wo's mat-vec may start prefetching its weights
     const int h = blockIdx.x, t = blockIdx.y, D = p.head_dim;
     const int n_past = p.n_past_dev ? *p.n_past_dev : p.n_past;
     const int T = n_past + t + 1;                            // keys visible to this query (causal)
@@ -80,6 +82,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_kernel(const float * __
         for (int g = 1; g < ngrp; g++) r += part[g * D + threadIdx.x];
         out[(size_t) t * out_stride + (size_t) h * D + threadIdx.x] = r;
     }
+    trace_end(p.trace);
 }
 
 size_t attention_scratch_bytes(const AttnParams &) { return 0; }
@@ -92,9 +95,11 @@ void launch_attention(const float * qkv, const float * k_cache, const float * v_
     const int t_max = p.n_past_dev ? p.n_ctx : p.n_past + p.n_tok;
     const size_t smem = (size_t) (p.head_dim + t_max) * sizeof(float);
     static bool set = false;
-    if (!set) { B200_CUDA_CHECK(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); set = true; }
+    if (!set) { B200_CUDA_CHECK(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        B200_CUDA_CHECK(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, B200_CARVEOUT)); set = true; }
     B200_ASSERT(smem <= 200 * 1024);
     dim3 grid((unsigned) p.n_head, (unsigned) p.n_tok);
-    attention_kernel<<<grid, ATT_THREADS, smem, stream>>>(qkv, k_cache, v_cache, out, out_stride, p);
+    AttnParams pt = p; pt.trace = b200_trace_slot("attention");
+    attention_kernel<<<grid, ATT_THREADS, smem, stream>>>(qkv, k_cache, v_cache, out, out_stride, pt);
     B200_CUDA_CHECK(cudaGetLastError());
 }

@@ -3,6 +3,7 @@
 #include "../../include/ggml_b200.h"
 #include <mutex>
 #include <cstring>
+#include <vector>
 
 struct b200_weight { WPlanes W; };
 struct b200_actq { ActQ A; void * base; size_t bytes; };
@@ -15,7 +16,36 @@ cudaStream_t b200_current_stream() { return g_stream; }
 void launch_gemm_simt(const WPlanes & W, const __half * X, int64_t x_stride, int N, float * Y, int64_t y_stride, int epi_gelu, cudaStream_t stream);
 bool launch_gemm_tc(const WPlanes & W, const __half * X, int64_t x_stride, int N, float * Y, int64_t y_stride, int epi_gelu, cudaStream_t stream);
 
+static unsigned long long * g_trace = nullptr; static int g_trace_cap = 0, g_trace_n = 0; static char g_trace_names[4096][24];
+unsigned long long * b200_trace_slot(const char * name) {
+    if (!g_trace || g_trace_n >= g_trace_cap) return nullptr;
+    strncpy(g_trace_names[g_trace_n], name, 23); g_trace_names[g_trace_n][23] = 0;
+    return g_trace + 2 * (g_trace_n++);
+}
+
 extern "C" {
+
+// debugging aid: per-kernel device timeline.  enable(n) allocates n slots and makes every instrumented launch claim one;
+// reset() re-arms the slots (call before replaying a captured graph); dump() copies {start, end} ns pairs and names out.
+void b200_trace_enable(int n_slots) {
+    if (g_trace) { cudaFree(g_trace); g_trace = nullptr; }
+    g_trace_cap = n_slots > 4096 ? 4096 : n_slots; g_trace_n = 0;
+    if (g_trace_cap > 0) B200_CUDA_CHECK(cudaMalloc(&g_trace, (size_t) g_trace_cap * 16));
+}
+void b200_trace_reset(void * stream) {
+    if (!g_trace) return;
+    std::vector<unsigned long long> init((size_t) g_trace_cap * 2);
+    for (int i = 0; i < g_trace_cap; i++) { init[2 * i] = ~0ull; init[2 * i + 1] = 0; }
+    B200_CUDA_CHECK(cudaMemcpy(g_trace, init.data(), init.size() * 8, cudaMemcpyHostToDevice));
+    (void) stream;
+}
+int b200_trace_dump(unsigned long long * out, char * names, int max_slots) {
+    const int n = g_trace_n < max_slots ? g_trace_n : max_slots;
+    B200_CUDA_CHECK(cudaDeviceSynchronize());
+    if (n > 0) B200_CUDA_CHECK(cudaMemcpy(out, g_trace, (size_t) n * 16, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < n; i++) memcpy(names + 24 * i, g_trace_names[i], 24);
+    return n;
+}
 
 int b200_device_count(void) {
     int n = 0;
@@ -135,6 +165,14 @@ void b200_mul_mat(const b200_weight * w, const float * x, int64_t x_stride, int 
     }
 }
 
+// y = W * Q(LayerNorm((ra + rb) + x) * gamma + beta)   (gamma == NULL: y = W * Q(x)), N = 1: the fused decode mat-vec
+int b200_mul_mat_vec_fused(const b200_weight * w, const float * x, const float * ra, const float * rb, const float * gamma, const float * beta,
+                           float * x_out, float * y, int epilogue) {
+    FastX X{}; X.mode = gamma ? 2 : 1; X.N = 1; X.x = x; X.x_stride = w->W.K; X.ra = ra; X.rb = rb; X.gamma = gamma; X.beta = beta; X.x_out = x_out;
+    MmvEpilogue e = { epilogue, nullptr, nullptr };
+    return launch_mmv_fast_x(w->W, X, y, w->W.M, e, g_stream) ? 1 : 0;
+}
+
 int b200_mul_mat_f16(const b200_weight * w, const void * x_f16, int64_t x_stride, int N, float * y, int64_t y_stride, int epi_gelu, int impl) {
     if (impl == 0) { launch_gemm_simt(w->W, (const __half *) x_f16, x_stride, N, y, y_stride, epi_gelu, g_stream); return 1; }
     return launch_gemm_tc(w->W, (const __half *) x_f16, x_stride, N, y, y_stride, epi_gelu, g_stream) ? 1 : 0;
@@ -147,7 +185,7 @@ void b200_rope_neox(float * x, int n_tok, int n_head, int head_dim, int64_t tok_
     launch_rope_neox(x, n_tok, n_head, head_dim, tok_stride, n_past, nullptr, rope_theta_scale_host(head_dim, n_ctx_rope, dyn, alpha, freq_base), g_stream);
 }
 void b200_attention(float * qkv, float * kc, float * vc, float * out, int n_head, int n_head_kv, int head_dim, int n_tok, int n_past, int n_ctx, int n_ctx_rope) {
-    AttnParams p = { n_head, n_head_kv, head_dim, n_tok, n_past, nullptr, n_ctx, (int64_t) (n_head + 2 * n_head_kv) * head_dim };
+    AttnParams p = { n_head, n_head_kv, head_dim, n_tok, n_past, nullptr, n_ctx, (int64_t) (n_head + 2 * n_head_kv) * head_dim, nullptr };
     launch_rope_kv_append(qkv, kc, vc, p, rope_theta_scale_host(head_dim, n_ctx_rope ? n_ctx_rope : n_ctx, 1, 2.0f, 0), g_stream);   // libfalcon.cpp:2231-2234
     if (n_tok > 1) {
         float * sc = (float *) scratch(attention_prefill_scratch_bytes(n_head, n_tok, n_past + n_tok));

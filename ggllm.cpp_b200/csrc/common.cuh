@@ -34,6 +34,11 @@ enum : int {
 
 static inline size_t round_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// One L1/shared-memory split (percent of shared) for every kernel of the decode step.  An SM cannot host kernels that
+// ask for different carve-outs at the same time, so without this the small attention kernels wait for the big
+// mat-vec of the other stream to drain (measured, profiles/r1_decode_timeline.md).  25 % = 57 KB shared, rest L1.
+#define B200_CARVEOUT 25
+
 #ifdef __CUDACC__
 
 // streaming 16-byte load of weight data: read-only path, do not allocate in L1 (each byte is used once)
@@ -109,4 +114,11 @@ __device__ __forceinline__ void tma_load_1d(void * smem_dst, const void * gmem_s
                  :: "r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
+// ---- optional device timeline (tools/trace_decode.py): every instrumented kernel gets a slot {min start, max end} in ns
+__device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+__device__ __forceinline__ void trace_begin(unsigned long long * slot) { if (slot && threadIdx.x == 0) atomicMin(slot, gtimer()); }
+__device__ __forceinline__ void trace_end(unsigned long long * slot) { if (slot && threadIdx.x == 0) atomicMax(slot + 1, gtimer()); }
+
 #endif // __CUDACC__
+
+unsigned long long * b200_trace_slot(const char * name);     // c_api.cu: next slot if tracing is on, else nullptr

@@ -69,6 +69,7 @@ struct b200_falcon {
     __half * xh_a = nullptr, * xh_b = nullptr;      // fp16 GEMM operands, one per branch
     void * gemm_ws_a = nullptr, * gemm_ws_b = nullptr; size_t gemm_ws_bytes = 0;
     float * attn_scratch = nullptr;
+    float * inp2 = nullptr, * ao2 = nullptr, * dn2 = nullptr;      // ping-pong partners of inp / ao / dn for the fused decode path
     int32_t * tokens_dev = nullptr; int * n_past_dev = nullptr;
     int32_t * tokens_h = nullptr; int * n_past_h = nullptr; float * logits_h = nullptr; size_t logits_h_floats = 0;
     cudaStream_t s_main = nullptr, s_mlp = nullptr;
@@ -172,6 +173,7 @@ b200_falcon * b200_falcon_create(const b200_falcon_params * p) {
     B200_CUDA_CHECK(cudaMalloc(&f->att, NB * f->E * 4)); B200_CUDA_CHECK(cudaMalloc(&f->ao, NB * f->E * 4));
     B200_CUDA_CHECK(cudaMalloc(&f->up, NB * f->FF * 4)); B200_CUDA_CHECK(cudaMalloc(&f->dn, NB * f->E * 4));
     B200_CUDA_CHECK(cudaMalloc(&f->logits, NB * f->V * 4));
+    B200_CUDA_CHECK(cudaMalloc(&f->inp2, (size_t) f->E * 4)); B200_CUDA_CHECK(cudaMalloc(&f->ao2, (size_t) f->E * 4)); B200_CUDA_CHECK(cudaMalloc(&f->dn2, (size_t) f->E * 4));
     B200_CUDA_CHECK(cudaMalloc(&f->tokens_dev, NB * 4)); B200_CUDA_CHECK(cudaMalloc(&f->n_past_dev, 4));
     B200_CUDA_CHECK(cudaMallocHost(&f->tokens_h, NB * 4)); B200_CUDA_CHECK(cudaMallocHost(&f->n_past_h, 4));
     f->logits_h_floats = (size_t) f->V; B200_CUDA_CHECK(cudaMallocHost(&f->logits_h, f->logits_h_floats * 4));
@@ -310,7 +312,7 @@ void b200_falcon_free(b200_falcon * f) {
     wplanes_free(f->tok_emb); wplanes_free(f->lm_head);
     cudaFree(f->lnf_g); cudaFree(f->lnf_b); cudaFree(f->k_cache); cudaFree(f->v_cache);
     cudaFree(f->inp); cudaFree(f->qkv); cudaFree(f->att); cudaFree(f->ao); cudaFree(f->up); cudaFree(f->dn); cudaFree(f->logits);
-    cudaFree(f->attn_scratch); cudaFree(f->actq_mem); cudaFree(f->xh_a); cudaFree(f->xh_b); cudaFree(f->gemm_ws_a); cudaFree(f->gemm_ws_b);
+    cudaFree(f->inp2); cudaFree(f->ao2); cudaFree(f->dn2); cudaFree(f->attn_scratch); cudaFree(f->actq_mem); cudaFree(f->xh_a); cudaFree(f->xh_b); cudaFree(f->gemm_ws_a); cudaFree(f->gemm_ws_b);
     cudaFree(f->tokens_dev); cudaFree(f->n_past_dev);
     cudaFreeHost(f->tokens_h); cudaFreeHost(f->n_past_h); cudaFreeHost(f->logits_h);
     for (int i = 0; i < 2; i++) if (f->graph[i]) cudaGraphExecDestroy(f->graph[i]);
@@ -338,8 +340,67 @@ static void mm(b200_falcon * f, const WPlanes & W, const ActQ & A, int N, float 
     }
 }
 
+// ---- decode (N == 1) with everything that is not a mat-vec folded into the mat-vec kernels' prologues / epilogues:
+// residual adds + LayerNorm + activation quantisation in the prologue of qkv / ffn_up / lm_head (FastX mode 2),
+// activation quantisation in the prologue of wo / ffn_down (mode 1), GELU in ffn_up's epilogue.  6 kernels per layer:
+//   s_main: qkv -> rope+kv append -> attention -> wo          s_mlp: ffn_up(+GELU) -> ffn_down
+static bool fused_decode_ok(const b200_falcon * f) {
+    if (getenv("B200_NO_FUSED_DECODE")) return false;
+    for (const auto & L : f->layers)
+        if (!mmv_fast_supports(L.wo.type, L.wo.K, 1) || !mmv_fast_supports(L.down.type, L.down.K, 1)) return false;
+    return f->act_type >= 0;
+}
+static void enqueue_decode_fused(b200_falcon * f, int n_past, float theta_scale, bool graph_mode) {
+    cudaStream_t sa = f->s_main, sb = f->s_mlp;
+    const int E = f->E;
+    const bool dual = f->hp.falcon_type == 40;
+    ensure_actq(f);
+    ActQ xa = f->xa, xm = f->xm, xf = f->xf; xa.N = xm.N = xf.N = 1;
+    if (f->first) { launch_dequant_rows(f->tok_emb, f->tokens_dev, 1, f->inp, E, sa); f->launches++; }
+    else B200_NCCL_CHECK(nccl().Recv(f->inp, (size_t) E, ncclFloat, f->hp.rank - 1, f->comm, sa));
+    const MmvEpilogue none = { EPI_NONE, nullptr, nullptr }, gelu = { EPI_GELU, nullptr, nullptr };
+    // debugging aid for timing experiments only (results are wrong when anything is skipped): B200_DBG_SKIP=ln,qkv,attn,up,down,wo
+    const char * dbg = getenv("B200_DBG_SKIP");
+    auto skip = [&](const char * what) { return dbg && strstr(dbg, what) != nullptr; };
+    // All four mat-vecs of a layer go back to back on ONE stream (each is launched with programmatic dependent launch,
+    // so its weight prefetch overlaps the previous one's tail); the small attention kernels run beside ffn_up on the
+    // second stream:   s_main: LN -> qkv -> ffn_up(+GELU) -> ffn_down -> wo        s_mlp: rope+kv append -> attention
+    for (int l = 0; l < f->NL; l++) {
+        const Layer & L = f->layers[l];
+        const float * ra = l > 0 ? f->dn : nullptr, * rb = l > 0 ? f->ao : nullptr;
+        if (skip("ln")) {}
+        else if (dual) launch_layernorm_q(f->inp, E, ra, rb, E, L.ln_attn_g, L.ln_attn_b, &xa, L.ln_mlp_g, L.ln_mlp_b, &xm, E, 1, sa);
+        else      launch_layernorm_q(f->inp, E, ra, rb, E, L.ln_mlp_g, L.ln_mlp_b, &xm, nullptr, nullptr, nullptr, E, 1, sa);
+        if (!skip("qkv")) launch_mmv(L.wqkv, dual ? xa : xm, f->qkv, f->QKV, none, sa);                         // libfalcon.cpp:2192
+        B200_CUDA_CHECK(cudaEventRecord(f->e_fork, sa));
+        B200_CUDA_CHECK(cudaStreamWaitEvent(sb, f->e_fork, 0));
+        AttnParams ap = { f->H, f->HKV, f->D, 1, n_past, graph_mode ? f->n_past_dev : nullptr, f->hp.n_ctx, (int64_t) f->QKV, nullptr };
+        const size_t kvoff = (size_t) l * f->hp.n_ctx * f->HKV * f->D;
+        if (!skip("attn")) {
+        launch_rope_kv_append(f->qkv, f->k_cache + kvoff, f->v_cache + kvoff, ap, theta_scale, sb);             // :2229-2281
+        launch_attention(f->qkv, f->k_cache + kvoff, f->v_cache + kvoff, f->att, E, ap, nullptr, sb);           // :2285-2366
+        }
+        B200_CUDA_CHECK(cudaEventRecord(f->e_join, sb));
+        if (!skip("up")) launch_mmv(L.up, xm, f->up, f->FF, gelu, sa);                                           // :2389-2392
+        FastX xd{}; xd.mode = 1; xd.N = 1; xd.x = f->up; xd.x_stride = f->FF;
+        if (!skip("down")) B200_ASSERT(launch_mmv_fast_x(L.down, xd, f->dn, E, none, sa));                      // :2394, activation quantised in the prologue
+        B200_CUDA_CHECK(cudaStreamWaitEvent(sa, f->e_join, 0));
+        FastX xo{}; xo.mode = 1; xo.N = 1; xo.x = f->att; xo.x_stride = E;
+        if (!skip("wo")) B200_ASSERT(launch_mmv_fast_x(L.wo, xo, f->ao, E, none, sa));                          // :2370
+        f->launches += 7;
+    }
+    if (f->last) {
+        launch_layernorm_q(f->inp, E, f->NL > 0 ? f->dn : nullptr, f->NL > 0 ? f->ao : nullptr, E, f->lnf_g, f->lnf_b, &xf, nullptr, nullptr, nullptr, E, 1, sa);   // :2399-2400, 2422-2431
+        launch_mmv(f->lm_head, xf, f->logits, f->V, none, sa); f->launches += 2;                                // :2440
+    } else {
+        if (f->NL > 0) { launch_add3(f->dn, f->ao, f->inp, f->inp, E, sa); f->launches++; }
+        B200_NCCL_CHECK(nccl().Send(f->inp, (size_t) E, ncclFloat, f->hp.rank + 1, f->comm, sa));
+    }
+}
+
 // Enqueue one eval of N tokens on (s_main, s_mlp).  Device scalars carry n_past when `graph_mode`.
 static void enqueue_eval(b200_falcon * f, int N, int n_past, float theta_scale, bool graph_mode, int logits_rows_from) {
+    if (N == 1 && fused_decode_ok(f)) { enqueue_decode_fused(f, n_past, theta_scale, graph_mode); return; }
     cudaStream_t sa = f->s_main, sb = f->s_mlp;
     const int E = f->E, FF = f->FF;
     const bool dual = f->hp.falcon_type == 40;
@@ -368,7 +429,7 @@ static void enqueue_eval(b200_falcon * f, int N, int n_past, float theta_scale, 
         B200_CUDA_CHECK(cudaEventRecord(f->e_join, sb));
         // attention branch on s_main
         mm(f, L.wqkv, attn_in, N, f->qkv, f->QKV, EPI_NONE, nullptr, nullptr, f->xh_a, f->gemm_ws_a, sa);      // :2192
-        AttnParams ap = { f->H, f->HKV, f->D, N, n_past, graph_mode ? f->n_past_dev : nullptr, f->hp.n_ctx, (int64_t) f->QKV };
+        AttnParams ap = { f->H, f->HKV, f->D, N, n_past, graph_mode ? f->n_past_dev : nullptr, f->hp.n_ctx, (int64_t) f->QKV, nullptr };
         const size_t kvoff = (size_t) l * f->hp.n_ctx * f->HKV * f->D;
         launch_rope_kv_append(f->qkv, f->k_cache + kvoff, f->v_cache + kvoff, ap, theta_scale, sa);             // :2229-2281
         if (N > 1 && !graph_mode) {
@@ -463,6 +524,7 @@ void b200_falcon_decode_dev(b200_falcon * f, const int32_t * token_dev, int n_pa
     // as a kernel argument, so the host may run ahead by any number of steps)
     set_i32_kernel<<<1, 1, 0, f->s_main>>>(f->n_past_dev, n_past);
     if (f->first && token_dev) B200_CUDA_CHECK(cudaMemcpyAsync(f->tokens_dev, token_dev, 4, cudaMemcpyDeviceToDevice, f->s_main));
+    if (getenv("B200_NO_GRAPH")) { f->launches = 0; enqueue_eval(f, 1, 0, theta, true, 0); return; }   // timing experiments: eager launches
     B200_CUDA_CHECK(cudaGraphLaunch(f->graph[0], f->s_main));
     f->launches = f->graph_launches;
 }

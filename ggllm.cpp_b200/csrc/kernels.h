@@ -22,6 +22,19 @@ struct MmvEpilogue { int kind; const float * r1; const float * r2; };       // A
 void   launch_mmv(const WPlanes & W, const ActQ & A, float * y, int64_t y_stride, MmvEpilogue epi, cudaStream_t stream);
 void   launch_mmv_f(const WPlanes & W, const float * x, int64_t x_stride, int N, float * y, int64_t y_stride, cudaStream_t stream); // f16/f32 weights
 
+// mmv_fast.cu: the tuned kernel (Q4_K, Q4_0) can take its activation row in three forms, see FastX there
+struct FastX {
+    int mode;                   // 0 quantised ActQ | 1 fp32 row, quantised in the prologue | 2 fp32 row, [+residuals] + LayerNorm + quantise in the prologue
+    int N;                      // activation rows (columns of Y)
+    ActQ A;                     // mode 0
+    const float * x; int64_t x_stride;          // modes 1, 2
+    const float * ra, * rb;     // mode 2, optional: x = (ra + rb) + x first
+    const float * gamma, * beta;
+    float * x_out;              // mode 2, optional: CTA 0 stores the updated x here
+};
+bool   launch_mmv_fast_x(const WPlanes & W, const FastX & X, float * y, int64_t y_stride, MmvEpilogue e, cudaStream_t stream);
+bool   mmv_fast_supports(int wtype, int K, int mode);
+
 // ---- ops.cu
 void   launch_layernorm(const float * x, int64_t x_stride, const float * g, const float * b, float * y, int64_t y_stride,
                         int n, int rows, cudaStream_t stream);              // y = norm(x)*g + b ; g,b may be null (plain ggml_norm)
@@ -49,6 +62,7 @@ struct AttnParams {
     const int * n_past_dev;     // optional device scalar (CUDA-graph replay)
     int n_ctx;                  // KV capacity (row count of the cache)
     int64_t qkv_stride;         // floats between consecutive tokens in the fused QKV buffer
+    unsigned long long * trace; // optional timeline slot (debug)
 };
 // fused: rope(Q), rope(K) -> K cache append, V cache append      (libfalcon.cpp:2229-2281)
 void   launch_rope_kv_append(float * qkv, float * k_cache, float * v_cache, const AttnParams & p, float theta_scale, cudaStream_t stream);

@@ -16,7 +16,17 @@
 // Arithmetic is identical to mmv.cu / the CPU's integer block dots (ggml.c:2591-2609, k_quants.c:1999-2055).
 #include "kernels.h"
 
-struct Epi { int kind; const float * r1; const float * r2; };
+struct Epi { int kind; const float * r1; const float * r2; unsigned long long * trace; };
+
+// Where the activation row comes from (FastX, kernels.h):
+//   mode 0: already quantised (ActQ, written by quantize_act / layernorm_q)
+//   mode 1: fp32 row x[K]; every CTA quantises it itself while its first weight rows are in flight
+//   mode 2: fp32 row -> [x = (ra + rb) + x] -> LayerNorm(gamma, beta) -> quantise, all in the prologue (J == 1 only):
+//           the residual adds that close the previous layer (libfalcon.cpp:2399-2400), the LayerNorm
+//           (ggml.c:10568-10595 + libfalcon.cpp:2166-2185) and the mat-mul's INIT pass (ggml.c:11462-11476) without a
+//           kernel of their own.  CTA 0 writes the updated residual row to x_out.
+// In modes 1/2 the 8 threads that share a Q8_K block hold exactly its 256 values (32 each), so the block maximum is
+// three shuffles away and the int8 codes are produced directly in the registers the dot products read.
 
 __device__ __forceinline__ int dot16(const uint32_t w0, const uint32_t w1, const uint32_t w2, const uint32_t w3, const uint4 x) {
     int s = dp4a_us(w0, (int) x.x, 0); s = dp4a_us(w1, (int) x.y, s); s = dp4a_us(w2, (int) x.z, s); return dp4a_us(w3, (int) x.w, s);
@@ -46,6 +56,43 @@ template <> struct FX<T_Q4_K> {
         r.xd = A.d[(size_t) n * (A.K / 256) + b];
         return r;
     }
+    // element offsets (in the row) of the two 16-value segments piece g multiplies
+    __device__ static void seg(int g, int & ea, int & eb) { const int b = g >> 3, pc = g & 7; ea = b * 256 + 64 * (pc >> 1) + 16 * (pc & 1); eb = ea + 32; }
+    // v[0..16) = segment a, v[16..32) = segment b of this thread's piece; the 8 lanes of a block quantise it together
+    // (quantize_row_q8_K_reference, k_quants.c:899-934: signed value of largest magnitude, first one on ties)
+    __device__ static XR quant_x(const float (&v)[32], int g, int lane) {
+        int ea, eb; seg(g, ea, eb);
+        float amax = 0.f, vmax = 0.f; int imax = 0;
+#pragma unroll
+        for (int i = 0; i < 32; i++) { const float ax = fabsf(v[i]); const int idx = (i < 16 ? ea : eb - 16) + i; if (ax > amax || (ax == amax && ax > 0.f && idx < imax)) { amax = ax; vmax = v[i]; imax = idx; } }
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) {
+            const float oa = __shfl_xor_sync(0xffffffffu, amax, o), ov = __shfl_xor_sync(0xffffffffu, vmax, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, imax, o);
+            if (oa > amax || (oa == amax && oi < imax)) { amax = oa; vmax = ov; imax = oi; }
+        }
+        XR r;
+        const bool zero = amax == 0.f;
+        const float iscale = zero ? 0.f : __fdiv_rn(-128.f, vmax);
+        r.xd = zero ? 0.f : __fdiv_rn(1.f, iscale);
+        int s0 = 0, s1 = 0;
+        uint32_t w[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) {                                         // codes are packed as they are produced: nothing but v[] stays live
+            uint32_t pk = 0;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int q = zero ? 0 : min(127, __float2int_rn(__fmul_rn(iscale, v[4 * i + k])));
+                if (i < 4) s0 += q; else s1 += q;
+                pk |= (uint32_t) (q & 0xff) << (8 * k);
+            }
+            w[i] = pk;
+        }
+        r.xl = make_uint4(w[0], w[1], w[2], w[3]); r.xh = make_uint4(w[4], w[5], w[6], w[7]);
+        r.bs = (s0 & 0xffff) | (s1 << 16);
+        (void) lane;
+        return r;
+    }
     __device__ static WR load_w(const WPlanes & W, size_t row, int g) {
         WR r;
         r.q = ldg_stream_v4(W.p[0] + row * W.stride[0] + (size_t) g * 16);
@@ -73,6 +120,28 @@ template <> struct FX<T_Q4_0> {
         r.xh = *reinterpret_cast<const uint4 *>(xq + g * 32 + 16);
         r.bs = A.bs[(size_t) n * (A.K / 32) + g];
         r.xd = A.d[(size_t) n * (A.K / 32) + g];
+        return r;
+    }
+    __device__ static void seg(int g, int & ea, int & eb) { ea = g * 32; eb = ea + 16; }
+    // a piece is a whole 32-value block: the x86 body of quantize_row_q8_0 (ggml.c:1201-1237), thread-local
+    __device__ static XR quant_x(const float (&v)[32], int, int) {
+        float amax = 0.f;
+#pragma unroll
+        for (int i = 0; i < 32; i++) amax = fmaxf(amax, fabsf(v[i]));
+        const float id = amax != 0.f ? __fdiv_rn(127.f, amax) : 0.f;
+        XR r;
+        r.xd = __half2float(__float2half_rn(__fdiv_rn(amax, 127.f)));
+        int s = 0;
+        uint32_t w[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            uint32_t pk = 0;
+#pragma unroll
+            for (int k = 0; k < 4; k++) { const int q = __float2int_rn(__fmul_rn(v[4 * i + k], id)); s += q; pk |= (uint32_t) (q & 0xff) << (8 * k); }
+            w[i] = pk;
+        }
+        r.xl = make_uint4(w[0], w[1], w[2], w[3]); r.xh = make_uint4(w[4], w[5], w[6], w[7]);
+        r.bs = s;
         return r;
     }
     __device__ static WR load_w(const WPlanes & W, size_t row, int g) {
@@ -124,23 +193,21 @@ template <int G> __device__ __forceinline__ float transpose_reduce(const float (
 // D = rows in flight per thread (register ring), reduced G = min(D, 4) rows at a time.  D * J = 8 pieces = 192 B in
 // flight per thread at all times (>= 96 KB per SM): the ring is refilled one row at a time, right after that row's
 // slot has been consumed, so the depth never drops while a group is being computed.
-template <int TYPE, int NT, int J, int D>
-__global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) mmv_fast_kernel(const WPlanes W, const ActQ A, float * __restrict__ y, int64_t y_stride, const Epi epi) {
+template <int TYPE, int NT, int J, int D, int MODE>
+__global__ void __launch_bounds__(NT, NT == 256 ? (D <= 6 ? 3 : 2) : 1) mmv_fast_kernel(const WPlanes W, const FastX X, float * __restrict__ y, int64_t y_stride, const Epi epi) {
     using T = FX<TYPE>;
-    constexpr int NW = NT / 32, G = D >= 4 ? 4 : D;
+    constexpr int NW = NT / 32, G = (D % 4 == 0) ? 4 : (D % 2 == 0) ? 2 : 1;
     extern __shared__ __align__(16) uint8_t smem[];
     uint64_t * bar = reinterpret_cast<uint64_t *>(smem);
     float * partial = reinterpret_cast<float *>(smem + 16);           // [2][NW][G]
-    int8_t * xq = reinterpret_cast<int8_t *>(smem + 16 + 2 * NW * 4 * 4);
+    double * red = reinterpret_cast<double *>(smem + 16 + 2 * NW * 4 * 4);      // [NW] block reduction scratch (mode 2)
+    int8_t * xq = reinterpret_cast<int8_t *>(smem + 16 + 2 * NW * 4 * 4 + NW * 8);
     const int n = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int P = W.nb * T::PPB;
+    const ActQ & A = X.A;
 
-    if (tid == 0) {
-        mbar_init(bar, 1);
-        mbar_fence_init();
-        mbar_expect_tx(bar, (uint32_t) W.K);
-        tma_load_1d(xq, A.q + (size_t) n * W.K, (uint32_t) W.K, bar);       // activation codes: global -> shared by TMA
-    }
+    trace_begin(epi.trace);
+    if (tid == 0 && MODE == 0) { mbar_init(bar, 1); mbar_fence_init(); }
     // rows [row0, row1) of this CTA, balanced to +-1
     const int per = W.M / gridDim.x, rem = W.M % gridDim.x;
     const int row0 = blockIdx.x * per + min((int) blockIdx.x, rem), row1 = row0 + per + ((int) blockIdx.x < rem ? 1 : 0);
@@ -158,14 +225,90 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) mmv_fast_kernel(const W
         for (int j = 0; j < J; j++) w[s][j] = T::load_w(W, (size_t) row, gidx[j]);
     }
 
-    __syncthreads();                                                          // barrier initialised
-    mbar_wait(bar, 0);
+    // everything above touched only weights; the activation row is produced by the previous kernel(s) of the stream
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     typename T::XR xr[J];
+    if (MODE == 0) {
+        if (tid == 0) {
+            mbar_expect_tx(bar, (uint32_t) W.K);
+            tma_load_1d(xq, A.q + (size_t) n * W.K, (uint32_t) W.K, bar);   // activation codes: global -> shared by TMA
+        }
+        __syncthreads();                                                      // barrier initialised (thread 0 did it before issuing)
+        mbar_wait(bar, 0);
 #pragma unroll
-    for (int j = 0; j < J; j++) xr[j] = T::load_x(xq, A, n, gidx[j]);
+        for (int j = 0; j < J; j++) xr[j] = T::load_x(xq, A, n, gidx[j]);
+    } else {
+        const float * xrow = X.x + (size_t) n * X.x_stride;
+        float mean = 0.f, scale = 1.f;
+#pragma unroll
+        for (int j = 0; j < J; j++) {
+            int ea, eb; T::seg(gidx[j], ea, eb);
+            float v[32];
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const float4 a = *reinterpret_cast<const float4 *>(xrow + ea + 4 * i), b = *reinterpret_cast<const float4 *>(xrow + eb + 4 * i);
+                v[4 * i] = a.x; v[4 * i + 1] = a.y; v[4 * i + 2] = a.z; v[4 * i + 3] = a.w;
+                v[16 + 4 * i] = b.x; v[17 + 4 * i] = b.y; v[18 + 4 * i] = b.z; v[19 + 4 * i] = b.w;
+            }
+            if (MODE == 2 && J == 1) {
+                if (X.ra) {                                                   // x = (ra + rb) + x, libfalcon.cpp:2399-2400
+                    const float * ra = X.ra + (size_t) n * X.x_stride, * rb = X.rb + (size_t) n * X.x_stride;
+#pragma unroll
+                    for (int i = 0; i < 16; i++) { v[i] = __fadd_rn(__fadd_rn(ra[ea + i], rb[ea + i]), v[i]); v[16 + i] = __fadd_rn(__fadd_rn(ra[eb + i], rb[eb + i]), v[16 + i]); }
+                }
+                if (X.x_out && blockIdx.x == 0 && valid[j]) {
+                    float * xo = X.x_out + (size_t) n * X.x_stride;
+#pragma unroll
+                    for (int i = 0; i < 16; i++) { xo[ea + i] = v[i]; xo[eb + i] = v[16 + i]; }
+                }
+                // LayerNorm over the whole row: this CTA's NT threads hold all K values (32 each)
+                double s = 0.0;
+                if (valid[j]) {
+#pragma unroll
+                    for (int i = 0; i < 32; i++) s += (double) v[i];
+                }
+                s = warp_sum_d(s);
+                if (lane == 0) red[warp] = s;
+                __syncthreads();
+                double t = 0.0;
+#pragma unroll
+                for (int wi = 0; wi < NW; wi++) t += red[wi];
+                mean = (float) (t / W.K);
+                __syncthreads();
+                double s2 = 0.0;
+                if (valid[j]) {
+#pragma unroll
+                    for (int i = 0; i < 32; i++) { const float c = __fsub_rn(v[i], mean); s2 += (double) __fmul_rn(c, c); }
+                }
+                s2 = warp_sum_d(s2);
+                if (lane == 0) red[warp] = s2;
+                __syncthreads();
+                t = 0.0;
+#pragma unroll
+                for (int wi = 0; wi < NW; wi++) t += red[wi];
+                scale = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn((float) (t / W.K), 1e-5f)));
+#pragma unroll
+                for (int i = 0; i < 16; i++) {
+                    v[i] = __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(v[i], mean), scale), X.gamma[ea + i]), X.beta[ea + i]);
+                    v[16 + i] = __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(v[16 + i], mean), scale), X.gamma[eb + i]), X.beta[eb + i]);
+                }
+            }
+            if (!valid[j]) {
+#pragma unroll
+                for (int i = 0; i < 32; i++) v[i] = 0.f;
+            }
+            xr[j] = T::quant_x(v, gidx[j], lane);
+        }
+        __syncthreads();                                                      // `partial` / `red` are reused below
+    }
 
     float acc[G];
     for (int base = 0; base < nrows; base += D) {
+        // Programmatic dependent launch: release the next kernel of the stream once this CTA has issued its last weight
+        // loads.  Triggering earlier would park the dependent grid's CTAs at the head of the hardware queue for the whole
+        // duration of this kernel and keep the small attention kernels of the other stream from being scheduled
+        // (measured: profiles/r1_decode_timeline.md).
+        if (base + 2 * D >= nrows) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 #pragma unroll
         for (int s = 0; s < D; s++) {
             float a = 0.f;
@@ -198,6 +341,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) mmv_fast_kernel(const W
             }
         }
     }
+    trace_end(epi.trace);
 }
 
 static int fast_num_sms() {
@@ -206,36 +350,60 @@ static int fast_num_sms() {
     return n;
 }
 
-template <int TYPE, int NT, int J, int D>
-static void launch_cfg(const WPlanes & W, const ActQ & A, float * y, int64_t y_stride, Epi epi, cudaStream_t stream) {
-    const size_t smem = 16 + 2 * (NT / 32) * 4 * 4 + (size_t) W.K;
+template <int TYPE, int NT, int J, int D, int MODE>
+static void launch_mode(const WPlanes & W, const FastX & X, float * y, int64_t y_stride, Epi epi, cudaStream_t stream) {
+    const size_t smem = 16 + 2 * (NT / 32) * 4 * 4 + (NT / 32) * 8 + (size_t) W.K;
     static bool set = false;
-    if (!set) { B200_CUDA_CHECK(cudaFuncSetAttribute(mmv_fast_kernel<TYPE, NT, J, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); set = true; }
-    int ctas = fast_num_sms() * (NT == 256 ? 2 : 1);
+    if (!set) { B200_CUDA_CHECK(cudaFuncSetAttribute(mmv_fast_kernel<TYPE, NT, J, D, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        // same L1/shared split as the small kernels of the other stream: an SM cannot host kernels with different carve-outs at once
+        B200_CUDA_CHECK(cudaFuncSetAttribute(mmv_fast_kernel<TYPE, NT, J, D, MODE>, cudaFuncAttributePreferredSharedMemoryCarveout, B200_CARVEOUT)); set = true; }
+    int ctas = fast_num_sms() * (NT == 256 ? (D <= 6 ? 3 : 2) : 1);
     if (ctas > (W.M + 3) / 4) ctas = (W.M + 3) / 4;
-    dim3 grid((unsigned) ctas, (unsigned) A.N);
-    mmv_fast_kernel<TYPE, NT, J, D><<<grid, NT, smem, stream>>>(W, A, y, y_stride, epi);
-    B200_CUDA_CHECK(cudaGetLastError());
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned) ctas, (unsigned) X.N); cfg.blockDim = dim3(NT); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;          // PDL: may start while the previous kernel of the stream drains
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = getenv("B200_NO_PDL") ? 0 : 1;
+    B200_CUDA_CHECK(cudaLaunchKernelEx(&cfg, mmv_fast_kernel<TYPE, NT, J, D, MODE>, W, X, y, y_stride, epi));
+}
+template <int TYPE, int NT, int J, int D>
+static void launch_cfg(const WPlanes & W, const FastX & X, float * y, int64_t y_stride, Epi epi, cudaStream_t stream) {
+    if (X.mode == 0) launch_mode<TYPE, NT, J, D, 0>(W, X, y, y_stride, epi, stream);
+    else if (X.mode == 1) launch_mode<TYPE, NT, J, D, 1>(W, X, y, y_stride, epi, stream);
+    else if (J == 1) launch_mode<TYPE, NT, J, D, J == 1 ? 2 : 1>(W, X, y, y_stride, epi, stream);
+    else B200_ASSERT(!"mmv_fast: LayerNorm prologue needs J == 1");
 }
 
 template <int TYPE>
-static bool launch_type(const WPlanes & W, const ActQ & A, float * y, int64_t y_stride, Epi epi, cudaStream_t stream) {
+static bool launch_type(const WPlanes & W, const FastX & X, float * y, int64_t y_stride, Epi epi, cudaStream_t stream) {
     const int P = W.nb * FX<TYPE>::PPB;
     if (W.K > 64 * 1024) return false;
-    if (P <= 256) launch_cfg<TYPE, 256, 1, 8>(W, A, y, y_stride, epi, stream);
-    else if (P <= 512) launch_cfg<TYPE, 512, 1, 8>(W, A, y, y_stride, epi, stream);
-    else if (P <= 1024) launch_cfg<TYPE, 512, 2, 4>(W, A, y, y_stride, epi, stream);
-    else if (P <= 2048) launch_cfg<TYPE, 512, 4, 2>(W, A, y, y_stride, epi, stream);
+    if (X.mode == 2 && P > 512) return false;                 // the fused LayerNorm needs the whole row inside one CTA pass (J == 1)
+    if (P <= 256) { if (getenv("B200_MMV_D6")) launch_cfg<TYPE, 256, 1, 6>(W, X, y, y_stride, epi, stream); else launch_cfg<TYPE, 256, 1, 8>(W, X, y, y_stride, epi, stream); }
+    else if (P <= 512) launch_cfg<TYPE, 512, 1, 8>(W, X, y, y_stride, epi, stream);
+    else if (P <= 1024) launch_cfg<TYPE, 512, 2, 4>(W, X, y, y_stride, epi, stream);
+    else if (P <= 2048) launch_cfg<TYPE, 512, 4, 2>(W, X, y, y_stride, epi, stream);
     else return false;
     return true;
 }
 
 // returns false if the shape / type is not covered (the caller then uses the generic ring kernel of mmv.cu)
-bool launch_mmv_fast(const WPlanes & W, const ActQ & A, float * y, int64_t y_stride, MmvEpilogue e, cudaStream_t stream) {
-    const Epi epi = { e.kind, e.r1, e.r2 };
+bool launch_mmv_fast_x(const WPlanes & W, const FastX & X, float * y, int64_t y_stride, MmvEpilogue e, cudaStream_t stream) {
+    const char * nm = W.M > 40000 ? "mmv_lmhead" : W.K > 16384 ? "mmv_down" : W.M > 16384 ? "mmv_up" : W.M > 8192 ? "mmv_qkv" : "mmv_wo";
+    const Epi epi = { e.kind, e.r1, e.r2, b200_trace_slot(nm) };
     switch (W.type) {
-        case T_Q4_K: return launch_type<T_Q4_K>(W, A, y, y_stride, epi, stream);
-        case T_Q4_0: return launch_type<T_Q4_0>(W, A, y, y_stride, epi, stream);
+        case T_Q4_K: return launch_type<T_Q4_K>(W, X, y, y_stride, epi, stream);
+        case T_Q4_0: return launch_type<T_Q4_0>(W, X, y, y_stride, epi, stream);
     }
     return false;
+}
+bool mmv_fast_supports(int wtype, int K, int mode) {
+    if (wtype != T_Q4_K && wtype != T_Q4_0) return false;
+    const int P = wtype == T_Q4_K ? K / 32 : K / 32;
+    return K <= 64 * 1024 && P <= (mode == 2 ? 512 : 2048);
+}
+bool launch_mmv_fast(const WPlanes & W, const ActQ & A, float * y, int64_t y_stride, MmvEpilogue e, cudaStream_t stream) {
+    FastX X{}; X.mode = 0; X.A = A; X.N = A.N;
+    return launch_mmv_fast_x(W, X, y, y_stride, e, stream);
 }

@@ -93,12 +93,106 @@ __global__ void __launch_bounds__(LN_THREADS) layernorm_q_kernel(float * __restr
         }
     }
 }
+// Register-resident variant for rows of up to 16384 values (every Falcon n_embd): 1024 threads, each owns one or two
+// chunks of 8 consecutive values, so the row is read from global memory exactly once, a warp's 32 chunks are one Q8_K
+// block (or eight 32-blocks) and the quantisation needs no shared memory.  On the decode critical path this kernel
+// runs alone on one SM, so what matters is its dependent-latency chain: 1 load round, 2 block reductions, 1 store round.
+#define LNR_THREADS 1024
+template <int ATYPE, int CH>
+__global__ void __launch_bounds__(LNR_THREADS) layernorm_q_reg_kernel(float * __restrict__ x, int64_t x_stride,
+        const float * __restrict__ ra, const float * __restrict__ rb, int64_t r_stride,
+        const float * __restrict__ g1, const float * __restrict__ b1, ActQ A1,
+        const float * __restrict__ g2, const float * __restrict__ b2, ActQ A2, int has2, int n, unsigned long long * trace) {
+    __shared__ double sh[LNR_THREADS / 32];
+    trace_begin(trace);
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the mat-vecs that follow may start prefetching their weights now
+    const int row = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float * xr = x + (size_t) row * x_stride;
+    float v[CH][8];
+    bool ok[CH];
+    double s = 0.0;
+#pragma unroll
+    for (int c = 0; c < CH; c++) {
+        const int e = (c * LNR_THREADS + threadIdx.x) * 8;
+        ok[c] = e < n;
+        if (ok[c]) {
+            float4 p = *reinterpret_cast<const float4 *>(xr + e), q = *reinterpret_cast<const float4 *>(xr + e + 4);
+            if (ra) {
+                const float4 a0 = *reinterpret_cast<const float4 *>(ra + (size_t) row * r_stride + e), a1 = *reinterpret_cast<const float4 *>(ra + (size_t) row * r_stride + e + 4);
+                const float4 c0 = *reinterpret_cast<const float4 *>(rb + (size_t) row * r_stride + e), c1 = *reinterpret_cast<const float4 *>(rb + (size_t) row * r_stride + e + 4);
+                p.x = __fadd_rn(__fadd_rn(a0.x, c0.x), p.x); p.y = __fadd_rn(__fadd_rn(a0.y, c0.y), p.y); p.z = __fadd_rn(__fadd_rn(a0.z, c0.z), p.z); p.w = __fadd_rn(__fadd_rn(a0.w, c0.w), p.w);
+                q.x = __fadd_rn(__fadd_rn(a1.x, c1.x), q.x); q.y = __fadd_rn(__fadd_rn(a1.y, c1.y), q.y); q.z = __fadd_rn(__fadd_rn(a1.z, c1.z), q.z); q.w = __fadd_rn(__fadd_rn(a1.w, c1.w), q.w);
+                *reinterpret_cast<float4 *>(xr + e) = p; *reinterpret_cast<float4 *>(xr + e + 4) = q;
+            }
+            v[c][0] = p.x; v[c][1] = p.y; v[c][2] = p.z; v[c][3] = p.w; v[c][4] = q.x; v[c][5] = q.y; v[c][6] = q.z; v[c][7] = q.w;
+#pragma unroll
+            for (int i = 0; i < 8; i++) s += (double) v[c][i];
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; i++) v[c][i] = 0.f;
+        }
+    }
+    auto block_total = [&](double t) -> double {
+        t = warp_sum_d(t);
+        __syncthreads();
+        if (lane == 0) sh[warp] = t;
+        __syncthreads();
+        double r = sh[lane];                           // 32 warps -> one value per lane
+        return warp_sum_d(r);
+    };
+    const float mean = (float) (block_total(s) / n);
+    double s2 = 0.0;
+#pragma unroll
+    for (int c = 0; c < CH; c++) if (ok[c]) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) { v[c][i] = __fsub_rn(v[c][i], mean); s2 += (double) __fmul_rn(v[c][i], v[c][i]); }
+    }
+    const float var = (float) (block_total(s2) / n);
+    const float scale = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(var, 1e-5f)));
+#pragma unroll
+    for (int c = 0; c < CH; c++) {
+        const int e = (c * LNR_THREADS + threadIdx.x) * 8;
+        if (!ok[c]) continue;                          // whole warps drop out together (n is a multiple of 256 for Q8_K, of 32 otherwise)
+        float y[8];
+        const float4 ga = *reinterpret_cast<const float4 *>(g1 + e), gb = *reinterpret_cast<const float4 *>(g1 + e + 4);
+        const float4 ba = *reinterpret_cast<const float4 *>(b1 + e), bb = *reinterpret_cast<const float4 *>(b1 + e + 4);
+        const float gg[8] = { ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w }, bv[8] = { ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w };
+#pragma unroll
+        for (int i = 0; i < 8; i++) y[i] = __fadd_rn(__fmul_rn(__fmul_rn(v[c][i], scale), gg[i]), bv[i]);
+        quantize_chunk8<ATYPE>(y, lane, A1, row, e);
+        if (has2) {
+            const float4 ha = *reinterpret_cast<const float4 *>(g2 + e), hb = *reinterpret_cast<const float4 *>(g2 + e + 4);
+            const float4 ca = *reinterpret_cast<const float4 *>(b2 + e), cb = *reinterpret_cast<const float4 *>(b2 + e + 4);
+            const float g2v[8] = { ha.x, ha.y, ha.z, ha.w, hb.x, hb.y, hb.z, hb.w }, b2v[8] = { ca.x, ca.y, ca.z, ca.w, cb.x, cb.y, cb.z, cb.w };
+#pragma unroll
+            for (int i = 0; i < 8; i++) y[i] = __fadd_rn(__fmul_rn(__fmul_rn(v[c][i], scale), g2v[i]), b2v[i]);
+            quantize_chunk8<ATYPE>(y, lane, A2, row, e);
+        }
+    }
+    trace_end(trace);
+}
+
 void launch_layernorm_q(float * x, int64_t x_stride, const float * ra, const float * rb, int64_t r_stride,
                         const float * g1, const float * b1, const ActQ * A1,
                         const float * g2, const float * b2, const ActQ * A2, int n, int rows, cudaStream_t stream) {
     if (rows <= 0) return;
     const ActQ a2 = A2 ? *A2 : *A1;
     B200_ASSERT(!A2 || A2->type == A1->type);
+    if (n <= 16384 && n % 8 == 0 && !getenv("B200_LN_SMEM")) {
+        const bool two = n > 8192;
+        unsigned long long * tr = b200_trace_slot("layernorm_q");
+#define LNRQ(T) do { if (two) layernorm_q_reg_kernel<T, 2><<<rows, LNR_THREADS, 0, stream>>>(x, x_stride, ra, rb, r_stride, g1, b1, *A1, g2, b2, a2, A2 != nullptr, n, tr); \
+                     else layernorm_q_reg_kernel<T, 1><<<rows, LNR_THREADS, 0, stream>>>(x, x_stride, ra, rb, r_stride, g1, b1, *A1, g2, b2, a2, A2 != nullptr, n, tr); } while (0)
+        switch (A1->type) {
+            case T_Q8_0: LNRQ(T_Q8_0); break;
+            case T_Q8_1: LNRQ(T_Q8_1); break;
+            case T_Q8_K: LNRQ(T_Q8_K); break;
+            default: B200_ASSERT(!"layernorm_q: bad activation type");
+        }
+#undef LNRQ
+        B200_CUDA_CHECK(cudaGetLastError());
+        return;
+    }
     const size_t smem = (size_t) n * 4;
 #define LNQ(T) do { static bool set = false; if (!set) { B200_CUDA_CHECK(cudaFuncSetAttribute(layernorm_q_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); set = true; } \
         layernorm_q_kernel<T><<<rows, LN_THREADS, smem, stream>>>(x, x_stride, ra, rb, r_stride, g1, b1, *A1, g2, b2, a2, A2 != nullptr, n); } while (0)
@@ -178,6 +272,8 @@ void launch_rope_neox(float * x, int n_tok, int n_head, int head_dim, int64_t to
 
 // fused RoPE(Q) + RoPE(K) + K append + V append (libfalcon.cpp:2229-2281): one CTA per (token, head slot)
 __global__ void rope_kv_append_kernel(float * __restrict__ qkv, float * __restrict__ kc, float * __restrict__ vc, AttnParams p, float theta_scale) {
+    trace_begin(p.trace);
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const int t = blockIdx.y, slot = blockIdx.x, i = threadIdx.x, D = p.head_dim, half = D / 2;
     const int n_past = p.n_past_dev ? *p.n_past_dev : p.n_past;
     const int pos = n_past + t;
@@ -189,10 +285,14 @@ __global__ void rope_kv_append_kernel(float * __restrict__ qkv, float * __restri
         float * dst = (is_k ? kc : vc) + ((size_t) pos * p.n_head_kv + kvh) * D;
         dst[i] = v[i]; dst[i + half] = v[i + half];
     }
+    trace_end(p.trace);
 }
 void launch_rope_kv_append(float * qkv, float * k_cache, float * v_cache, const AttnParams & p, float theta_scale, cudaStream_t stream) {
     if (p.n_tok <= 0) return;
     dim3 grid((unsigned) (p.n_head + 2 * p.n_head_kv), (unsigned) p.n_tok);
-    rope_kv_append_kernel<<<grid, p.head_dim / 2, 0, stream>>>(qkv, k_cache, v_cache, p, theta_scale);
+    static bool set = false;
+    if (!set) { B200_CUDA_CHECK(cudaFuncSetAttribute(rope_kv_append_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, B200_CARVEOUT)); set = true; }
+    AttnParams pt = p; pt.trace = b200_trace_slot("rope_kv");
+    rope_kv_append_kernel<<<grid, p.head_dim / 2, 0, stream>>>(qkv, k_cache, v_cache, pt, theta_scale);
     B200_CUDA_CHECK(cudaGetLastError());
 }

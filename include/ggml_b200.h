@@ -85,6 +85,13 @@ void   b200_mul_mat(const b200_weight * w, const float * x_dev, int64_t x_stride
 /* the two halves separately; epilogue: 0 none, 1 GELU (fp16-LUT semantics), 2 y = (dot + r1) + r2 */
 void   b200_mul_mat_vec_q(const b200_weight * w, const b200_actq * a, float * y_dev, int64_t y_stride,
                           int epilogue, const float * r1_dev, const float * r2_dev);
+/* the decode mat-vec with its producers folded into the prologue (N = 1, Q4_K / Q4_0 weights):
+ *   gamma != NULL : y = W * Q( LayerNorm((ra + rb) + x) * gamma + beta ), ra/rb optional, x_out (optional) receives
+ *                   the updated row (ra + rb) + x   -- libfalcon.cpp:2399-2400, 2166-2185 + ggml.c:10568-10595, 11462-11476
+ *   gamma == NULL : y = W * Q(x)
+ * returns 0 if the type / shape is not covered by the fused kernel (callers then use b200_layernorm + b200_mul_mat) */
+int    b200_mul_mat_vec_fused(const b200_weight * w, const float * x_dev, const float * ra_dev, const float * rb_dev,
+                              const float * gamma_dev, const float * beta_dev, float * x_out_dev, float * y_dev, int epilogue);
 int    b200_mmv_max_n(void);
 /* the GEMM half alone, on fp16 activations x[n][k] already on the device (what b200_mul_mat does after quantising):
  * impl 1 = tcgen05 tensor-core kernel (returns 0 if the shape is not covered: N > 512 or K % 64 != 0),
