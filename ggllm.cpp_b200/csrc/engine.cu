@@ -77,6 +77,7 @@ struct b200_falcon {
     // decode graphs: [0] = device-resident step, [1] = host-to-host step (token H2D + logits D2H nodes inside)
     cudaGraphExec_t graph[2] = { nullptr, nullptr }; float graph_theta[2] = { -1.f, -1.f }; int graph_launches = 0;
     int act_type = -1;
+    void * mega_layers = nullptr; unsigned * mega_flags = nullptr; int mega_state = 0;     // persistent decode kernel: 0 = not decided, 1 = on, -1 = off
     ncclComm_t comm = nullptr;
     int launches = 0; float last_ms = 0.f;
     size_t weight_bytes = 0;
@@ -313,7 +314,7 @@ void b200_falcon_free(b200_falcon * f) {
     cudaFree(f->lnf_g); cudaFree(f->lnf_b); cudaFree(f->k_cache); cudaFree(f->v_cache);
     cudaFree(f->inp); cudaFree(f->qkv); cudaFree(f->att); cudaFree(f->ao); cudaFree(f->up); cudaFree(f->dn); cudaFree(f->logits);
     cudaFree(f->inp2); cudaFree(f->ao2); cudaFree(f->dn2); cudaFree(f->attn_scratch); cudaFree(f->actq_mem); cudaFree(f->xh_a); cudaFree(f->xh_b); cudaFree(f->gemm_ws_a); cudaFree(f->gemm_ws_b);
-    cudaFree(f->tokens_dev); cudaFree(f->n_past_dev);
+    cudaFree(f->tokens_dev); cudaFree(f->n_past_dev); cudaFree(f->mega_layers); cudaFree(f->mega_flags);
     cudaFreeHost(f->tokens_h); cudaFreeHost(f->n_past_h); cudaFreeHost(f->logits_h);
     for (int i = 0; i < 2; i++) if (f->graph[i]) cudaGraphExecDestroy(f->graph[i]);
     if (f->comm) nccl().CommDestroy(f->comm);
@@ -344,6 +345,47 @@ static void mm(b200_falcon * f, const WPlanes & W, const ActQ & A, int N, float 
 // residual adds + LayerNorm + activation quantisation in the prologue of qkv / ffn_up / lm_head (FastX mode 2),
 // activation quantisation in the prologue of wo / ffn_down (mode 1), GELU in ffn_up's epilogue.  6 kernels per layer:
 //   s_main: qkv -> rope+kv append -> attention -> wo          s_mlp: ffn_up(+GELU) -> ffn_down
+// One persistent kernel for all local layers of a decode step (decode_mega.cu) when every layer has the shape / type it covers
+static bool mega_decode_ok(b200_falcon * f) {
+    if (f->mega_state) return f->mega_state > 0;
+    f->mega_state = -1;
+    if (getenv("B200_NO_MEGA") || f->NL == 0 || f->act_type < 0) return false;
+    const int t = f->layers[0].wqkv.type;
+    for (const auto & L : f->layers) if (L.wqkv.type != t || L.wo.type != t || L.up.type != t || L.down.type != t) return false;
+    int dev, nsm; B200_CUDA_CHECK(cudaGetDevice(&dev)); B200_CUDA_CHECK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
+    if (!decode_mega_supports(t, f->E, f->FF, f->H, f->HKV, f->D, f->hp.n_ctx, nsm)) return false;
+    const size_t lb = decode_mega_layer_bytes();
+    std::vector<uint8_t> host(lb * f->NL);
+    for (int l = 0; l < f->NL; l++) {
+        const Layer & L = f->layers[l];
+        const size_t kvoff = (size_t) l * f->hp.n_ctx * f->HKV * f->D;
+        const bool dual = f->hp.falcon_type == 40;
+        decode_mega_fill_layer(host.data() + lb * l, L.wqkv, L.up, L.down, L.wo, dual ? L.ln_attn_g : L.ln_mlp_g, dual ? L.ln_attn_b : L.ln_mlp_b,
+                               L.ln_mlp_g, L.ln_mlp_b, f->k_cache + kvoff, f->v_cache + kvoff);
+    }
+    B200_CUDA_CHECK(cudaMalloc(&f->mega_layers, host.size()));
+    B200_CUDA_CHECK(cudaMemcpy(f->mega_layers, host.data(), host.size(), cudaMemcpyHostToDevice));
+    B200_CUDA_CHECK(cudaMalloc(&f->mega_flags, (size_t) f->NL * 4 * sizeof(unsigned)));
+    f->mega_state = 1;
+    return true;
+}
+// embedding (or the previous rank's row) -> persistent layer kernel -> final LayerNorm + lm_head (or send to the next rank)
+static void enqueue_decode_mega(b200_falcon * f, int n_past, float theta_scale, bool graph_mode) {
+    cudaStream_t sa = f->s_main;
+    const int E = f->E;
+    ensure_actq(f);
+    ActQ xf = f->xf; xf.N = 1;
+    if (f->first) { launch_dequant_rows(f->tok_emb, f->tokens_dev, 1, f->inp, E, sa); f->launches++; }
+    else B200_NCCL_CHECK(nccl().Recv(f->inp, (size_t) E, ncclFloat, f->hp.rank - 1, f->comm, sa));
+    launch_decode_mega(f->layers[0].wqkv.type, f->mega_layers, f->NL, f->inp, f->qkv, f->up, f->att, f->mega_flags,
+                       graph_mode ? f->n_past_dev : nullptr, n_past, f->hp.n_ctx, E, f->FF, f->H, f->HKV, f->D, f->hp.falcon_type == 40, theta_scale, sa);
+    f->launches++;
+    if (f->last) {
+        launch_layernorm_q(f->inp, E, nullptr, nullptr, 0, f->lnf_g, f->lnf_b, &xf, nullptr, nullptr, nullptr, E, 1, sa);      // :2422-2431
+        launch_mmv(f->lm_head, xf, f->logits, f->V, { EPI_NONE, nullptr, nullptr }, sa); f->launches += 2;                     // :2440
+    } else B200_NCCL_CHECK(nccl().Send(f->inp, (size_t) E, ncclFloat, f->hp.rank + 1, f->comm, sa));
+}
+
 static bool fused_decode_ok(const b200_falcon * f) {
     if (getenv("B200_NO_FUSED_DECODE")) return false;
     for (const auto & L : f->layers)
@@ -383,9 +425,9 @@ static void enqueue_decode_fused(b200_falcon * f, int n_past, float theta_scale,
         B200_CUDA_CHECK(cudaEventRecord(f->e_join, sb));
         if (!skip("up")) launch_mmv(L.up, xm, f->up, f->FF, gelu, sa);                                           // :2389-2392
         FastX xd{}; xd.mode = 1; xd.N = 1; xd.x = f->up; xd.x_stride = f->FF;
+        FastX xo{}; xo.mode = 1; xo.N = 1; xo.x = f->att; xo.x_stride = E;
         if (!skip("down")) B200_ASSERT(launch_mmv_fast_x(L.down, xd, f->dn, E, none, sa));                      // :2394, activation quantised in the prologue
         B200_CUDA_CHECK(cudaStreamWaitEvent(sa, f->e_join, 0));
-        FastX xo{}; xo.mode = 1; xo.N = 1; xo.x = f->att; xo.x_stride = E;
         if (!skip("wo")) B200_ASSERT(launch_mmv_fast_x(L.wo, xo, f->ao, E, none, sa));                          // :2370
         f->launches += 7;
     }
@@ -400,6 +442,7 @@ static void enqueue_decode_fused(b200_falcon * f, int n_past, float theta_scale,
 
 // Enqueue one eval of N tokens on (s_main, s_mlp).  Device scalars carry n_past when `graph_mode`.
 static void enqueue_eval(b200_falcon * f, int N, int n_past, float theta_scale, bool graph_mode, int logits_rows_from) {
+    if (N == 1 && mega_decode_ok(f)) { enqueue_decode_mega(f, n_past, theta_scale, graph_mode); return; }
     if (N == 1 && fused_decode_ok(f)) { enqueue_decode_fused(f, n_past, theta_scale, graph_mode); return; }
     cudaStream_t sa = f->s_main, sb = f->s_mlp;
     const int E = f->E, FF = f->FF;

@@ -34,6 +34,13 @@ struct FastX {
 };
 bool   launch_mmv_fast_x(const WPlanes & W, const FastX & X, float * y, int64_t y_stride, MmvEpilogue e, cudaStream_t stream);
 bool   mmv_fast_supports(int wtype, int K, int mode);
+// decode_mega.cu: every layer of one decode step in a single persistent kernel
+bool   decode_mega_supports(int wtype, int E, int FF, int H, int HKV, int D, int n_ctx, int n_sm);
+size_t decode_mega_layer_bytes();
+void   decode_mega_fill_layer(void * dst_host, const WPlanes & qkv, const WPlanes & up, const WPlanes & down, const WPlanes & wo,
+                              const float * ga, const float * ba, const float * gm, const float * bm, float * kc, float * vc);
+void   launch_decode_mega(int wtype, const void * layers_dev, int n_layer, float * x, float * qkv, float * up, float * att, unsigned * flags,
+                          const int * n_past_dev, int n_past, int n_ctx, int E, int FF, int H, int HKV, int D, int dual, float theta_scale, cudaStream_t stream);
 
 // ---- ops.cu
 void   launch_layernorm(const float * x, int64_t x_stride, const float * g, const float * b, float * y, int64_t y_stride,
