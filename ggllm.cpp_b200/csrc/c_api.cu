@@ -173,6 +173,21 @@ int b200_mul_mat_vec_fused(const b200_weight * w, const float * x, const float *
     return launch_mmv_fast_x(w->W, X, y, w->W.M, e, g_stream) ? 1 : 0;
 }
 
+int b200_mul_mat_vec_q_chain(const b200_weight * w, const b200_actq * a_in, float * y, int epilogue, b200_actq * a_out) {
+    const WPlanes & W = w->W;
+    if (!mmv_fast_supports(W.type, W.K, 0) || W.M % 256 != 0 || a_in->A.N != 1 || a_out->A.K != W.M) return 0;
+    if (a_out->A.type != T_Q8_K && a_out->A.type != T_Q8_0) return 0;
+    static unsigned * ctr = nullptr; static int ctr_n = 0;
+    if (ctr_n < W.M / 256) {
+        if (ctr) { B200_CUDA_CHECK(cudaStreamSynchronize(g_stream)); B200_CUDA_CHECK(cudaFree(ctr)); }
+        ctr_n = W.M / 256; B200_CUDA_CHECK(cudaMalloc(&ctr, (size_t) ctr_n * sizeof(unsigned))); B200_CUDA_CHECK(cudaMemset(ctr, 0, (size_t) ctr_n * sizeof(unsigned)));
+    }
+    ActQ out = a_out->A; out.N = 1;
+    MmvEpilogue e = { epilogue, nullptr, nullptr, &out, ctr };
+    FastX X{}; X.mode = 0; X.N = 1; X.A = a_in->A;
+    return launch_mmv_fast_x(W, X, y, W.M, e, g_stream) ? 1 : 0;
+}
+
 int b200_mul_mat_f16(const b200_weight * w, const void * x_f16, int64_t x_stride, int N, float * y, int64_t y_stride, int epi_gelu, int impl) {
     if (impl == 0) { launch_gemm_simt(w->W, (const __half *) x_f16, x_stride, N, y, y_stride, epi_gelu, g_stream); return 1; }
     return launch_gemm_tc(w->W, (const __half *) x_f16, x_stride, N, y, y_stride, epi_gelu, g_stream) ? 1 : 0;

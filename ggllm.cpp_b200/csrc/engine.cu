@@ -77,6 +77,7 @@ struct b200_falcon {
     // decode graphs: [0] = device-resident step, [1] = host-to-host step (token H2D + logits D2H nodes inside)
     cudaGraphExec_t graph[2] = { nullptr, nullptr }; float graph_theta[2] = { -1.f, -1.f }; int graph_launches = 0;
     int act_type = -1;
+    unsigned * q_ctr = nullptr;                 // chunk counters of the quantise-on-completion epilogue (ffn_up -> ffn_down)
     void * mega_layers = nullptr; unsigned * mega_flags = nullptr; int mega_state = 0;     // persistent decode kernel: 0 = not decided, 1 = on, -1 = off
     ncclComm_t comm = nullptr;
     int launches = 0; float last_ms = 0.f;
@@ -182,6 +183,7 @@ b200_falcon * b200_falcon_create(const b200_falcon_params * p) {
 }
 
 static void ensure_actq(b200_falcon * f) {
+    if (!f->q_ctr) { B200_CUDA_CHECK(cudaMalloc(&f->q_ctr, (size_t) (f->FF / 256 + 1) * sizeof(unsigned))); B200_CUDA_CHECK(cudaMemset(f->q_ctr, 0, (size_t) (f->FF / 256 + 1) * sizeof(unsigned))); }
     if (f->actq_mem || f->act_type < 0) return;
     const int at = f->act_type; const int NB = f->hp.n_batch > 0 ? f->hp.n_batch : 1;
     const size_t bE = actq_bytes(at, f->E, NB), bF = actq_bytes(at, f->FF, NB);
@@ -314,7 +316,7 @@ void b200_falcon_free(b200_falcon * f) {
     cudaFree(f->lnf_g); cudaFree(f->lnf_b); cudaFree(f->k_cache); cudaFree(f->v_cache);
     cudaFree(f->inp); cudaFree(f->qkv); cudaFree(f->att); cudaFree(f->ao); cudaFree(f->up); cudaFree(f->dn); cudaFree(f->logits);
     cudaFree(f->inp2); cudaFree(f->ao2); cudaFree(f->dn2); cudaFree(f->attn_scratch); cudaFree(f->actq_mem); cudaFree(f->xh_a); cudaFree(f->xh_b); cudaFree(f->gemm_ws_a); cudaFree(f->gemm_ws_b);
-    cudaFree(f->tokens_dev); cudaFree(f->n_past_dev); cudaFree(f->mega_layers); cudaFree(f->mega_flags);
+    cudaFree(f->tokens_dev); cudaFree(f->n_past_dev); cudaFree(f->mega_layers); cudaFree(f->mega_flags); cudaFree(f->q_ctr);
     cudaFreeHost(f->tokens_h); cudaFreeHost(f->n_past_h); cudaFreeHost(f->logits_h);
     for (int i = 0; i < 2; i++) if (f->graph[i]) cudaGraphExecDestroy(f->graph[i]);
     if (f->comm) nccl().CommDestroy(f->comm);
@@ -389,18 +391,21 @@ static void enqueue_decode_mega(b200_falcon * f, int n_past, float theta_scale, 
 static bool fused_decode_ok(const b200_falcon * f) {
     if (getenv("B200_NO_FUSED_DECODE")) return false;
     for (const auto & L : f->layers)
-        if (!mmv_fast_supports(L.wo.type, L.wo.K, 1) || !mmv_fast_supports(L.down.type, L.down.K, 1)) return false;
-    return f->act_type >= 0;
+        if (!mmv_fast_supports(L.wo.type, L.wo.K, 0) || !mmv_fast_supports(L.down.type, L.down.K, 0) ||
+            !mmv_fast_supports(L.up.type, L.up.K, 0) || !mmv_fast_supports(L.wqkv.type, L.wqkv.K, 0)) return false;
+    return f->act_type >= 0 && f->FF % 256 == 0;
 }
 static void enqueue_decode_fused(b200_falcon * f, int n_past, float theta_scale, bool graph_mode) {
     cudaStream_t sa = f->s_main, sb = f->s_mlp;
     const int E = f->E;
     const bool dual = f->hp.falcon_type == 40;
     ensure_actq(f);
-    ActQ xa = f->xa, xm = f->xm, xf = f->xf; xa.N = xm.N = xf.N = 1;
+    ActQ xa = f->xa, xm = f->xm, xf = f->xf, xup = f->xup, xatt = f->xatt; xa.N = xm.N = xf.N = xup.N = xatt.N = 1;
     if (f->first) { launch_dequant_rows(f->tok_emb, f->tokens_dev, 1, f->inp, E, sa); f->launches++; }
     else B200_NCCL_CHECK(nccl().Recv(f->inp, (size_t) E, ncclFloat, f->hp.rank - 1, f->comm, sa));
-    const MmvEpilogue none = { EPI_NONE, nullptr, nullptr }, gelu = { EPI_GELU, nullptr, nullptr };
+    const MmvEpilogue none = { EPI_NONE, nullptr, nullptr, nullptr, nullptr };
+    // ffn_up applies GELU and, chunk by chunk as CTAs finish, quantises its output row for ffn_down (no INIT pass, no prologue work there)
+    const MmvEpilogue gelu = { EPI_GELU, nullptr, nullptr, &xup, f->q_ctr };
     // debugging aid for timing experiments only (results are wrong when anything is skipped): B200_DBG_SKIP=ln,qkv,attn,up,down,wo
     const char * dbg = getenv("B200_DBG_SKIP");
     auto skip = [&](const char * what) { return dbg && strstr(dbg, what) != nullptr; };
@@ -421,15 +426,14 @@ static void enqueue_decode_fused(b200_falcon * f, int n_past, float theta_scale,
         if (!skip("attn")) {
         launch_rope_kv_append(f->qkv, f->k_cache + kvoff, f->v_cache + kvoff, ap, theta_scale, sb);             // :2229-2281
         launch_attention(f->qkv, f->k_cache + kvoff, f->v_cache + kvoff, f->att, E, ap, nullptr, sb);           // :2285-2366
+        launch_quantize_act(f->att, E, xatt, sb);                                                               // wo's INIT pass, off the critical path
         }
         B200_CUDA_CHECK(cudaEventRecord(f->e_join, sb));
         if (!skip("up")) launch_mmv(L.up, xm, f->up, f->FF, gelu, sa);                                           // :2389-2392
-        FastX xd{}; xd.mode = 1; xd.N = 1; xd.x = f->up; xd.x_stride = f->FF;
-        FastX xo{}; xo.mode = 1; xo.N = 1; xo.x = f->att; xo.x_stride = E;
-        if (!skip("down")) B200_ASSERT(launch_mmv_fast_x(L.down, xd, f->dn, E, none, sa));                      // :2394, activation quantised in the prologue
+        if (!skip("down")) launch_mmv(L.down, xup, f->dn, E, none, sa);                                         // :2394
         B200_CUDA_CHECK(cudaStreamWaitEvent(sa, f->e_join, 0));
-        if (!skip("wo")) B200_ASSERT(launch_mmv_fast_x(L.wo, xo, f->ao, E, none, sa));                          // :2370
-        f->launches += 7;
+        if (!skip("wo")) launch_mmv(L.wo, xatt, f->ao, E, none, sa);                                            // :2370
+        f->launches += 8;
     }
     if (f->last) {
         launch_layernorm_q(f->inp, E, f->NL > 0 ? f->dn : nullptr, f->NL > 0 ? f->ao : nullptr, E, f->lnf_g, f->lnf_b, &xf, nullptr, nullptr, nullptr, E, 1, sa);   // :2399-2400, 2422-2431

@@ -18,7 +18,10 @@ void   launch_actq_to_f16(const ActQ & A, __half * dst, int64_t dst_stride, cuda
 
 // ---- mmv.cu : y[n][m] = sum_k W[m][k] * xq[n][k], N small (decode), integer dots on quantised activations
 enum { EPI_NONE = 0, EPI_GELU = 1, EPI_ADD2 = 2 };
-struct MmvEpilogue { int kind; const float * r1; const float * r2; };       // ADD2: y = (dot + r1[m]) + r2[m]
+struct MmvEpilogue { int kind; const float * r1; const float * r2;         // ADD2: y = (dot + r1[m]) + r2[m]
+    // optional (fast kernel, N == 1, M % 256 == 0): the output row is also quantised for the NEXT mat-mul (its INIT pass,
+    // ggml.c:11462-11476) by whichever CTA completes a 256-value chunk; qctr = M / 256 zero-initialised, self-resetting counters
+    const ActQ * qout; unsigned * qctr; };
 void   launch_mmv(const WPlanes & W, const ActQ & A, float * y, int64_t y_stride, MmvEpilogue epi, cudaStream_t stream);
 void   launch_mmv_f(const WPlanes & W, const float * x, int64_t x_stride, int N, float * y, int64_t y_stride, cudaStream_t stream); // f16/f32 weights
 
@@ -31,6 +34,7 @@ struct FastX {
     const float * ra, * rb;     // mode 2, optional: x = (ra + rb) + x first
     const float * gamma, * beta;
     float * x_out;              // mode 2, optional: CTA 0 stores the updated x here
+    int l2_dist;                // set by the launcher: rows of HBM -> L2 prefetch ahead of the register ring
 };
 bool   launch_mmv_fast_x(const WPlanes & W, const FastX & X, float * y, int64_t y_stride, MmvEpilogue e, cudaStream_t stream);
 bool   mmv_fast_supports(int wtype, int K, int mode);

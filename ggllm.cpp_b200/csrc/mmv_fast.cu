@@ -49,6 +49,8 @@ __device__ __forceinline__ void mmv_body(const WPlanes & W, const FastX & X, flo
 
     typename T::WR w[D][J];
     ring_fill<TYPE, J, D>(w, wp, row0, row1);                                // weights are in flight before the activation arrives
+    const L2PF pf = l2pf_of(W, X.l2_dist);
+    if (pf.dist > 0 && tid == 0) l2_prefetch_rows(pf, min(row0 + D, row1), min(row0 + D + pf.dist, row1));
 
     // everything above touched only weights; the activation row is produced by the previous kernel(s) of the stream
     asm volatile("griddepcontrol.wait;" ::: "memory");
@@ -139,7 +141,35 @@ __device__ __forceinline__ void mmv_body(const WPlanes & W, const FastX & X, flo
             else if (ekind == EPI_ADD2) v = (v + r1p[(size_t) n * y_stride + row]) + r2p[(size_t) n * y_stride + row];
             y[(size_t) n * y_stride + row] = v;
         },
-        [&]() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); });
+        [&]() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }, pf);
+    if (epi.qctr) {
+        // Quantise the finished output row for the next mat-mul, 256 values at a time.  A chunk's rows belong to up to
+        // three CTAs; each adds its row count to the chunk's counter once its own rows are stored and fenced, and the CTA
+        // that completes the count quantises the chunk (one warp) and re-arms the counter for the next launch.
+        __shared__ int s_do;
+        __threadfence();
+        __syncthreads();
+        if (nrows > 0) {
+            for (int b = row0 >> 8; b <= (row1 - 1) >> 8; b++) {
+                if (tid == 0) {
+                    const unsigned cnt = (unsigned) (min(row1, (b + 1) << 8) - max(row0, b << 8));
+                    const unsigned old = atomicAdd(epi.qctr + b, cnt);
+                    s_do = old + cnt == 256u;
+                    if (s_do) epi.qctr[b] = 0;
+                }
+                __syncthreads();
+                if (s_do && warp == 0) {
+                    __threadfence();
+                    const float * src = y + (size_t) n * y_stride + (b << 8) + lane * 8;
+                    const float4 p = __ldcg(reinterpret_cast<const float4 *>(src)), q = __ldcg(reinterpret_cast<const float4 *>(src) + 1);
+                    const float v[8] = { p.x, p.y, p.z, p.w, q.x, q.y, q.z, q.w };
+                    if (epi.qA.type == T_Q8_K) quantize_chunk8<T_Q8_K>(v, lane, epi.qA, n, (b << 8) + lane * 8);
+                    else quantize_chunk8<T_Q8_0>(v, lane, epi.qA, n, (b << 8) + lane * 8);
+                }
+                __syncthreads();
+            }
+        }
+    }
     trace_end(epi.trace);
 }
 
@@ -198,10 +228,19 @@ static bool launch_type(const WPlanes & W, const FastX & X, float * y, int64_t y
 // returns false if the shape / type is not covered (the caller then uses the generic ring kernel of mmv.cu)
 bool launch_mmv_fast_x(const WPlanes & W, const FastX & X, float * y, int64_t y_stride, MmvEpilogue e, cudaStream_t stream) {
     const char * nm = W.M > 40000 ? "mmv_lmhead" : W.K > 16384 ? "mmv_down" : W.M > 16384 ? "mmv_up" : W.M > 8192 ? "mmv_qkv" : "mmv_wo";
-    const Epi epi = { e.kind, e.r1, e.r2, b200_trace_slot(nm) };
+    Epi epi = { e.kind, e.r1, e.r2, b200_trace_slot(nm), ActQ{}, nullptr };
+    if (e.qout && e.qctr) {
+        B200_ASSERT(X.N == 1 && W.M % 256 == 0 && e.qout->K == W.M && (e.qout->type == T_Q8_K || e.qout->type == T_Q8_0));
+        epi.qA = *e.qout; epi.qctr = e.qctr;
+    }
+    static int dist_bytes = -1;
+    // HBM -> L2 prefetch ahead of the ring: off by default, measured slower at every distance (profiles/r1_decode_timeline.md)
+    if (dist_bytes < 0) { const char * s = getenv("B200_L2PF_KB"); dist_bytes = (s ? atoi(s) : 0) * 1024; }
+    FastX Xp = X;
+    Xp.l2_dist = W.stride[0] ? (int) (dist_bytes / W.stride[0]) : 0;
     switch (W.type) {
-        case T_Q4_K: return launch_type<T_Q4_K>(W, X, y, y_stride, epi, stream);
-        case T_Q4_0: return launch_type<T_Q4_0>(W, X, y, y_stride, epi, stream);
+        case T_Q4_K: return launch_type<T_Q4_K>(W, Xp, y, y_stride, epi, stream);
+        case T_Q4_0: return launch_type<T_Q4_0>(W, Xp, y, y_stride, epi, stream);
     }
     return false;
 }

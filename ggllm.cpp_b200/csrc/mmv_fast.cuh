@@ -1,8 +1,9 @@
 // mmv_fast.cuh -- per-type pieces of the register-resident decode mat-vec (used by mmv_fast.cu and decode_mega.cu)
 #pragma once
 #include "kernels.h"
+#include "actquant.cuh"
 
-struct Epi { int kind; const float * r1; const float * r2; unsigned long long * trace; };
+struct Epi { int kind; const float * r1; const float * r2; unsigned long long * trace; ActQ qA; unsigned * qctr; };
 
 // Where the activation row comes from (FastX, kernels.h):
 //   mode 0: already quantised (ActQ, written by quantize_act / layernorm_q)
@@ -193,6 +194,28 @@ template <int G> __device__ __forceinline__ float transpose_reduce(const float (
 }
 
 
+// HBM -> L2 prefetch of whole rows, `dist` rows ahead of the register ring.  The ring alone keeps 64 KB per SM in flight,
+// which at the ~2 us loaded HBM latency caps the stream at ~4.7 TB/s (ncu: 27 % of all stall samples sit on the first use
+// of a ring slot, profiles/r1_mmv_up_narrow.md); one bulk-prefetch instruction per plane and pass, issued by a single
+// thread, moves the latency the ring has to cover from HBM to L2.
+struct L2PF { const uint8_t * p[3]; uint32_t s[3]; int dist; };
+__device__ __forceinline__ void l2_prefetch_rows(const L2PF & pf, int a, int b) {       // rows [a, b) of every plane
+    if (b <= a) return;
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        if (!pf.p[i]) continue;
+        const uint8_t * src = pf.p[i] + (size_t) a * pf.s[i];
+        const uint32_t bytes = (uint32_t) (b - a) * pf.s[i];
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(src), "r"(bytes) : "memory");
+    }
+}
+__device__ __forceinline__ L2PF l2pf_of(const WPlanes & W, int dist) {
+    L2PF r; r.dist = dist;
+#pragma unroll
+    for (int i = 0; i < 3; i++) { r.p[i] = W.p[i]; r.s[i] = W.stride[i]; }
+    return r;
+}
+
 __device__ __forceinline__ void named_sync(int id, int n) { asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(n) : "memory"); }
 
 template <int TYPE> __device__ __forceinline__ typename FX<TYPE>::XR zero_xr() {
@@ -267,12 +290,14 @@ template <int TYPE, int NTG, int J, int D, bool HASNEXT, class Store, class Tail
 __device__ __forceinline__ void ring_run(typename FX<TYPE>::WR (&w)[D][J], const WP (&wp)[J], const int r0, const int r1,
                                          const WP (&wpn)[J], const int n0, const int n1,
                                          const typename FX<TYPE>::XR (&xr)[J], float * partial, int & gcount, const int bar_id, const int tg,
-                                         Store store, Tail before_tail) {
+                                         Store store, Tail before_tail, const L2PF pf = L2PF{ { nullptr, nullptr, nullptr }, { 0, 0, 0 }, 0 }) {
     const int nrows = r1 - r0, npad = (nrows + D - 1) / D * D;
     if (npad == 0) { before_tail(); if (HASNEXT) ring_fill<TYPE, J, D>(w, wpn, n0, n1); return; }
     int base = 0;
-    for (; base + 2 * D <= nrows; base += D)
+    for (; base + 2 * D <= nrows; base += D) {
+        if (pf.dist > 0 && tg == 0) l2_prefetch_rows(pf, min(r0 + base + D + pf.dist, r1), min(r0 + base + 2 * D + pf.dist, r1));
         ring_pass<TYPE, NTG, J, D, false, false>(w, wp, r0, nrows, npad, base, wpn, n0, n1, xr, partial, gcount, bar_id, tg, store);
+    }
     before_tail();
     for (; base < npad; base += D)
         ring_pass<TYPE, NTG, J, D, true, HASNEXT>(w, wp, r0, nrows, npad, base, wpn, n0, n1, xr, partial, gcount, bar_id, tg, store);

@@ -92,6 +92,11 @@ void   b200_mul_mat_vec_q(const b200_weight * w, const b200_actq * a, float * y_
  * returns 0 if the type / shape is not covered by the fused kernel (callers then use b200_layernorm + b200_mul_mat) */
 int    b200_mul_mat_vec_fused(const b200_weight * w, const float * x_dev, const float * ra_dev, const float * rb_dev,
                               const float * gamma_dev, const float * beta_dev, float * x_out_dev, float * y_dev, int epilogue);
+/* y = epilogue(W * a_in) for N = 1 and, from the SAME kernel, a_out = Q(y): the next mat-mul's INIT-pass quantisation
+ * (ggml.c:11462-11476) done chunk by chunk as the CTAs that own a 256-value chunk finish (decode: ffn_up -> ffn_down,
+ * libfalcon.cpp:2389-2394).  a_out must have K == rows of w and the activation type of the next weight.
+ * returns 0 if the type / shape is not covered (rows % 256 != 0, or not Q4_K / Q4_0). */
+int    b200_mul_mat_vec_q_chain(const b200_weight * w, const b200_actq * a_in, float * y_dev, int epilogue, b200_actq * a_out);
 int    b200_mmv_max_n(void);
 /* the GEMM half alone, on fp16 activations x[n][k] already on the device (what b200_mul_mat does after quantising):
  * impl 1 = tcgen05 tensor-core kernel (returns 0 if the shape is not covered: N > 512 or K % 64 != 0),

@@ -286,3 +286,26 @@ def test_fused_matvec_large_k(gpu, orc):
     want = orc.mul_mat(t, wq, K, M, x[None, :])[0]
     wd = np.abs(orc.dequantize(t, wq, K))
     assert np.all(np.abs(yd.download(np.float32, (M,)) - want) <= 2e-5 * (wd @ np.abs(x)) + 1e-6)
+
+
+@pytest.mark.parametrize("t,K,M", [(po.Q4_K, 8192, 32768), (po.Q4_K, 512, 768), (po.Q4_0, 4544, 18176)])
+def test_matvec_chain_quantises_output_for_next_matmul(gpu, orc, t, K, M):
+    """ffn_up -> ffn_down hand-over: the mat-vec's own CTAs quantise the (GELU'd) output row, 256 values at a time, as
+    they finish.  Codes / scales / sums must equal the standalone quantiser run on the same fp32 row, bit for bit,
+    launch after launch (the chunk counters re-arm themselves)."""
+    rng = np.random.default_rng(K + M)
+    wq = _weights(orc, t, M, K, seed=9)
+    W = gpu.Weight(t, K, M, wq)
+    A_in, A_out, A_ref = gpu.ActQ(t, K, 1), gpu.ActQ(t, M, 1), gpu.ActQ(t, M, 1)
+    yd = gpu.DevBuf(M * 4)
+    for it in range(3):
+        x = rng.standard_normal(K).astype(np.float32)
+        xd = gpu.DevBuf(src=x)
+        A_in.quantize(xd.ptr)
+        assert gpu.lib().b200_mul_mat_vec_q_chain(W.h, A_in.h, yd.ptr, 1, A_out.h) == 1
+        y = yd.download(np.float32, (M,))
+        gpu.lib().b200_mul_mat_vec_q(W.h, A_in.h, yd.ptr, M, 1, None, None)          # same kernel without the hand-over
+        assert np.array_equal(y, yd.download(np.float32, (M,)))
+        A_ref.quantize(yd.ptr)
+        (q, d, _, bs), (q0, d0, _, bs0) = A_out.download(), A_ref.download()      # (the s plane exists for Q8_1 only)
+        assert np.array_equal(q, q0) and np.array_equal(d, d0) and np.array_equal(bs, bs0)
