@@ -12,6 +12,7 @@
 //     boundary with a single ncclSend/ncclRecv on the compute stream (replaces the row-split tensor parallelism of
 //     ggml-cuda.cu:2594-2601, 2719-2725, 2779-2788)
 #include "kernels.h"
+#include "ln_tail.cuh"
 #include "../../include/ggml_b200.h"
 #include <nccl.h>
 #include <dlfcn.h>
@@ -77,6 +78,7 @@ struct b200_falcon {
     // decode graphs: [0] = device-resident step, [1] = host-to-host step (token H2D + logits D2H nodes inside)
     cudaGraphExec_t graph[2] = { nullptr, nullptr }; float graph_theta[2] = { -1.f, -1.f }; int graph_launches = 0;
     int act_type = -1;
+    unsigned * ln_ctr = nullptr;                // arrival counter of the LayerNorm tail (last CTA of wo)
     unsigned * q_ctr = nullptr;                 // chunk counters of the quantise-on-completion epilogue (ffn_up -> ffn_down)
     void * mega_layers = nullptr; unsigned * mega_flags = nullptr; int mega_state = 0;     // persistent decode kernel: 0 = not decided, 1 = on, -1 = off
     ncclComm_t comm = nullptr;
@@ -183,6 +185,7 @@ b200_falcon * b200_falcon_create(const b200_falcon_params * p) {
 }
 
 static void ensure_actq(b200_falcon * f) {
+    if (!f->ln_ctr) { B200_CUDA_CHECK(cudaMalloc(&f->ln_ctr, sizeof(unsigned))); B200_CUDA_CHECK(cudaMemset(f->ln_ctr, 0, sizeof(unsigned))); }
     if (!f->q_ctr) { B200_CUDA_CHECK(cudaMalloc(&f->q_ctr, (size_t) (f->FF / 256 + 1) * sizeof(unsigned))); B200_CUDA_CHECK(cudaMemset(f->q_ctr, 0, (size_t) (f->FF / 256 + 1) * sizeof(unsigned))); }
     if (f->actq_mem || f->act_type < 0) return;
     const int at = f->act_type; const int NB = f->hp.n_batch > 0 ? f->hp.n_batch : 1;
@@ -316,7 +319,7 @@ void b200_falcon_free(b200_falcon * f) {
     cudaFree(f->lnf_g); cudaFree(f->lnf_b); cudaFree(f->k_cache); cudaFree(f->v_cache);
     cudaFree(f->inp); cudaFree(f->qkv); cudaFree(f->att); cudaFree(f->ao); cudaFree(f->up); cudaFree(f->dn); cudaFree(f->logits);
     cudaFree(f->inp2); cudaFree(f->ao2); cudaFree(f->dn2); cudaFree(f->attn_scratch); cudaFree(f->actq_mem); cudaFree(f->xh_a); cudaFree(f->xh_b); cudaFree(f->gemm_ws_a); cudaFree(f->gemm_ws_b);
-    cudaFree(f->tokens_dev); cudaFree(f->n_past_dev); cudaFree(f->mega_layers); cudaFree(f->mega_flags); cudaFree(f->q_ctr);
+    cudaFree(f->tokens_dev); cudaFree(f->n_past_dev); cudaFree(f->mega_layers); cudaFree(f->mega_flags); cudaFree(f->q_ctr); cudaFree(f->ln_ctr);
     cudaFreeHost(f->tokens_h); cudaFreeHost(f->n_past_h); cudaFreeHost(f->logits_h);
     for (int i = 0; i < 2; i++) if (f->graph[i]) cudaGraphExecDestroy(f->graph[i]);
     if (f->comm) nccl().CommDestroy(f->comm);
@@ -351,7 +354,8 @@ static void mm(b200_falcon * f, const WPlanes & W, const ActQ & A, int N, float 
 static bool mega_decode_ok(b200_falcon * f) {
     if (f->mega_state) return f->mega_state > 0;
     f->mega_state = -1;
-    if (getenv("B200_NO_MEGA") || f->NL == 0 || f->act_type < 0) return false;
+    // opt-in (B200_MEGA=1): correct and tested, but slower than the per-node path so far
+    if (!getenv("B200_MEGA") || f->NL == 0 || f->act_type < 0) return false;
     const int t = f->layers[0].wqkv.type;
     for (const auto & L : f->layers) if (L.wqkv.type != t || L.wo.type != t || L.up.type != t || L.down.type != t) return false;
     int dev, nsm; B200_CUDA_CHECK(cudaGetDevice(&dev)); B200_CUDA_CHECK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
@@ -403,19 +407,22 @@ static void enqueue_decode_fused(b200_falcon * f, int n_past, float theta_scale,
     ActQ xa = f->xa, xm = f->xm, xf = f->xf, xup = f->xup, xatt = f->xatt; xa.N = xm.N = xf.N = xup.N = xatt.N = 1;
     if (f->first) { launch_dequant_rows(f->tok_emb, f->tokens_dev, 1, f->inp, E, sa); f->launches++; }
     else B200_NCCL_CHECK(nccl().Recv(f->inp, (size_t) E, ncclFloat, f->hp.rank - 1, f->comm, sa));
-    const MmvEpilogue none = { EPI_NONE, nullptr, nullptr, nullptr, nullptr };
+    const MmvEpilogue none = { EPI_NONE, nullptr, nullptr, nullptr, nullptr, nullptr };
     // ffn_up applies GELU and, chunk by chunk as CTAs finish, quantises its output row for ffn_down (no INIT pass, no prologue work there)
-    const MmvEpilogue gelu = { EPI_GELU, nullptr, nullptr, &xup, f->q_ctr };
+    const MmvEpilogue gelu = { EPI_GELU, nullptr, nullptr, &xup, f->q_ctr, nullptr };
     // debugging aid for timing experiments only (results are wrong when anything is skipped): B200_DBG_SKIP=ln,qkv,attn,up,down,wo
     const char * dbg = getenv("B200_DBG_SKIP");
     auto skip = [&](const char * what) { return dbg && strstr(dbg, what) != nullptr; };
     // All four mat-vecs of a layer go back to back on ONE stream (each is launched with programmatic dependent launch,
     // so its weight prefetch overlaps the previous one's tail); the small attention kernels run beside ffn_up on the
     // second stream:   s_main: LN -> qkv -> ffn_up(+GELU) -> ffn_down -> wo        s_mlp: rope+kv append -> attention
+    // The residual adds that close layer l and the LayerNorm(s) of layer l+1 (or the final one) are run by the last CTA
+    // of layer l's wo mat-vec (ln_tail.cuh); only the first local layer needs the stand-alone kernel.
+    const bool tail = E % 256 == 0 && getenv("B200_LN_TAIL") && !dbg;       // opt-in: correct, but the single-CTA tail is still slower than the kernel it replaces
     for (int l = 0; l < f->NL; l++) {
         const Layer & L = f->layers[l];
         const float * ra = l > 0 ? f->dn : nullptr, * rb = l > 0 ? f->ao : nullptr;
-        if (skip("ln")) {}
+        if (skip("ln") || (tail && l > 0)) {}
         else if (dual) launch_layernorm_q(f->inp, E, ra, rb, E, L.ln_attn_g, L.ln_attn_b, &xa, L.ln_mlp_g, L.ln_mlp_b, &xm, E, 1, sa);
         else      launch_layernorm_q(f->inp, E, ra, rb, E, L.ln_mlp_g, L.ln_mlp_b, &xm, nullptr, nullptr, nullptr, E, 1, sa);
         if (!skip("qkv")) launch_mmv(L.wqkv, dual ? xa : xm, f->qkv, f->QKV, none, sa);                         // libfalcon.cpp:2192
@@ -432,12 +439,23 @@ static void enqueue_decode_fused(b200_falcon * f, int n_past, float theta_scale,
         if (!skip("up")) launch_mmv(L.up, xm, f->up, f->FF, gelu, sa);                                           // :2389-2392
         if (!skip("down")) launch_mmv(L.down, xup, f->dn, E, none, sa);                                         // :2394
         B200_CUDA_CHECK(cudaStreamWaitEvent(sa, f->e_join, 0));
-        if (!skip("wo")) launch_mmv(L.wo, xatt, f->ao, E, none, sa);                                            // :2370
-        f->launches += 8;
+        LnTail lt{}; MmvEpilogue wo_epi = none;
+        if (tail && (l + 1 < f->NL || f->last)) {
+            lt.x = f->inp; lt.ra = f->dn; lt.n = E; lt.ctr = f->ln_ctr;
+            if (l + 1 < f->NL) {
+                const Layer & Ln = f->layers[l + 1];
+                if (dual) { lt.g1 = Ln.ln_attn_g; lt.b1 = Ln.ln_attn_b; lt.A1 = xa; lt.g2 = Ln.ln_mlp_g; lt.b2 = Ln.ln_mlp_b; lt.A2 = xm; lt.has2 = 1; }
+                else      { lt.g1 = Ln.ln_mlp_g; lt.b1 = Ln.ln_mlp_b; lt.A1 = xm; lt.A2 = xm; lt.has2 = 0; }
+            } else { lt.g1 = f->lnf_g; lt.b1 = f->lnf_b; lt.A1 = xf; lt.A2 = xf; lt.has2 = 0; }                      // :2422-2431
+            wo_epi.ln = &lt;
+        }
+        if (!skip("wo")) launch_mmv(L.wo, xatt, f->ao, E, wo_epi, sa);                                          // :2370
+        f->launches += (tail && l > 0) ? 7 : 8;
     }
     if (f->last) {
-        launch_layernorm_q(f->inp, E, f->NL > 0 ? f->dn : nullptr, f->NL > 0 ? f->ao : nullptr, E, f->lnf_g, f->lnf_b, &xf, nullptr, nullptr, nullptr, E, 1, sa);   // :2399-2400, 2422-2431
-        launch_mmv(f->lm_head, xf, f->logits, f->V, none, sa); f->launches += 2;                                // :2440
+        if (!(tail && f->NL > 0))
+            launch_layernorm_q(f->inp, E, f->NL > 0 ? f->dn : nullptr, f->NL > 0 ? f->ao : nullptr, E, f->lnf_g, f->lnf_b, &xf, nullptr, nullptr, nullptr, E, 1, sa);   // :2399-2400, 2422-2431
+        launch_mmv(f->lm_head, xf, f->logits, f->V, none, sa); f->launches += (tail && f->NL > 0) ? 1 : 2;      // :2440
     } else {
         if (f->NL > 0) { launch_add3(f->dn, f->ao, f->inp, f->inp, E, sa); f->launches++; }
         B200_NCCL_CHECK(nccl().Send(f->inp, (size_t) E, ncclFloat, f->hp.rank + 1, f->comm, sa));

@@ -21,7 +21,9 @@ enum { EPI_NONE = 0, EPI_GELU = 1, EPI_ADD2 = 2 };
 struct MmvEpilogue { int kind; const float * r1; const float * r2;         // ADD2: y = (dot + r1[m]) + r2[m]
     // optional (fast kernel, N == 1, M % 256 == 0): the output row is also quantised for the NEXT mat-mul (its INIT pass,
     // ggml.c:11462-11476) by whichever CTA completes a 256-value chunk; qctr = M / 256 zero-initialised, self-resetting counters
-    const ActQ * qout; unsigned * qctr; };
+    const ActQ * qout; unsigned * qctr;
+    // optional (fast kernel, N == 1): the last CTA to finish runs the layer-closing residual adds + next LayerNorm(s) + quantisation
+    const struct LnTail * ln; };
 void   launch_mmv(const WPlanes & W, const ActQ & A, float * y, int64_t y_stride, MmvEpilogue epi, cudaStream_t stream);
 void   launch_mmv_f(const WPlanes & W, const float * x, int64_t x_stride, int N, float * y, int64_t y_stride, cudaStream_t stream); // f16/f32 weights
 

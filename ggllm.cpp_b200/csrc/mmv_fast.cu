@@ -170,6 +170,18 @@ __device__ __forceinline__ void mmv_body(const WPlanes & W, const FastX & X, flo
             }
         }
     }
+    if (epi.ln.ctr) {
+        __shared__ int s_last;
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) { const unsigned old = atomicAdd(epi.ln.ctr, 1u); s_last = old == (unsigned) nctas - 1; if (s_last) *epi.ln.ctr = 0; }
+        __syncthreads();
+        if (s_last) {
+            __threadfence();
+            float * sv = reinterpret_cast<float *>(smem + 16 + 2 * NW * 4 * 4 + NW * 8 + (MODE == 0 ? ((W.K + 15) & ~15) : 0));
+            ln_tail_run<NT>(epi.ln, y + (size_t) n * y_stride, sv, red);
+        }
+    }
     trace_end(epi.trace);
 }
 
@@ -189,7 +201,7 @@ static int fast_num_sms() {
 
 template <int TYPE, int NT, int J, int D, int MODE>
 static void launch_mode(const WPlanes & W, const FastX & X, float * y, int64_t y_stride, Epi epi, cudaStream_t stream) {
-    const size_t smem = 16 + 2 * (NT / 32) * 4 * 4 + (NT / 32) * 8 + (size_t) W.K;
+    const size_t smem = 16 + 2 * (NT / 32) * 4 * 4 + (NT / 32) * 8 + (size_t) ((W.K + 15) & ~15) + (epi.ln.ctr ? (size_t) epi.ln.n * 4 : 0);
     static bool set = false;
     if (!set) { B200_CUDA_CHECK(cudaFuncSetAttribute(mmv_fast_kernel<TYPE, NT, J, D, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         // same L1/shared split as the small kernels of the other stream: an SM cannot host kernels with different carve-outs at once
@@ -228,7 +240,11 @@ static bool launch_type(const WPlanes & W, const FastX & X, float * y, int64_t y
 // returns false if the shape / type is not covered (the caller then uses the generic ring kernel of mmv.cu)
 bool launch_mmv_fast_x(const WPlanes & W, const FastX & X, float * y, int64_t y_stride, MmvEpilogue e, cudaStream_t stream) {
     const char * nm = W.M > 40000 ? "mmv_lmhead" : W.K > 16384 ? "mmv_down" : W.M > 16384 ? "mmv_up" : W.M > 8192 ? "mmv_qkv" : "mmv_wo";
-    Epi epi = { e.kind, e.r1, e.r2, b200_trace_slot(nm), ActQ{}, nullptr };
+    Epi epi = { e.kind, e.r1, e.r2, b200_trace_slot(nm), ActQ{}, nullptr, LnTail{} };
+    if (e.ln && e.ln->ctr) {
+        B200_ASSERT(X.N == 1 && e.ln->n == W.M && W.M % 256 == 0);
+        epi.ln = *e.ln;
+    }
     if (e.qout && e.qctr) {
         B200_ASSERT(X.N == 1 && W.M % 256 == 0 && e.qout->K == W.M && (e.qout->type == T_Q8_K || e.qout->type == T_Q8_0));
         epi.qA = *e.qout; epi.qctr = e.qctr;

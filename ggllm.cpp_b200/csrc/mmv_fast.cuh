@@ -2,8 +2,9 @@
 #pragma once
 #include "kernels.h"
 #include "actquant.cuh"
+#include "ln_tail.cuh"
 
-struct Epi { int kind; const float * r1; const float * r2; unsigned long long * trace; ActQ qA; unsigned * qctr; };
+struct Epi { int kind; const float * r1; const float * r2; unsigned long long * trace; ActQ qA; unsigned * qctr; LnTail ln; };
 
 // Where the activation row comes from (FastX, kernels.h):
 //   mode 0: already quantised (ActQ, written by quantize_act / layernorm_q)

@@ -107,6 +107,17 @@ __global__ void __launch_bounds__(LNR_THREADS) layernorm_q_reg_kernel(float * __
     trace_begin(trace);
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the mat-vecs that follow may start prefetching their weights now
     const int row = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // launched with programmatic stream serialisation: gamma / beta do not depend on the previous kernel, so they are
+    // pulled into L2 while it drains; everything below the wait reads what it wrote
+#pragma unroll
+    for (int c = 0; c < CH; c++) {
+        const int e = (c * LNR_THREADS + threadIdx.x) * 8;
+        if (e < n) {
+            asm volatile("prefetch.global.L2 [%0];" :: "l"(g1 + e)); asm volatile("prefetch.global.L2 [%0];" :: "l"(b1 + e));
+            if (has2) { asm volatile("prefetch.global.L2 [%0];" :: "l"(g2 + e)); asm volatile("prefetch.global.L2 [%0];" :: "l"(b2 + e)); }
+        }
+    }
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     float * xr = x + (size_t) row * x_stride;
     float v[CH][8];
     bool ok[CH];
@@ -181,8 +192,14 @@ void launch_layernorm_q(float * x, int64_t x_stride, const float * ra, const flo
     if (n <= 16384 && n % 8 == 0 && !getenv("B200_LN_SMEM")) {
         const bool two = n > 8192;
         unsigned long long * tr = b200_trace_slot("layernorm_q");
-#define LNRQ(T) do { if (two) layernorm_q_reg_kernel<T, 2><<<rows, LNR_THREADS, 0, stream>>>(x, x_stride, ra, rb, r_stride, g1, b1, *A1, g2, b2, a2, A2 != nullptr, n, tr); \
-                     else layernorm_q_reg_kernel<T, 1><<<rows, LNR_THREADS, 0, stream>>>(x, x_stride, ra, rb, r_stride, g1, b1, *A1, g2, b2, a2, A2 != nullptr, n, tr); } while (0)
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3((unsigned) rows); cfg.blockDim = dim3(LNR_THREADS); cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr; cfg.numAttrs = getenv("B200_NO_PDL") ? 0 : 1;
+        const int has2 = A2 != nullptr;
+#define LNRQ(T) do { if (two) B200_CUDA_CHECK(cudaLaunchKernelEx(&cfg, layernorm_q_reg_kernel<T, 2>, x, x_stride, ra, rb, r_stride, g1, b1, *A1, g2, b2, a2, has2, n, tr)); \
+                     else B200_CUDA_CHECK(cudaLaunchKernelEx(&cfg, layernorm_q_reg_kernel<T, 1>, x, x_stride, ra, rb, r_stride, g1, b1, *A1, g2, b2, a2, has2, n, tr)); } while (0)
         switch (A1->type) {
             case T_Q8_0: LNRQ(T_Q8_0); break;
             case T_Q8_1: LNRQ(T_Q8_1); break;

@@ -143,3 +143,19 @@ def test_against_reference_golden_logits(gpu, name):
         flags.append(assert_logits_close(got, g["decode_logits"][i:i + 1], name + " decode %d" % i))
     assert_mostly_tight(flags, name)
     f.free()
+
+
+@pytest.mark.parametrize("env", ["B200_MEGA", "B200_LN_TAIL", "B200_NO_FUSED_DECODE"])
+@pytest.mark.parametrize("hp,wt", [(TINY_40B, po.Q4_K), (TINY_7B, po.Q4_0)])
+def test_alternative_decode_paths_match_oracle(gpu, hp, wt, env):
+    """the opt-in decode paths (persistent all-layers kernel, LayerNorm run by the last CTA of wo) and the generic
+    per-node path compute the same function as the default fused path"""
+    tensors = synth_model(hp, wt, seed=1234)
+    os.environ[env] = "1"
+    try:
+        outs, launches = run_model(gpu, hp, tensors, n_ctx=64, n_batch=8, prompt=[11, 100, 101, 102, 103], n_decode=6)
+    finally:
+        del os.environ[env]
+    assert_mostly_tight([assert_logits_close(got, want, "%s step %d" % (env, i)) for i, (got, want) in enumerate(outs)], env)
+    if env == "B200_MEGA":
+        assert launches <= 5          # embedding + the persistent kernel + final LayerNorm + lm_head
