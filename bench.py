@@ -9,11 +9,13 @@ hot path.  Weights are generated directly as well-formed Q4_K blocks on the devi
   value  : tokens/s with the token id and logits resident in HBM (b200_falcon_decode_dev), timed with CUDA events
   e2e    : tokens/s through the reference-facing C-ABI call b200_falcon_eval with HOST buffers: token id H2D and
            logits D2H inside the timed region
-  roofline: the dominant kernel (mmv_kernel<Q4_K>) timed alone on the model's own matrices with CUDA events
+  roofline: the dominant kernel (mmv_fast_kernel<Q4_K>) timed alone on the model's own matrices with CUDA events;
+           traffic = DRAM bytes per launch from the committed ncu launch list (profiles/r1_traffic.json)
   cpu_baseline / --impl reference: the UNMODIFIED reference's CPU path (oracle/_ref falcon_eval) on the host cores,
            on a bounded sample (a 6-layer slice of the same 40B-shaped model), scaled by weight bytes
-N > 1: contiguous layer ranges, one rank per GPU, the residual stream crosses each boundary by ncclSend/ncclRecv
-(one decode stream: pipeline stages run one after another, so this reports capacity scaling, not speed-up).
+N > 1: contiguous layer ranges, one rank per GPU, the residual stream crosses each boundary by ncclSend/ncclRecv.
+value / e2e use teacher-forced token ids (consecutive tokens overlap across the pipeline stages); config also reports
+autoregressive_tok_s, the strict single-stream rate (the last rank's argmax is broadcast before the next step).
 """
 import argparse
 import json
@@ -257,6 +259,12 @@ def main():
         return
 
     peak, peak_src = peaks()
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as tf:
+            traffic = float(json.load(tf)["dram_bytes_per_matvec_launch"])
+    except Exception:
+        pass
     value = args.steps / (dev_ms / 1e3)
     kv_bytes = hp["n_layer"] * 2 * (pos - args.steps) * hp["n_head_kv"] * 64 * 4
     step_bytes = weight_bytes + kv_bytes
@@ -272,8 +280,9 @@ def main():
                    "ms_per_step": e2e_ms / args.steps, "api": "b200_falcon_eval (host token id in, host logits out)"},
            "gpu_launches": int(launches),
            "clocks": clocks,
-           "roofline": {"bound": "hbm", "kernel": "mmv_kernel<Q4_K> (fused dequantise + int8 dot mat-vec)", "achieved": ach, "peak": peak, "unit": "GB/s",
-                        "frac": ach / peak, "peak_source": peak_src, "traffic": None,
+           "roofline": {"bound": "hbm", "kernel": "mmv_fast_kernel<Q4_K> (register-resident fused dequantise + int8 dot mat-vec)", "achieved": ach, "peak": peak, "unit": "GB/s",
+                        "frac": ach / peak, "peak_source": peak_src, "traffic": traffic,
+                        "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum per mat-vec launch, profiles/r1_bench_launches.csv" if traffic else None,
                         "launches_timed": int(mv_n), "avg_launch_us": mv_ms * 1e3 / max(mv_n, 1), "algorithmic_bytes_per_launch": mv_bytes / max(mv_n, 1),
                         "how": "all resident mat-vecs (4 per layer + lm_head) launched back to back x3 on the eval stream, CUDA events around the region; "
                                "each launch reads a different matrix, one pass = 23.2 GB >> L2",
