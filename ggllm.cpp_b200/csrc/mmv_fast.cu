@@ -49,6 +49,7 @@ __device__ __forceinline__ void mmv_body(const WPlanes & W, const FastX & X, flo
 
     typename T::WR w[D][J];
     ring_fill<TYPE, J, D>(w, wp, row0, row1);                                // weights are in flight before the activation arrives
+    if (epi.ln.ctr && cta == 0) ln_tail_prefetch(epi.ln);
     const L2PF pf = l2pf_of(W, X.l2_dist);
     if (pf.dist > 0 && tid == 0) l2_prefetch_rows(pf, min(row0 + D, row1), min(row0 + D + pf.dist, row1));
 
@@ -178,8 +179,7 @@ __device__ __forceinline__ void mmv_body(const WPlanes & W, const FastX & X, flo
         __syncthreads();
         if (s_last) {
             __threadfence();
-            float * sv = reinterpret_cast<float *>(smem + 16 + 2 * NW * 4 * 4 + NW * 8 + (MODE == 0 ? ((W.K + 15) & ~15) : 0));
-            ln_tail_run<NT>(epi.ln, y + (size_t) n * y_stride, sv, red);
+            ln_tail_run<NT>(epi.ln, y + (size_t) n * y_stride, red);
         }
     }
     trace_end(epi.trace);
@@ -201,7 +201,7 @@ static int fast_num_sms() {
 
 template <int TYPE, int NT, int J, int D, int MODE>
 static void launch_mode(const WPlanes & W, const FastX & X, float * y, int64_t y_stride, Epi epi, cudaStream_t stream) {
-    const size_t smem = 16 + 2 * (NT / 32) * 4 * 4 + (NT / 32) * 8 + (size_t) ((W.K + 15) & ~15) + (epi.ln.ctr ? (size_t) epi.ln.n * 4 : 0);
+    const size_t smem = 16 + 2 * (NT / 32) * 4 * 4 + (NT / 32) * 8 + (size_t) ((W.K + 15) & ~15);
     static bool set = false;
     if (!set) { B200_CUDA_CHECK(cudaFuncSetAttribute(mmv_fast_kernel<TYPE, NT, J, D, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         // same L1/shared split as the small kernels of the other stream: an SM cannot host kernels with different carve-outs at once
@@ -242,7 +242,7 @@ bool launch_mmv_fast_x(const WPlanes & W, const FastX & X, float * y, int64_t y_
     const char * nm = W.M > 40000 ? "mmv_lmhead" : W.K > 16384 ? "mmv_down" : W.M > 16384 ? "mmv_up" : W.M > 8192 ? "mmv_qkv" : "mmv_wo";
     Epi epi = { e.kind, e.r1, e.r2, b200_trace_slot(nm), ActQ{}, nullptr, LnTail{} };
     if (e.ln && e.ln->ctr) {
-        B200_ASSERT(X.N == 1 && e.ln->n == W.M && W.M % 256 == 0);
+        B200_ASSERT(X.N == 1 && e.ln->n == W.M && W.M % 256 == 0 && W.M <= 256 * 8 * 8);
         epi.ln = *e.ln;
     }
     if (e.qout && e.qctr) {
