@@ -84,6 +84,8 @@ void   launch_attention(const float * qkv, const float * k_cache, const float * 
                         const AttnParams & p, float * scratch, cudaStream_t stream);
 size_t attention_scratch_bytes(const AttnParams & p);
 // N > 1 (prompt): tiled two-kernel version with a score scratch matrix (attention_prefill.cu)
+bool   launch_attention_tc(const float * qkv, const float * k_cache, const float * v_cache, float * out, int64_t out_stride,
+                           const AttnParams & p, cudaStream_t stream);       // attention_tc.cu: N > 1 on tcgen05 (head_dim 64)
 size_t attention_prefill_scratch_bytes(int n_head, int n_tok, int T);
 void   launch_attention_prefill(const float * qkv, const float * k_cache, const float * v_cache, float * out, int64_t out_stride,
                                 const AttnParams & p, float * scratch, cudaStream_t stream);

@@ -4,6 +4,7 @@ Bars: bit-exact for integer/byte work (block dequantisation, activation codes + 
 block dots, so only fp32 summation order differs from the CPU -> |err| <= 2e-5 * sum_k |w_k x_k| (stated per test);
 float ops (LayerNorm, GELU, RoPE, softmax/attention) within the tolerances written next to each assert.
 """
+import os
 import numpy as np
 import pytest
 import pyoracle as po
@@ -196,7 +197,11 @@ def test_attention(gpu, orc, n_head, n_head_kv, n_tok, n_past):
     vc[:n_past] = rng.standard_normal((n_past, n_head_kv, hd)).astype(np.float32)
     qkv = rng.standard_normal((n_tok, QKV)).astype(np.float32)
     qd, kd, vd, od = gpu.DevBuf(src=qkv), gpu.DevBuf(src=kc), gpu.DevBuf(src=vc), gpu.DevBuf(n_tok * n_head * hd * 4)
-    gpu.lib().b200_attention(qd.ptr, kd.ptr, vd.ptr, od.ptr, n_head, n_head_kv, hd, n_tok, n_past, n_ctx, n_ctx)
+    os.environ["B200_ATTN_TC"] = "1"            # tensor-core kernel for every n_tok > 1 (the engine uses it for n_tok > 8)
+    try:
+        gpu.lib().b200_attention(qd.ptr, kd.ptr, vd.ptr, od.ptr, n_head, n_head_kv, hd, n_tok, n_past, n_ctx, n_ctx)
+    finally:
+        del os.environ["B200_ATTN_TC"]
     got = od.download(np.float32, (n_tok, n_head, hd))
     # oracle
     q3 = qkv.reshape(n_tok, -1, hd)
@@ -216,8 +221,21 @@ def test_attention(gpu, orc, n_head, n_head_kv, n_tok, n_past):
             want[t, h] = p @ vc[:T, h // grp]
     # tolerance: the exp LUT rounds (s - max) to fp16, so a 1e-6 difference in a score can move one probability
     # by one fp16 ulp (2^-11 relative); outputs are O(1) averages of V
-    assert np.allclose(got, want, rtol=0, atol=2e-3)
-    assert np.median(np.abs(got - want)) < 2e-6
+    if n_tok == 1:                      # decode kernel: fp32 throughout
+        assert np.allclose(got, want, rtol=0, atol=2e-3)
+        assert np.median(np.abs(got - want)) < 2e-6
+    else:                               # tensor-core kernel: Q, K, V rounded to fp16 (2^-11 relative), fp32 accumulation, P exact
+        assert np.allclose(got, want, rtol=0, atol=5e-3)
+        assert np.median(np.abs(got - want)) < 5e-4
+        os.environ["B200_ATTN_SIMT"] = "1"      # the CUDA-core fp32 kernels it replaces keep the tight bound
+        qd2 = gpu.DevBuf(src=qkv)
+        try:
+            gpu.lib().b200_attention(qd2.ptr, kd.ptr, vd.ptr, od.ptr, n_head, n_head_kv, hd, n_tok, n_past, n_ctx, n_ctx)
+        finally:
+            del os.environ["B200_ATTN_SIMT"]
+        got = od.download(np.float32, (n_tok, n_head, hd))
+        assert np.allclose(got, want, rtol=0, atol=2e-3)
+        assert np.median(np.abs(got - want)) < 2e-6
 
 
 @pytest.mark.parametrize("t,M,K,N,gelu", [(po.Q4_K, 256, 512, 40, 0), (po.Q4_K, 1000, 1024, 300, 0), (po.Q4_K, 384, 2048, 512, 1),
