@@ -170,7 +170,7 @@ def main():
     if args.layers:
         hp["n_layer"] = args.layers
         config["INVALID_debug_layers"] = args.layers
-    f = b.Falcon(hp, n_ctx=config["n_ctx"], n_batch=1, rank=rank, world=world)
+    f = b.Falcon(hp, n_ctx=config["n_ctx"], n_batch=int(os.environ.get("BENCH_NBATCH", "512")), rank=rank, world=world)      # 512: the prompt leg below (BASELINE config 3); decode uses row 0
     f.set_random(ggcc.falcon_shapes(hp), Q4_K, seed=1234)
     if world > 1:
         ids = [b.Falcon.nccl_unique_id() if rank == 0 else None]
@@ -242,14 +242,27 @@ def main():
         barrier()
         auto_ms = (time.perf_counter() - t0) * 1e3 / n_auto
 
+    # ---- BASELINE's second headline number: prompt processing, n_batch = 512, 2048 synthetic tokens (4 evals at n_past
+    # 0 / 512 / 1024 / 1536) through the same host-buffer C-ABI call; reported beside the decode metric, not as `value`
+    ptoks = np.random.default_rng(7).integers(12, hp["n_vocab"], size=2048).astype(np.int32)
+    prompt_s = float("nan")
+    if int(os.environ.get("BENCH_NBATCH", "512")) >= 512:
+        f.eval(ptoks[:512], 0, 0)                      # warm-up (tensor maps, scratch)
+        barrier()
+        t0 = time.perf_counter()
+        for c in range(4):
+            f.eval(ptoks[512 * c: 512 * (c + 1)], 512 * c, 0)
+        barrier()
+        prompt_s = time.perf_counter() - t0
+
     # ---- dominant kernel alone (roofline): every resident mat-vec back to back, CUDA events
     mv_ms, mv_n, mv_bytes = f.profile_matvec(reps=3)
 
     if dist is not None:
         import torch
-        t = torch.tensor([dev_ms, e2e_s * 1e3, t_wall * 1e3, auto_ms], device="cuda")
+        t = torch.tensor([dev_ms, e2e_s * 1e3, t_wall * 1e3, auto_ms, prompt_s], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dev_ms, e2e_ms, wall_ms, auto_ms = [float(v) for v in t.tolist()]
+        dev_ms, e2e_ms, wall_ms, auto_ms, prompt_s = [float(v) for v in t.tolist()]
         agg = torch.tensor([float(f.weight_bytes()), float(launches)], device="cuda", dtype=torch.float64)
         dist.all_reduce(agg, op=dist.ReduceOp.SUM)
         weight_bytes, launches = [float(v) for v in agg.tolist()]      # the roofline probe stays per GPU (rank 0's own matrices)
@@ -288,7 +301,11 @@ def main():
                                "each launch reads a different matrix, one pass = 23.2 GB >> L2",
                         "step_achieved_GBs_per_gpu": step_bytes * value / 1e9 / world, "step_frac": step_bytes * value / 1e9 / world / peak,
                         "step_bytes": step_bytes, "step_roofline_tok_s_per_gpu": peak * 1e9 / step_bytes},
-           "wall_ms_per_step": wall_ms / args.steps}
+           "wall_ms_per_step": wall_ms / args.steps,
+           "prompt": {"tok_s": 2048 / prompt_s, "tokens": 2048, "n_batch": 512, "seconds": prompt_s,
+                      "matmul_TFLOPs": 2.0 * (weight_bytes / 0.5625) * 2048 / prompt_s / 1e12,
+                      "what": "Falcon-40B Q4_K prompt (BASELINE config 3): 4 x b200_falcon_eval of 512 host tokens, tcgen05 GEMM with fused "
+                              "dequantisation + tcgen05 attention, wall clock incl. H2D / D2H"}}
     if world == 1 and not args.no_cpu_baseline:
         try:
             r = reference_cpu_decode(steps=8, warmup=2)

@@ -85,11 +85,272 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_kernel(const float * __
     trace_end(p.trace);
 }
 
-size_t attention_scratch_bytes(const AttnParams &) { return 0; }
+// ------------------------------------------------------------------------------------------------------------------
+// Split-KV decode attention (n_tok == 1, head_dim 64).  The kernel above walks a head's keys with one 128-thread CTA and
+// re-reads the KV head's K / V once per query head: fine at 100 keys, 745 us per layer at 8192 (tools/ctx_decode.py:
+// 210 tok/s at n_past 8, 20 tok/s at 8184).  Here the G query heads of a KV head are processed TOGETHER (K / V are read
+// once per KV head) and the keys are split over AT_SPLITS CTAs per KV head:
+//   kernel 1 (scores): a warp takes one key per step, lane l holds dims 2l, 2l+1 of the key (one coalesced 256-byte row) and
+//                      of the G <= 16 query vectors; G partial dots per lane are reduced with a transposing butterfly
+//                      (16 shuffles); s = dot * scale goes to the scratch row S[head][key], per-(head, split) maxima on the side
+//   kernel 2 (values) : gmax = max over splits; e = LUT(s - gmax) for the CTA's own keys (shared memory, [key][head]),
+//                      their sum in double per (head, split); O_partial[head][d] += V[key][d] * e (lane = 2 dims, G heads
+//                      in registers); the LAST CTA of a KV head sums the partial sums and outputs in split order and scales by
+//                      (float)(1 / sum)  -- ggml.c:12427-12449 multiplies each e by that factor before the product with V;
+//                      scaling the product instead is a reassociation-level difference (as the tensor-core prompt kernel does).
+// Both kernels read n_past from a device scalar, so the captured decode graph serves every position.
+#define AD_THREADS 128                   // small CTAs at <= 85 registers: one fits beside ffn_up's two 256-thread CTAs on every SM
+#define AD_WARPS (AD_THREADS / 32)
+#define AD_SPLITS 32
+#define AD_B 4                           // key rows per warp step (plus the same number in flight for the next step)
+#define AD_G 16                          // query heads per KV head handled together (n_head / n_head_kv <= 16)
 
-void launch_attention(const float * qkv, const float * k_cache, const float * v_cache, float * out, int64_t out_stride,
-                      const AttnParams & p, float *, cudaStream_t stream) {
-    if (p.n_tok <= 0) return;
+struct AttnDecArgs {
+    const float * qkv; const float * kc; const float * vc; float * out;
+    float * S; float * pmax; double * psum; float * opart; unsigned * ctr;
+    int n_head, n_head_kv, G, n_past; const int * n_past_dev; int n_ctx; int64_t qkv_stride;
+    unsigned long long * trace;
+};
+
+// 16 per-lane values -> lane l ends up with the warp total of value (l >> 1)
+__device__ __forceinline__ float butterfly16(float (&v)[16], int lane) {
+    float w8[8], w4[4], w2[2];
+    const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2;
+#pragma unroll
+    for (int i = 0; i < 8; i++) { const float keep = b4 ? v[8 + i] : v[i], send = b4 ? v[i] : v[8 + i]; w8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16); }
+#pragma unroll
+    for (int i = 0; i < 4; i++) { const float keep = b3 ? w8[4 + i] : w8[i], send = b3 ? w8[i] : w8[4 + i]; w4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8); }
+#pragma unroll
+    for (int i = 0; i < 2; i++) { const float keep = b2 ? w4[2 + i] : w4[i], send = b2 ? w4[i] : w4[2 + i]; w2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4); }
+    const float keep = b1 ? w2[1] : w2[0], send = b1 ? w2[0] : w2[1];
+    float r = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+    r += __shfl_xor_sync(0xffffffffu, r, 1);
+    return r;
+}
+__device__ __forceinline__ void split_range(int T, int split, int & k_lo, int & k_hi) {
+    const int per = (T + AD_SPLITS - 1) / AD_SPLITS;
+    k_lo = min(T, split * per); k_hi = min(T, k_lo + per);
+}
+
+__global__ void __launch_bounds__(AD_THREADS, 6) attn_dec_scores_kernel(const AttnDecArgs a) {
+    __shared__ float wmax[AD_WARPS][AD_G];
+    trace_begin(a.trace);
+    const int split = blockIdx.x, kvh = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int h0 = kvh * a.G + blockIdx.z * AD_G, G = min(AD_G, a.G - (int) blockIdx.z * AD_G);      // this CTA's query heads: h0 .. h0 + G - 1
+    const int n_past = a.n_past_dev ? *a.n_past_dev : a.n_past, T = n_past + 1;
+    int k_lo, k_hi; split_range(T, split, k_lo, k_hi);
+    const float scale = 1.0f / sqrtf(64.0f);
+    const size_t kv_row = (size_t) a.n_head_kv * 64;
+    float2 q[AD_G];
+#pragma unroll
+    for (int h = 0; h < AD_G; h++)
+        q[h] = h < G ? *reinterpret_cast<const float2 *>(a.qkv + (size_t) (h0 + h) * 64 + 2 * lane) : make_float2(0.f, 0.f);
+    const int hh = lane >> 1;                                     // the head whose total this lane receives
+    float lmax = -INFINITY;
+    const float * kp = a.kc + (size_t) kvh * 64 + 2 * lane;
+    // AD_B keys per warp and step, the next batch's rows already in flight (memory-level parallelism without more warps)
+    float2 cur[AD_B], nxt[AD_B];
+#pragma unroll
+    for (int b = 0; b < AD_B; b++) { const int kk = k_lo + warp + b * AD_WARPS; cur[b] = kk < k_hi ? __ldg(reinterpret_cast<const float2 *>(kp + (size_t) kk * kv_row)) : make_float2(0.f, 0.f); }
+    for (int k = k_lo + warp; k < k_hi; k += AD_B * AD_WARPS) {
+#pragma unroll
+        for (int b = 0; b < AD_B; b++) { const int kk = k + (AD_B + b) * AD_WARPS; nxt[b] = kk < k_hi ? __ldg(reinterpret_cast<const float2 *>(kp + (size_t) kk * kv_row)) : make_float2(0.f, 0.f); }
+#pragma unroll
+        for (int b = 0; b < AD_B; b++) {
+            const int kk = k + b * AD_WARPS;
+            float part[AD_G];
+#pragma unroll
+            for (int h = 0; h < AD_G; h++) part[h] = cur[b].x * q[h].x + cur[b].y * q[h].y;
+            const float s = __fmul_rn(butterfly16(part, lane), scale);   // libfalcon.cpp:2313-2317
+            if (hh < G && kk < k_hi) {
+                if ((lane & 1) == 0) a.S[(size_t) (h0 + hh) * a.n_ctx + kk] = s;
+                lmax = fmaxf(lmax, s);
+            }
+        }
+#pragma unroll
+        for (int b = 0; b < AD_B; b++) cur[b] = nxt[b];
+    }
+    if ((lane & 1) == 0 && hh < AD_G) wmax[warp][hh] = lmax;
+    __syncthreads();
+    if (threadIdx.x < G) {
+        float mx = wmax[0][threadIdx.x];
+#pragma unroll
+        for (int w = 1; w < AD_WARPS; w++) mx = fmaxf(mx, wmax[w][threadIdx.x]);
+        a.pmax[(size_t) (h0 + threadIdx.x) * AD_SPLITS + split] = mx;
+    }
+    trace_end(a.trace);
+}
+
+__global__ void __launch_bounds__(AD_THREADS, 6) attn_dec_values_kernel(const AttnDecArgs a, const int per_max) {
+    extern __shared__ __align__(16) float sm_dyn[];                // es[per_max][AD_G]
+    __shared__ float gmax[AD_G];
+    __shared__ double dsum[AD_THREADS / AD_G][AD_G];
+    __shared__ float2 oacc[AD_WARPS][AD_G][32];                    // per-warp partial outputs: [head][lane] = dims 2l, 2l+1
+    __shared__ float inv_s[AD_G];
+    __shared__ int s_last;
+    float * es = sm_dyn;
+    const int split = blockIdx.x, kvh = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int h0 = kvh * a.G + blockIdx.z * AD_G, G = min(AD_G, a.G - (int) blockIdx.z * AD_G);
+    const int n_past = a.n_past_dev ? *a.n_past_dev : a.n_past, T = n_past + 1;
+    int k_lo, k_hi; split_range(T, split, k_lo, k_hi);
+    const int nk = k_hi - k_lo;
+    const size_t kv_row = (size_t) a.n_head_kv * 64;
+    trace_begin(a.trace);
+    if (tid < AD_G) {
+        float mx = -INFINITY;
+        if (tid < G) for (int s = 0; s < AD_SPLITS; s++) mx = fmaxf(mx, a.pmax[(size_t) (h0 + tid) * AD_SPLITS + s]);
+        gmax[tid] = mx;
+    }
+    __syncthreads();
+    // e = table_exp_f16[f16(s - max)] (ggml.c:12427-12440) for the CTA's keys, sums in double
+    {
+        const int h = tid % AD_G;
+        double s = 0.0;
+        if (h < G) {
+            const float * Sr = a.S + (size_t) (h0 + h) * a.n_ctx + k_lo;
+            for (int j = tid / AD_G; j < nk; j += AD_THREADS / AD_G) {
+                const float e = exp_f16lut(__fsub_rn(__ldcg(Sr + j), gmax[h]));
+                es[j * AD_G + h] = e; s += (double) e;
+            }
+        } else for (int j = tid / AD_G; j < nk; j += AD_THREADS / AD_G) es[j * AD_G + h] = 0.f;
+        dsum[tid / AD_G][h] = s;
+    }
+    __syncthreads();
+    if (tid < G) {
+        double s = 0.0;
+#pragma unroll
+        for (int r = 0; r < AD_THREADS / AD_G; r++) s += dsum[r][tid];
+        a.psum[(size_t) (h0 + tid) * AD_SPLITS + split] = s;
+    }
+    // O_partial[h][2l..2l+1] = sum over the warp's keys of V[key][2l..2l+1] * e[key][h]
+    float2 acc[AD_G];
+#pragma unroll
+    for (int h = 0; h < AD_G; h++) acc[h] = make_float2(0.f, 0.f);
+    const float * vp = a.vc + (size_t) kvh * 64 + 2 * lane;
+    float2 cur[AD_B], nxt[AD_B];
+#pragma unroll
+    for (int b = 0; b < AD_B; b++) { const int jj = warp + b * AD_WARPS; cur[b] = jj < nk ? __ldg(reinterpret_cast<const float2 *>(vp + (size_t) (k_lo + jj) * kv_row)) : make_float2(0.f, 0.f); }
+    for (int j = warp; j < nk; j += AD_B * AD_WARPS) {
+#pragma unroll
+        for (int b = 0; b < AD_B; b++) { const int jj = j + (AD_B + b) * AD_WARPS; nxt[b] = jj < nk ? __ldg(reinterpret_cast<const float2 *>(vp + (size_t) (k_lo + jj) * kv_row)) : make_float2(0.f, 0.f); }
+#pragma unroll
+        for (int b = 0; b < AD_B; b++) {
+            const int jj = j + b * AD_WARPS;
+            if (jj < nk) {                                                    // warp-uniform
+                const float4 * er = reinterpret_cast<const float4 *>(es + jj * AD_G);
+                const float2 vv = cur[b];
+#pragma unroll
+                for (int c = 0; c < AD_G / 4; c++) {
+                    const float4 e = er[c];
+                    acc[4 * c].x += vv.x * e.x;     acc[4 * c].y += vv.y * e.x;
+                    acc[4 * c + 1].x += vv.x * e.y; acc[4 * c + 1].y += vv.y * e.y;
+                    acc[4 * c + 2].x += vv.x * e.z; acc[4 * c + 2].y += vv.y * e.z;
+                    acc[4 * c + 3].x += vv.x * e.w; acc[4 * c + 3].y += vv.y * e.w;
+                }
+            }
+        }
+#pragma unroll
+        for (int b = 0; b < AD_B; b++) cur[b] = nxt[b];
+    }
+#pragma unroll
+    for (int h = 0; h < AD_G; h++) oacc[warp][h][lane] = acc[h];
+    __syncthreads();
+    for (int i = tid; i < AD_G * 32; i += AD_THREADS) {             // fixed warp order: deterministic
+        const int h = i / 32, l = i % 32;
+        float2 r = oacc[0][h][l];
+#pragma unroll
+        for (int w = 1; w < AD_WARPS; w++) { r.x += oacc[w][h][l].x; r.y += oacc[w][h][l].y; }
+        if (h < G) *reinterpret_cast<float2 *>(a.opart + ((size_t) (split * a.n_head + h0 + h)) * 64 + 2 * l) = r;
+    }
+    // the last CTA of this KV head combines the splits
+    __threadfence();
+    __syncthreads();
+    unsigned * ctr = a.ctr + kvh * gridDim.z + blockIdx.z;
+    if (tid == 0) { const unsigned old = atomicAdd(ctr, 1u); s_last = old == AD_SPLITS - 1; if (s_last) *ctr = 0; }
+    __syncthreads();
+    if (!s_last) { trace_end(a.trace); return; }
+    __threadfence();
+    if (tid < AD_G) {
+        double s = 0.0;
+        if (tid < G) for (int sp = 0; sp < AD_SPLITS; sp++) s += __ldcg(a.psum + (size_t) (h0 + tid) * AD_SPLITS + sp);
+        inv_s[tid] = (float) (1.0 / s);
+    }
+    __syncthreads();
+    // 16 x 64 outputs as 256 float4 items, two per thread, every split's partial read once: batches of 8 splits x 2 items in
+    // flight (this tail is the fixed cost of the kernel, keep it short)
+    {
+        const int i0 = tid, i1 = tid + AD_THREADS;                          // item = (head, 4 dims): head = i / 16, dims 4 * (i % 16)
+        float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0;
+        const float * base = a.opart + (size_t) h0 * 64;
+#pragma unroll 1
+        for (int sp = 0; sp < AD_SPLITS; sp += 8) {
+            float4 t0[8], t1[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const float * ps = base + (size_t) (sp + u) * a.n_head * 64;
+                t0[u] = i0 / 16 < G ? __ldcg(reinterpret_cast<const float4 *>(ps) + i0) : make_float4(0.f, 0.f, 0.f, 0.f);
+                t1[u] = i1 / 16 < G ? __ldcg(reinterpret_cast<const float4 *>(ps) + i1) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < 8; u++) {                                   // fixed split order: deterministic
+                r0.x += t0[u].x; r0.y += t0[u].y; r0.z += t0[u].z; r0.w += t0[u].w;
+                r1.x += t1[u].x; r1.y += t1[u].y; r1.z += t1[u].z; r1.w += t1[u].w;
+            }
+        }
+        const int hA = i0 / 16, hB = i1 / 16;
+        if (hA < G) { const float s = inv_s[hA]; *(reinterpret_cast<float4 *>(a.out + (size_t) h0 * 64) + i0) = make_float4(__fmul_rn(r0.x, s), __fmul_rn(r0.y, s), __fmul_rn(r0.z, s), __fmul_rn(r0.w, s)); }
+        if (hB < G) { const float s = inv_s[hB]; *(reinterpret_cast<float4 *>(a.out + (size_t) h0 * 64) + i1) = make_float4(__fmul_rn(r1.x, s), __fmul_rn(r1.y, s), __fmul_rn(r1.z, s), __fmul_rn(r1.w, s)); }
+    }
+    trace_end(a.trace);
+}
+
+static size_t align256(size_t v) { return (v + 255) & ~(size_t) 255; }
+#define AD_CTR_BYTES 4096                 // arrival counters at the START of the scratch block (n_head_kv * head groups <= 1024)
+size_t attention_scratch_bytes(const AttnParams & p) {
+    if (p.n_tok != 1 || p.head_dim != 64) return 0;
+    return AD_CTR_BYTES + align256((size_t) p.n_head * p.n_ctx * 4) + align256((size_t) p.n_head * AD_SPLITS * 4) + align256((size_t) p.n_head * AD_SPLITS * 8) +
+           align256((size_t) AD_SPLITS * p.n_head * 64 * 4);
+}
+// scratch: attention_scratch_bytes(p) bytes whose first AD_CTR_BYTES were zeroed once by the owner (the counters re-arm themselves)
+static bool launch_attention_split(const float * qkv, const float * k_cache, const float * v_cache, float * out, const AttnParams & p, float * scratch, cudaStream_t stream) {
+    if (!scratch || p.n_tok != 1 || p.head_dim != 64 || p.n_head % p.n_head_kv || getenv("B200_ATTN_NOSPLIT")) return false;
+    const int G = p.n_head / p.n_head_kv, groups = (G + AD_G - 1) / AD_G;
+    if ((size_t) p.n_head_kv * groups * 4 > AD_CTR_BYTES) return false;
+    const int per_max = (p.n_ctx + AD_SPLITS - 1) / AD_SPLITS;
+    const size_t smem = (size_t) per_max * AD_G * 4;
+    if (smem > 160 * 1024) return false;
+    AttnDecArgs a;
+    uint8_t * s = reinterpret_cast<uint8_t *>(scratch);
+    a.ctr = reinterpret_cast<unsigned *>(s); s += AD_CTR_BYTES;
+    a.S = reinterpret_cast<float *>(s); s += align256((size_t) p.n_head * p.n_ctx * 4);
+    a.pmax = reinterpret_cast<float *>(s); s += align256((size_t) p.n_head * AD_SPLITS * 4);
+    a.psum = reinterpret_cast<double *>(s); s += align256((size_t) p.n_head * AD_SPLITS * 8);
+    a.opart = reinterpret_cast<float *>(s);
+    a.qkv = qkv; a.kc = k_cache; a.vc = v_cache; a.out = out;
+    a.n_head = p.n_head; a.n_head_kv = p.n_head_kv; a.G = p.n_head / p.n_head_kv; a.n_past = p.n_past; a.n_past_dev = p.n_past_dev; a.n_ctx = p.n_ctx;
+    a.qkv_stride = p.qkv_stride;
+    static bool set = false;
+    if (!set) {
+        B200_CUDA_CHECK(cudaFuncSetAttribute(attn_dec_values_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        B200_CUDA_CHECK(cudaFuncSetAttribute(attn_dec_scores_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, B200_CARVEOUT));
+        B200_CUDA_CHECK(cudaFuncSetAttribute(attn_dec_values_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, B200_CARVEOUT));
+        set = true;
+    }
+    dim3 grid(AD_SPLITS, (unsigned) p.n_head_kv, (unsigned) groups);
+    a.trace = b200_trace_slot("attn_scores");
+    attn_dec_scores_kernel<<<grid, AD_THREADS, 0, stream>>>(a);
+    B200_CUDA_CHECK(cudaGetLastError());
+    a.trace = b200_trace_slot("attn_values");
+    attn_dec_values_kernel<<<grid, AD_THREADS, smem, stream>>>(a, per_max);
+    B200_CUDA_CHECK(cudaGetLastError());
+    return true;
+}
+
+// returns the number of kernels launched
+int launch_attention(const float * qkv, const float * k_cache, const float * v_cache, float * out, int64_t out_stride,
+                      const AttnParams & p, float * scratch, cudaStream_t stream) {
+    if (p.n_tok <= 0) return 0;
+    if (launch_attention_split(qkv, k_cache, v_cache, out, p, scratch, stream)) return 2;
     B200_ASSERT(p.head_dim % 4 == 0 && ATT_THREADS % p.head_dim == 0);
     // shared memory is sized for the worst case so that a captured graph stays valid while n_past grows
     const int t_max = p.n_past_dev ? p.n_ctx : p.n_past + p.n_tok;
@@ -102,4 +363,5 @@ void launch_attention(const float * qkv, const float * k_cache, const float * v_
     AttnParams pt = p; pt.trace = b200_trace_slot("attention");
     attention_kernel<<<grid, ATT_THREADS, smem, stream>>>(qkv, k_cache, v_cache, out, out_stride, pt);
     B200_CUDA_CHECK(cudaGetLastError());
+    return 1;
 }

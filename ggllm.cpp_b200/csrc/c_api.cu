@@ -205,7 +205,12 @@ void b200_attention(float * qkv, float * kc, float * vc, float * out, int n_head
     if (n_tok > 1) {
         float * sc = (float *) scratch(attention_prefill_scratch_bytes(n_head, n_tok, n_past + n_tok));
         launch_attention_prefill(qkv, kc, vc, out, (int64_t) n_head * head_dim, p, sc, g_stream);
-    } else launch_attention(qkv, kc, vc, out, (int64_t) n_head * head_dim, p, nullptr, g_stream);
+    } else {
+        const size_t sb = attention_scratch_bytes(p);
+        float * sc = sb ? (float *) scratch(sb) : nullptr;
+        if (sc) B200_CUDA_CHECK(cudaMemsetAsync(sc, 0, 4096, g_stream));      // arrival counters (the shared scratch block may hold anything)
+        launch_attention(qkv, kc, vc, out, (int64_t) n_head * head_dim, p, sc, g_stream);
+    }
 }
 
 } // extern "C"

@@ -70,6 +70,7 @@ struct b200_falcon {
     __half * xh_a = nullptr, * xh_b = nullptr;      // fp16 GEMM operands, one per branch
     void * gemm_ws_a = nullptr, * gemm_ws_b = nullptr; size_t gemm_ws_bytes = 0;
     float * attn_scratch = nullptr;
+    float * attn_dec_scratch = nullptr;            // split-KV decode attention: counters + scores + partials (attention.cu)
     float * inp2 = nullptr, * ao2 = nullptr, * dn2 = nullptr;      // ping-pong partners of inp / ao / dn for the fused decode path
     int32_t * tokens_dev = nullptr; int * n_past_dev = nullptr;
     int32_t * tokens_h = nullptr; int * n_past_h = nullptr; float * logits_h = nullptr; size_t logits_h_floats = 0;
@@ -185,6 +186,11 @@ b200_falcon * b200_falcon_create(const b200_falcon_params * p) {
 }
 
 static void ensure_actq(b200_falcon * f) {
+    if (!f->attn_dec_scratch) {
+        AttnParams ap = { f->H, f->HKV, f->D, 1, 0, nullptr, f->hp.n_ctx, (int64_t) f->QKV, nullptr };
+        const size_t sb = attention_scratch_bytes(ap);
+        if (sb) { B200_CUDA_CHECK(cudaMalloc(&f->attn_dec_scratch, sb)); B200_CUDA_CHECK(cudaMemset(f->attn_dec_scratch, 0, sb)); }
+    }
     if (!f->ln_ctr) { B200_CUDA_CHECK(cudaMalloc(&f->ln_ctr, sizeof(unsigned))); B200_CUDA_CHECK(cudaMemset(f->ln_ctr, 0, sizeof(unsigned))); }
     if (!f->q_ctr) { B200_CUDA_CHECK(cudaMalloc(&f->q_ctr, (size_t) (f->FF / 256 + 1) * sizeof(unsigned))); B200_CUDA_CHECK(cudaMemset(f->q_ctr, 0, (size_t) (f->FF / 256 + 1) * sizeof(unsigned))); }
     if (f->actq_mem || f->act_type < 0) return;
@@ -319,7 +325,7 @@ void b200_falcon_free(b200_falcon * f) {
     cudaFree(f->lnf_g); cudaFree(f->lnf_b); cudaFree(f->k_cache); cudaFree(f->v_cache);
     cudaFree(f->inp); cudaFree(f->qkv); cudaFree(f->att); cudaFree(f->ao); cudaFree(f->up); cudaFree(f->dn); cudaFree(f->logits);
     cudaFree(f->inp2); cudaFree(f->ao2); cudaFree(f->dn2); cudaFree(f->attn_scratch); cudaFree(f->actq_mem); cudaFree(f->xh_a); cudaFree(f->xh_b); cudaFree(f->gemm_ws_a); cudaFree(f->gemm_ws_b);
-    cudaFree(f->tokens_dev); cudaFree(f->n_past_dev); cudaFree(f->mega_layers); cudaFree(f->mega_flags); cudaFree(f->q_ctr); cudaFree(f->ln_ctr);
+    cudaFree(f->tokens_dev); cudaFree(f->n_past_dev); cudaFree(f->mega_layers); cudaFree(f->mega_flags); cudaFree(f->q_ctr); cudaFree(f->ln_ctr); cudaFree(f->attn_dec_scratch);
     cudaFreeHost(f->tokens_h); cudaFreeHost(f->n_past_h); cudaFreeHost(f->logits_h);
     for (int i = 0; i < 2; i++) if (f->graph[i]) cudaGraphExecDestroy(f->graph[i]);
     if (f->comm) nccl().CommDestroy(f->comm);
@@ -432,7 +438,7 @@ static void enqueue_decode_fused(b200_falcon * f, int n_past, float theta_scale,
         const size_t kvoff = (size_t) l * f->hp.n_ctx * f->HKV * f->D;
         if (!skip("attn")) {
         launch_rope_kv_append(f->qkv, f->k_cache + kvoff, f->v_cache + kvoff, ap, theta_scale, sb);             // :2229-2281
-        launch_attention(f->qkv, f->k_cache + kvoff, f->v_cache + kvoff, f->att, E, ap, nullptr, sb);           // :2285-2366
+        f->launches += launch_attention(f->qkv, f->k_cache + kvoff, f->v_cache + kvoff, f->att, E, ap, f->attn_dec_scratch, sb) - 1; // :2285-2366
         launch_quantize_act(f->att, E, xatt, sb);                                                               // wo's INIT pass, off the critical path
         }
         B200_CUDA_CHECK(cudaEventRecord(f->e_join, sb));
@@ -500,7 +506,7 @@ static void enqueue_eval(b200_falcon * f, int N, int n_past, float theta_scale, 
         if (N > 1 && !graph_mode) {
             if (!f->attn_scratch) B200_CUDA_CHECK(cudaMalloc(&f->attn_scratch, attention_prefill_scratch_bytes(f->H, f->hp.n_batch, f->hp.n_ctx)));
             launch_attention_prefill(f->qkv, f->k_cache + kvoff, f->v_cache + kvoff, f->att, E, ap, f->attn_scratch, sa); f->launches++;
-        } else launch_attention(f->qkv, f->k_cache + kvoff, f->v_cache + kvoff, f->att, E, ap, nullptr, sa);     // :2285-2366
+        } else launch_attention(f->qkv, f->k_cache + kvoff, f->v_cache + kvoff, f->att, E, ap, N == 1 ? f->attn_dec_scratch : nullptr, sa);     // :2285-2366
         launch_quantize_act(f->att, E, xatt, sa);
         f->launches += 3;
         mm(f, L.wo, xatt, N, f->ao, E, EPI_NONE, nullptr, nullptr, f->xh_a, f->gemm_ws_a, sa);                  // :2370

@@ -80,7 +80,7 @@ struct AttnParams {
 // fused: rope(Q), rope(K) -> K cache append, V cache append      (libfalcon.cpp:2229-2281)
 void   launch_rope_kv_append(float * qkv, float * k_cache, float * v_cache, const AttnParams & p, float theta_scale, cudaStream_t stream);
 // out[t][h*head_dim + i] = softmax(scale * Q K^T + causal mask) V   (libfalcon.cpp:2285-2366)
-void   launch_attention(const float * qkv, const float * k_cache, const float * v_cache, float * out, int64_t out_stride,
+int    launch_attention(const float * qkv, const float * k_cache, const float * v_cache, float * out, int64_t out_stride,
                         const AttnParams & p, float * scratch, cudaStream_t stream);
 size_t attention_scratch_bytes(const AttnParams & p);
 // N > 1 (prompt): tiled two-kernel version with a score scratch matrix (attention_prefill.cu)
