@@ -13,16 +13,17 @@
 //   S[128 x 128] = Q[128 x 64] K^T      tcgen05.mma.kind::f16  M 128, N 128, 4 x K 16     -> TMEM columns [0, 128)
 //   O[128 x 64] += P[128 x 128] V       tcgen05.mma.kind::f16  M 128, N  64, 8 x K 16     -> TMEM columns [128, 192)
 // Operands are converted fp32 -> fp16 by the CTA's 128 threads straight into the K-major SWIZZLE_128B layout
-// (V transposed on the way: the cache is [key][d], the B operand wants [d][key]); thread t owns TMEM lane t = row t.
+// (V transposed on the way: the cache is [key][d], the B operand wants [d][key]); threads t and t + 128 own TMEM lane t =
+// row t and split its columns (conversion work, softmax and the exp LUT are what bounds this kernel, not the MMAs).
 // 82 KB of shared memory and 256 TMEM columns per CTA: two CTAs per SM overlap each other's load / MMA / softmax phases.
 // Precision: Q, K, V rounded to fp16 (11 bits), fp32 accumulation; P exact.  Tolerance: tests/test_falcon_gpu.py (GEMM path).
 #include "kernels.h"
 
 namespace {
 
-constexpr int AT_M = 128, AT_N = 128, AT_D = 64, AT_THREADS = 128;
-constexpr int SQ = 0, SK = 16384, SV = 32768, SP = 49152, SBAR = 81920;      // byte offsets in the (1024-aligned) shared memory
-constexpr size_t AT_SMEM = 1024 + 81920 + 64;
+constexpr int AT_M = 128, AT_N = 128, AT_D = 64, AT_THREADS = 256;      // two threads per query row: thread t and t + 128 split the columns
+constexpr int SQ = 0, SK = 16384, SV = 32768, SP = 49152, SBAR = 81920, SX = 81984;      // byte offsets in the (1024-aligned) shared memory
+constexpr size_t AT_SMEM = 1024 + 81984 + 2 * 128 * 4;                                   // SX: per-row exchange between the two column halves
 
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -67,11 +68,13 @@ struct AttnTcArgs {
 };
 
 // 64 fp32 values (or zeros) -> one 128-byte row of a K-major SWIZZLE_128B tile
-__device__ __forceinline__ void store_row_f16(uint8_t * tile, int r, const float * src, bool valid) {
+// (half h of the row: chunks 4h .. 4h+3, i.e. 32 of the 64 values)
+__device__ __forceinline__ void store_row_f16(uint8_t * tile, int r, const float * src, bool valid, int h) {
     uint8_t * row = tile + r * 128;
     const int sw = r & 7;
 #pragma unroll
-    for (int c = 0; c < 8; c++) {
+    for (int cc = 0; cc < 4; cc++) {
+        const int c = 4 * h + cc;
         uint4 h = make_uint4(0, 0, 0, 0);
         if (valid) {
             const float4 a = __ldg(reinterpret_cast<const float4 *>(src) + 2 * c), b = __ldg(reinterpret_cast<const float4 *>(src) + 2 * c + 1);
@@ -86,7 +89,8 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attention_tc_kernel(const AttnT
     uint8_t * smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t) 1023);
     uint64_t * bar_s = reinterpret_cast<uint64_t *>(smem + SBAR), * bar_pv = bar_s + 1;
     uint32_t * tmem_slot = reinterpret_cast<uint32_t *>(bar_s + 2);
-    const int t = threadIdx.x, warp = t >> 5;
+    float * xch = reinterpret_cast<float *>(smem + SX);                   // [2][128]
+    const int tt = threadIdx.x, t = tt & 127, hf = tt >> 7, warp = (tt >> 5) & 3;     // row t (= TMEM lane), column half hf, TMEM lane quarter
     const int g = blockIdx.y, r0 = blockIdx.x * AT_M;
     const int row = r0 + t;
     const bool row_ok = row < a.rows;
@@ -96,12 +100,12 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attention_tc_kernel(const AttnT
     const int kmax = a.n_past + t_last + 1, ntiles = (kmax + AT_N - 1) / AT_N;
     const float scale = 1.0f / sqrtf((float) AT_D);
 
-    if (t == 0) { mbar_init(bar_s, 1); mbar_init(bar_pv, 1); mbar_fence_init(); }
-    if (warp == 0) {
+    if (tt == 0) { mbar_init(bar_s, 1); mbar_init(bar_pv, 1); mbar_fence_init(); }
+    if (tt < 32) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"(256) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    store_row_f16(smem + SQ, t, a.qkv + (size_t) tok * a.qkv_stride + (size_t) head * AT_D, row_ok);
+    store_row_f16(smem + SQ, t, a.qkv + (size_t) tok * a.qkv_stride + (size_t) head * AT_D, row_ok, hf);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -113,7 +117,7 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attention_tc_kernel(const AttnT
 
     auto load_k = [&](int k0) {
         const int key = k0 + t;
-        store_row_f16(smem + SK, t, a.kc + ((size_t) key * a.n_head_kv + g) * AT_D, key < a.T);
+        store_row_f16(smem + SK, t, a.kc + ((size_t) key * a.n_head_kv + g) * AT_D, key < a.T, hf);
     };
     auto s_mma = [&]() {                                                   // S = Q K^T, thread 0 only
         tc_fence_after();
@@ -129,17 +133,21 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attention_tc_kernel(const AttnT
         fence_proxy_async();
         tc_fence_before();
         __syncthreads();
-        if (t == 0) s_mma();
+        if (tt == 0) s_mma();
         mbar_wait(bar_s, ns & 1); ns++;
         tc_fence_after();
 #pragma unroll
-        for (int c = 0; c < AT_N / 32; c++) {
+        for (int cc = 0; cc < 2; cc++) {
+            const int c = 2 * hf + cc;
             uint32_t v[32];
             tmem_ld32(tmem_row + (uint32_t) (c * 32), v);
 #pragma unroll
             for (int j = 0; j < 32; j++) { const float s = __fmul_rn(__uint_as_float(v[j]), scale); if (kt * AT_N + c * 32 + j < vis) m = fmaxf(m, s); }
         }
     }
+    xch[hf * 128 + t] = m;                                                 // the row maximum over both column halves
+    __syncthreads();
+    m = fmaxf(xch[t], xch[128 + t]);
 
     // ---------------------------------------------------------------- pass 2: e = LUT(s - max), O += e V
     float l = 0.f;
@@ -153,7 +161,8 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attention_tc_kernel(const AttnT
             uint8_t * base = smem + SV + (t >> 6) * 8192 + (t & 7) * 2;
             const int kc8 = (t & 63) >> 3;
 #pragma unroll
-            for (int c = 0; c < 16; c++) {
+            for (int cc = 0; cc < 8; cc++) {
+                const int c = 8 * hf + cc;                                     // this thread's 32 of the key's 64 dims
                 float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (ok) f = __ldg(reinterpret_cast<const float4 *>(src) + c);
                 const float fv[4] = { f.x, f.y, f.z, f.w };
@@ -167,11 +176,12 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attention_tc_kernel(const AttnT
         fence_proxy_async();
         tc_fence_before();
         __syncthreads();
-        if (t == 0) s_mma();
+        if (tt == 0) s_mma();
         mbar_wait(bar_s, ns & 1); ns++;
         tc_fence_after();
 #pragma unroll
-        for (int c = 0; c < AT_N / 32; c++) {
+        for (int cc = 0; cc < 2; cc++) {
+            const int c = 2 * hf + cc;
             uint32_t v[32];
             tmem_ld32(tmem_row + (uint32_t) (c * 32), v);
             uint8_t * prow = smem + SP + (c >> 1) * 16384 + t * 128;
@@ -191,7 +201,7 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attention_tc_kernel(const AttnT
         fence_proxy_async();
         tc_fence_before();
         __syncthreads();
-        if (t == 0) {
+        if (tt == 0) {
             tc_fence_after();
 #pragma unroll
             for (int k = 0; k < AT_N / 16; k++)
@@ -201,24 +211,24 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attention_tc_kernel(const AttnT
     }
     mbar_wait(bar_pv, npv & 1);
     tc_fence_after();
+    xch[hf * 128 + t] = l;                                                 // row sum over both column halves, fixed order
+    __syncthreads();
+    l = xch[t] + xch[128 + t];
     {
         const float inv = (float) (1.0 / (double) l);                      // ggml.c:12427-12449
-        float * dst = a.out + (size_t) tok * a.out_stride + (size_t) head * AT_D;
+        float * dst = a.out + (size_t) tok * a.out_stride + (size_t) head * AT_D + hf * 32;
+        uint32_t v[32];
+        tmem_ld32(tmem_row + (uint32_t) (AT_N + hf * 32), v);              // warp-collective: every lane loads, valid rows store
+        if (row_ok) {
 #pragma unroll
-        for (int c = 0; c < 2; c++) {
-            uint32_t v[32];
-            tmem_ld32(tmem_row + (uint32_t) (AT_N + c * 32), v);           // warp-collective: every lane loads, valid rows store
-            if (row_ok) {
-#pragma unroll
-                for (int j = 0; j < 32; j += 4)
-                    *reinterpret_cast<float4 *>(dst + c * 32 + j) = make_float4(__fmul_rn(__uint_as_float(v[j]), inv), __fmul_rn(__uint_as_float(v[j + 1]), inv),
-                                                                                __fmul_rn(__uint_as_float(v[j + 2]), inv), __fmul_rn(__uint_as_float(v[j + 3]), inv));
-            }
+            for (int j = 0; j < 32; j += 4)
+                *reinterpret_cast<float4 *>(dst + j) = make_float4(__fmul_rn(__uint_as_float(v[j]), inv), __fmul_rn(__uint_as_float(v[j + 1]), inv),
+                                                                   __fmul_rn(__uint_as_float(v[j + 2]), inv), __fmul_rn(__uint_as_float(v[j + 3]), inv));
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(256) : "memory");
+    if (tt < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(256) : "memory");
 }
 
 } // namespace
