@@ -151,6 +151,9 @@ __global__ void __launch_bounds__(MG_NT, 1) falcon_decode_mega_kernel(const Mega
 #pragma unroll
     for (int j = 0; j < JD; j++) { const int g = j * MG_NT + tid; vd[j] = g < PF; gd[j] = vd[j] ? g : PF - 1; }
 
+    const int aux0[1] = { 0 }; int auxd[JD];
+#pragma unroll
+    for (int j = 0; j < JD; j++) auxd[j] = 0;
     int gc_half = 0, gc_full = 0;
     int d0, d1; split_rows(a.E, cta, ncta, d0, d1);      // rows of ffn_down AND wo this CTA owns
     const int dh = d0 + (d1 - d0 + 1) / 2;
@@ -205,11 +208,11 @@ __global__ void __launch_bounds__(MG_NT, 1) falcon_decode_mega_kernel(const Mega
         mg_trace(tr, 0, true); mg_trace(tr, 1, false);
         {
             float * yq = a.qkv;
-            ring_run<TYPE, MG_HALF, 1, DE, true>(we, pq, q0, q1, pu, u0, u1, xa, S.part_half[half], gc_half, hbar, th,
+            ring_run<TYPE, MG_HALF, 1, DE, true>(we, pq, q0, q1, pu, u0, u1, xa, aux0, S.part_half[half], gc_half, hbar, th,
                                                  [&](int row, float v) { yq[row] = v; }, [] {});
             group_arrive(flag + 0, hbar, MG_HALF, th);
             float * yu = a.up;
-            ring_run<TYPE, MG_HALF, 1, DE, false>(we, pu, u0, u1, pu, 0, 0, xm, S.part_half[half], gc_half, hbar, th,
+            ring_run<TYPE, MG_HALF, 1, DE, false>(we, pu, u0, u1, pu, 0, 0, xm, aux0, S.part_half[half], gc_half, hbar, th,
                                                   [&](int row, float v) { yu[row] = gelu_lut(v); }, [] {});
             group_arrive(flag + 1, hbar, MG_HALF, th);
         }
@@ -295,7 +298,7 @@ __global__ void __launch_bounds__(MG_NT, 1) falcon_decode_mega_kernel(const Mega
                 xd[j] = T::quant_x(v, gd[j], lane);
             }
             float * dn = S.dn;
-            ring_run<TYPE, MG_NT, JD, DD, false>(wd, pd, d0, d1, pd, 0, 0, xd, S.part_full, gc_full, 0, tid,
+            ring_run<TYPE, MG_NT, JD, DD, false>(wd, pd, d0, d1, pd, 0, 0, xd, auxd, S.part_full, gc_full, 0, tid,
                                                  [&](int row, float v) { dn[row - d0] = v; }, [] {});
         }
         mg_trace(tr, 3, true);
@@ -312,7 +315,7 @@ __global__ void __launch_bounds__(MG_NT, 1) falcon_decode_mega_kernel(const Mega
             load_piece_cg<TYPE>(a.att, ge[0], ve[0], v);
             xo[0] = T::quant_x(v, ge[0], lane);
             float * x = a.x; const float * dn = S.dn;
-            ring_run<TYPE, MG_HALF, 1, DE, false>(we, po, o0, o1, po, 0, 0, xo, S.part_half[half], gc_half, hbar, th,
+            ring_run<TYPE, MG_HALF, 1, DE, false>(we, po, o0, o1, po, 0, 0, xo, aux0, S.part_half[half], gc_half, hbar, th,
                                                   [&](int row, float v) { x[row] = __fadd_rn(__fadd_rn(dn[row - d0], v), ld_cg(x + row)); }, [] {});
         }
         group_arrive(flag + 3, hbar, MG_HALF, th);

@@ -16,6 +16,8 @@
 // kind 1 (Q4_K/Q5_K scales): the 12-byte packed 6-bit (scale,min) field at src_off is expanded losslessly into
 // 16 bytes, {sc[2p], sc[2p+1], min[2p], min[2p+1]} for p = 0..3 (get_scale_min_k4, k_quants.c:264-271), so that a
 // lane fetches the four values of its sub-block pair with one 32-bit load and feeds them straight to dp2a.
+// kind 2 (Q3_K scales): the 12-byte packed 6-bit field -> 16 SIGNED bytes (scale - 32, k_quants.c:486-493 + :646), ordered so that
+// the four scales of a 16-byte qs piece are one 32-bit word: byte 4 * (2n + c) + quad = scale of elements 128n + 32 quad + 16c ..+15.
 struct PlaneSpec { int src_off; int bytes; int kind; };
 struct TypeSpec {
     int blk_elems;      // weights per block (32 legacy, 256 K-quants, 1 for f16/f32)
@@ -35,7 +37,7 @@ static inline TypeSpec type_spec(int t) {
         case T_Q5_1: return {32, 24, 3, {{8, 16}, {4, 4}, {0, 4}}};                  // qs | qh | d,m
         case T_Q8_0: return {32, 34, 2, {{2, 32}, {0, 2}}};                          // qs | d
         case T_Q2_K: return {256, 84, 3, {{16, 64}, {0, 16}, {80, 4}}};              // qs | scales | d,dmin
-        case T_Q3_K: return {256, 110, 4, {{32, 64}, {0, 32}, {96, 12}, {108, 2}}};  // qs | hmask | scales | d
+        case T_Q3_K: return {256, 110, 4, {{32, 64}, {0, 32}, {96, 16, 2}, {108, 2}}}; // qs | hmask | scales (expanded, signed) | d
         case T_Q4_K: return {256, 144, 3, {{16, 128}, {4, 16, 1}, {0, 4}}};          // qs | scales+mins (expanded) | d,dmin
         case T_Q5_K: return {256, 176, 4, {{48, 128}, {16, 32}, {4, 16, 1}, {0, 4}}}; // qs | qh | scales+mins (expanded) | d,dmin
         case T_Q6_K: return {256, 210, 4, {{0, 128}, {128, 64}, {192, 16}, {208, 2}}}; // ql | qh | scales | d
@@ -86,6 +88,9 @@ __device__ __forceinline__ int q3_scale(const uint8_t * s, int j) {   // 6-bit s
     const int hi = (s[8 + (j & 3)] >> (2 * (j >> 2))) & 3;
     return lo | (hi << 4);
 }
+
+// scale j (already minus 32) from the expanded 16-byte field of the device layout (PlaneSpec kind 2)
+__device__ __forceinline__ int q3_scale16(const uint8_t * s16, int j) { return reinterpret_cast<const int8_t *>(s16)[4 * (2 * (j >> 3) + (j & 1)) + ((j >> 1) & 3)]; }
 
 __device__ inline float dequant_elem(const WPlanes & W, size_t row, int e) {
     const int t = W.type;
@@ -146,7 +151,7 @@ __device__ inline float dequant_elem(const WPlanes & W, size_t row, int e) {
         const uint8_t qb = (W.p[0] + row * W.stride[0])[b * 64 + n * 32 + l];
         const uint8_t hb = (W.p[1] + row * W.stride[1])[b * 32 + l];
         const int code = ((qb >> (2 * quad)) & 3) - (((hb >> (4 * n + quad)) & 1) ? 0 : 4);
-        const int sc = q3_scale(W.p[2] + row * W.stride[2] + b * 12, i >> 4) - 32;
+        const int sc = q3_scale16(W.p[2] + row * W.stride[2] + b * 16, i >> 4);
         const float d = f16_bits_to_f32(reinterpret_cast<const uint16_t *>(W.p[3] + row * W.stride[3])[b]);
         return __fmul_rn(__fmul_rn(d, (float) sc), (float) code);
     }

@@ -143,23 +143,19 @@ template <> struct MV<T_Q6_K> {
 template <> struct MV<T_Q3_K> {
     static constexpr int PPB = 4;                // 16 bytes of qs = 64 weights
     static constexpr int CH = 32, NPL = 4;
-    __host__ __device__ static constexpr int pb(int p) { return p == 0 ? 64 : p == 1 ? 32 : p == 2 ? 12 : 2; }
-    static constexpr int O1 = CH * 64, O2 = O1 + CH * 32, O3 = O2 + CH * 12;
-    struct Regs { uint4 q, hm; uint32_t s0, s1, s2, d; };
+    __host__ __device__ static constexpr int pb(int p) { return p == 0 ? 64 : p == 1 ? 32 : p == 2 ? 16 : 2; }
+    static constexpr int O1 = CH * 64, O2 = O1 + CH * 32, O3 = O2 + CH * 16;
+    struct Regs { uint4 q, hm; uint32_t sc, d; };                  // sc: the piece's four signed scales (expanded device layout)
     __device__ static Regs load(const uint8_t * sb, int b, int pc) {
         Regs r;
         r.q = *reinterpret_cast<const uint4 *>(sb + b * 64 + pc * 16);                            // = n*32 + c*16
         r.hm = *reinterpret_cast<const uint4 *>(sb + O1 + b * 32 + (pc & 1) * 16);
-        const uint32_t * s = reinterpret_cast<const uint32_t *>(sb + O2 + b * 12);
-        r.s0 = s[0]; r.s1 = s[1]; r.s2 = s[2];
+        r.sc = reinterpret_cast<const uint32_t *>(sb + O2 + b * 16)[pc];
         r.d = *reinterpret_cast<const uint16_t *>(sb + O3 + b * 2);
         return r;
     }
     __device__ static float dot(const Regs & r, int b, int pc, const XS & x) {
         const int n = pc >> 1, c = pc & 1;
-        const uint8_t sb[12] = { (uint8_t) r.s0, (uint8_t) (r.s0 >> 8), (uint8_t) (r.s0 >> 16), (uint8_t) (r.s0 >> 24),
-                                 (uint8_t) r.s1, (uint8_t) (r.s1 >> 8), (uint8_t) (r.s1 >> 16), (uint8_t) (r.s1 >> 24),
-                                 (uint8_t) r.s2, (uint8_t) (r.s2 >> 8), (uint8_t) (r.s2 >> 16), (uint8_t) (r.s2 >> 24) };
         int isum = 0;
 #pragma unroll
         for (int quad = 0; quad < 4; quad++) {
@@ -170,7 +166,7 @@ template <> struct MV<T_Q3_K> {
             int i = dot16_u(C3(r.q.x, r.hm.x), C3(r.q.y, r.hm.y), C3(r.q.z, r.hm.z), C3(r.q.w, r.hm.w), xv);
 #undef C3
             i -= 4 * x.bs[b * 16 + (el >> 4)];                          // code = (q2 | hbit<<2) - 4
-            isum += (q3_scale(sb, el >> 4) - 32) * i;
+            isum += (int) (int8_t) (r.sc >> (8 * quad)) * i;
         }
         return (f16_bits_to_f32((uint16_t) r.d) * x.d[b]) * (float) isum;
     }

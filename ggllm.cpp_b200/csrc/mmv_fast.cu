@@ -44,8 +44,9 @@ __device__ __forceinline__ void mmv_body(const WPlanes & W, const FastX & X, flo
 
     int gidx[J]; bool valid[J];
     WP wp[J];
+    int aux[J];
 #pragma unroll
-    for (int j = 0; j < J; j++) { const int g = j * NT + tid; valid[j] = g < P; gidx[j] = valid[j] ? g : P - 1; wp[j] = T::wp(W, gidx[j]); }
+    for (int j = 0; j < J; j++) { const int g = j * NT + tid; valid[j] = g < P; gidx[j] = valid[j] ? g : P - 1; wp[j] = T::wp(W, gidx[j]); aux[j] = piece_aux<TYPE>(gidx[j]); }
 
     typename T::WR w[D][J];
     ring_fill<TYPE, J, D>(w, wp, row0, row1);                                // weights are in flight before the activation arrives
@@ -65,7 +66,7 @@ __device__ __forceinline__ void mmv_body(const WPlanes & W, const FastX & X, flo
         mbar_wait(bar, 0);
 #pragma unroll
         for (int j = 0; j < J; j++) xr[j] = valid[j] ? T::load_x(xq, A, n, gidx[j]) : zero_xr<TYPE>();
-    } else {
+    } else if constexpr (T::HAS_PROLOGUE_QUANT) {
         const float * xrow = X.x + (size_t) n * X.x_stride;
         float mean = 0.f, scale = 1.f;
 #pragma unroll
@@ -136,7 +137,7 @@ __device__ __forceinline__ void mmv_body(const WPlanes & W, const FastX & X, flo
     // (measured: profiles/r1_decode_timeline.md).
     int gcount = 0;
     const int ekind = epi.kind; const float * r1p = epi.r1, * r2p = epi.r2;
-    ring_run<TYPE, NT, J, D, false>(w, wp, row0, row1, wp, 0, 0, xr, partial, gcount, 0, tid,
+    ring_run<TYPE, NT, J, D, false>(w, wp, row0, row1, wp, 0, 0, xr, aux, partial, gcount, 0, tid,
         [&](int row, float v) {
             if (ekind == EPI_GELU) v = gelu_lut(v);
             else if (ekind == EPI_ADD2) v = (v + r1p[(size_t) n * y_stride + row]) + r2p[(size_t) n * y_stride + row];
@@ -188,7 +189,7 @@ __device__ __forceinline__ void mmv_body(const WPlanes & W, const FastX & X, flo
 template <int TYPE, int NT, int J, int D, int MODE>
 // 96 registers for the 256-thread shapes: two CTAs per SM leave a quarter of the register file to the small attention
 // kernels of the other stream, which then run beside ffn_up instead of after it
-__global__ void __launch_bounds__(NT) __maxnreg__(NT == 256 ? (D <= 6 ? 80 : 96) : 128) mmv_fast_kernel(const WPlanes W, const FastX X, float * __restrict__ y, int64_t y_stride, const Epi epi) {
+__global__ void __launch_bounds__(NT) __maxnreg__(NT <= 256 ? 96 : 128) mmv_fast_kernel(const WPlanes W, const FastX X, float * __restrict__ y, int64_t y_stride, const Epi epi) {
     extern __shared__ __align__(16) uint8_t smem[];
     mmv_body<TYPE, NT, J, D, MODE>(W, X, y, y_stride, epi, (int) blockIdx.x, (int) gridDim.x, (int) blockIdx.y, smem);
 }
@@ -206,7 +207,7 @@ static void launch_mode(const WPlanes & W, const FastX & X, float * y, int64_t y
     if (!set) { B200_CUDA_CHECK(cudaFuncSetAttribute(mmv_fast_kernel<TYPE, NT, J, D, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         // same L1/shared split as the small kernels of the other stream: an SM cannot host kernels with different carve-outs at once
         B200_CUDA_CHECK(cudaFuncSetAttribute(mmv_fast_kernel<TYPE, NT, J, D, MODE>, cudaFuncAttributePreferredSharedMemoryCarveout, B200_CARVEOUT)); set = true; }
-    int ctas = fast_num_sms() * (NT == 256 ? (D <= 6 ? 3 : 2) : 1);
+    int ctas = fast_num_sms() * (NT == 128 ? 4 : NT == 256 ? 2 : 1);
     if (ctas > (W.M + 3) / 4) ctas = (W.M + 3) / 4;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned) ctas, (unsigned) X.N); cfg.blockDim = dim3(NT); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
@@ -219,9 +220,11 @@ static void launch_mode(const WPlanes & W, const FastX & X, float * y, int64_t y
 template <int TYPE, int NT, int J, int D>
 static void launch_cfg(const WPlanes & W, const FastX & X, float * y, int64_t y_stride, Epi epi, cudaStream_t stream) {
     if (X.mode == 0) launch_mode<TYPE, NT, J, D, 0>(W, X, y, y_stride, epi, stream);
-    else if (X.mode == 1) launch_mode<TYPE, NT, J, D, 1>(W, X, y, y_stride, epi, stream);
-    else if (J == 1) launch_mode<TYPE, NT, J, D, J == 1 ? 2 : 1>(W, X, y, y_stride, epi, stream);
-    else B200_ASSERT(!"mmv_fast: LayerNorm prologue needs J == 1");
+    else if constexpr (FX<TYPE>::HAS_PROLOGUE_QUANT) {
+        if (X.mode == 1) launch_mode<TYPE, NT, J, D, 1>(W, X, y, y_stride, epi, stream);
+        else if (J == 1) launch_mode<TYPE, NT, J, D, J == 1 ? 2 : 1>(W, X, y, y_stride, epi, stream);
+        else B200_ASSERT(!"mmv_fast: LayerNorm prologue needs J == 1");
+    } else B200_ASSERT(!"mmv_fast: this weight type takes quantised activations only (mode 0)");
 }
 
 template <int TYPE>
@@ -229,10 +232,12 @@ static bool launch_type(const WPlanes & W, const FastX & X, float * y, int64_t y
     const int P = W.nb * FX<TYPE>::PPB;
     if (W.K > 64 * 1024) return false;
     if (X.mode == 2 && P > 512) return false;                 // the fused LayerNorm needs the whole row inside one CTA pass (J == 1)
-    if (P <= 256) { if (getenv("B200_MMV_D6")) launch_cfg<TYPE, 256, 1, 6>(W, X, y, y_stride, epi, stream); else launch_cfg<TYPE, 256, 1, 8>(W, X, y, y_stride, epi, stream); }
-    else if (P <= 512) launch_cfg<TYPE, 512, 1, 8>(W, X, y, y_stride, epi, stream);
-    else if (P <= 1024) launch_cfg<TYPE, 512, 2, 4>(W, X, y, y_stride, epi, stream);
-    else if (P <= 2048) launch_cfg<TYPE, 512, 4, 2>(W, X, y, y_stride, epi, stream);
+    constexpr int D1 = FX<TYPE>::D256;                        // ring depth for one piece per thread; D * J stays constant
+    if (P <= 128 && D1 == 4) launch_cfg<TYPE, 128, 1, D1>(W, X, y, y_stride, epi, stream);       // 64-weight pieces (Q3_K): K = 8192 is 128 pieces
+    else if (P <= 256) launch_cfg<TYPE, 256, 1, D1>(W, X, y, y_stride, epi, stream);
+    else if (P <= 512) launch_cfg<TYPE, 512, 1, D1>(W, X, y, y_stride, epi, stream);
+    else if (P <= 1024) launch_cfg<TYPE, 512, 2, D1 / 2>(W, X, y, y_stride, epi, stream);
+    else if (P <= 2048 && D1 == 8) launch_cfg<TYPE, 512, 4, 2>(W, X, y, y_stride, epi, stream);
     else return false;
     return true;
 }
@@ -257,9 +262,13 @@ bool launch_mmv_fast_x(const WPlanes & W, const FastX & X, float * y, int64_t y_
     switch (W.type) {
         case T_Q4_K: return launch_type<T_Q4_K>(W, Xp, y, y_stride, epi, stream);
         case T_Q4_0: return launch_type<T_Q4_0>(W, Xp, y, y_stride, epi, stream);
+        case T_Q3_K: return X.mode == 0 && !getenv("B200_Q3K_GENERIC") && launch_type<T_Q3_K>(W, Xp, y, y_stride, epi, stream);
     }
     return false;
 }
+// Which (type, K, activation mode) the fused single-stream decode path of engine.cu may rely on.  Q3_K has a fast mat-vec
+// (used through launch_mmv) but is NOT listed: its kernel is issue-bound, and the two-stream per-node path, which runs the
+// attention and MLP branches' mat-vecs concurrently, is faster for it (189 vs 180 tok/s, Falcon-40B).
 bool mmv_fast_supports(int wtype, int K, int mode) {
     if (wtype != T_Q4_K && wtype != T_Q4_0) return false;
     const int P = wtype == T_Q4_K ? K / 32 : K / 32;

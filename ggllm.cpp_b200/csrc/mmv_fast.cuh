@@ -21,13 +21,15 @@ __device__ __forceinline__ int dot16(const uint32_t w0, const uint32_t w1, const
 }
 __device__ __forceinline__ int dp2a_lo_su(int pair16, uint32_t bytes) { int d; asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(pair16), "r"(bytes), "r"(0)); return d; }
 __device__ __forceinline__ int dp2a_hi_su(int pair16, uint32_t bytes) { int d; asm("dp2a.hi.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(pair16), "r"(bytes), "r"(0)); return d; }
+__device__ __forceinline__ int dp2a_lo_ss(int pair16, uint32_t bytes, int c) { int d; asm("dp2a.lo.s32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(pair16), "r"(bytes), "r"(c)); return d; }
+__device__ __forceinline__ int dp2a_hi_ss(int pair16, uint32_t bytes, int c) { int d; asm("dp2a.hi.s32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(pair16), "r"(bytes), "r"(c)); return d; }
 __device__ __forceinline__ float gelu_lut(float v) {      // fp16-LUT semantics, ggml.c:3461-3484
     const float f = __half2float(__float2half_rn(v));
     const float g = 0.5f * f * (1.0f + tanhf(0.79788456080286535587989211986876f * f * (1.0f + 0.044715f * f * f)));
     return __half2float(__float2half_rn(g));
 }
 
-struct WP { const uint8_t * b0, * b1, * b2; uint32_t s0, s1, s2; };
+struct WP { const uint8_t * b0, * b1, * b2, * b3; uint32_t s0, s1, s2, s3; };
 // keeps the compiler from splitting a per-thread plane pointer back into (uniform base) + (thread offset): with an opaque
 // 64-bit register the row address is a single IMAD.WIDE.U32 instead of IMAD.WIDE + IADD3 + IADD3.X
 __device__ __forceinline__ const uint8_t * opaque_ptr(const uint8_t * p) { unsigned long long v = (unsigned long long) p; asm volatile("" : "+l"(v)); return (const uint8_t *) v; }
@@ -36,6 +38,8 @@ template <int TYPE> struct FX;
 
 template <> struct FX<T_Q4_K> {
     static constexpr int PPB = 8;                                   // pieces per block
+    static constexpr bool HAS_PROLOGUE_QUANT = true;                // modes 1 / 2 (fp32 row quantised in the prologue)
+    static constexpr int D256 = 8;                                  // ring depth of the J = 1 shapes
     struct XR { uint4 xl, xh; int bs; float xd; };                  // activation state of one piece position (all zero: contributes 0)
     struct WR { uint4 q; uint32_t sm, dd; };
     __device__ static XR load_x(const int8_t * xq, const ActQ & A, int n, int g) {
@@ -111,6 +115,8 @@ template <> struct FX<T_Q4_K> {
 
 template <> struct FX<T_Q4_0> {
     static constexpr int PPB = 1;
+    static constexpr bool HAS_PROLOGUE_QUANT = true;
+    static constexpr int D256 = 8;
     struct XR { uint4 xl, xh; int bs; float xd; };
     struct WR { uint4 q; uint32_t d; };
     __device__ static XR load_x(const int8_t * xq, const ActQ & A, int n, int g) {
@@ -159,6 +165,64 @@ template <> struct FX<T_Q4_0> {
         s += dot16(w.q.x & 0xF0F0F0F0, w.q.y & 0xF0F0F0F0, w.q.z & 0xF0F0F0F0, w.q.w & 0xF0F0F0F0, x.xh) >> 4;
         s -= 8 * x.bs;                                                       // codes are stored +8
         return ((float) s * f16_bits_to_f32((uint16_t) w.d)) * x.xd;
+    }
+};
+
+// -------------------------------------------------------------------------------------------------- Q3_K x Q8_K
+// piece g = 16 bytes of the 2-bit plane: block b = g / 4, half n = (g % 4) / 2, c = g % 2; bit pair `quad` of byte l holds
+// element 128 n + 32 quad + 16 c + l, its high bit is bit 4 n + quad of hmask[16 c + l] (k_quants.c:1684-1745, 646-692).
+// code = (q2 | hbit << 2) - 4, scale - 32 comes pre-expanded (PlaneSpec kind 2): the piece's four scales are one word.
+template <> struct FX<T_Q3_K> {
+    static constexpr int PPB = 4;
+    static constexpr bool HAS_PROLOGUE_QUANT = false;               // mode 0 only (the decode path hands over quantised rows)
+    static constexpr int D256 = 4;                                  // 10 registers per ring slot, 19 for the activation piece
+    struct XR { uint4 x[4]; int bsA, bsB; float xd; };              // the four 16-code segments, their sums (4 x s16), Q8_K scale
+    struct WR { uint4 q, hm; uint32_t sc, d; };
+    __device__ static XR load_x(const int8_t * xq, const ActQ & A, int n, int g) {
+        const int b = g >> 2, pc = g & 3, hn = pc >> 1, c = pc & 1;
+        XR r;
+        const int16_t * bs = A.bs + (size_t) n * (A.K / 16) + b * 16 + 8 * hn + c;
+#pragma unroll
+        for (int quad = 0; quad < 4; quad++) r.x[quad] = *reinterpret_cast<const uint4 *>(xq + b * 256 + 128 * hn + 32 * quad + 16 * c);
+        r.bsA = ((int) bs[0] & 0xffff) | ((int) bs[2] << 16);
+        r.bsB = ((int) bs[4] & 0xffff) | ((int) bs[6] << 16);
+        r.xd = A.d[(size_t) n * (A.K / 256) + b];
+        return r;
+    }
+    __device__ static void seg(int, int & ea, int & eb) { ea = 0; eb = 0; }
+    __device__ static XR quant_x(const float (&)[32], int, int) { return XR{}; }      // never instantiated on a live path
+    __device__ static WP wp(const WPlanes & W, int g) {
+        WP r;
+        r.b0 = opaque_ptr(W.p[0] + (size_t) g * 16); r.b1 = opaque_ptr(W.p[1] + (size_t) (g >> 2) * 32 + (g & 1) * 16);
+        r.b2 = opaque_ptr(W.p[2] + (size_t) g * 4);  r.b3 = opaque_ptr(W.p[3] + (size_t) (g >> 2) * 2);
+        r.s0 = W.stride[0]; r.s1 = W.stride[1]; r.s2 = W.stride[2]; r.s3 = W.stride[3];
+        return r;
+    }
+    __device__ static WR load_w(const WP & p, uint32_t row) {
+        WR r;
+        r.q = ldg_stream_v4(p.b0 + (uint64_t) row * p.s0);
+        r.hm = ldg_v4(p.b1 + (uint64_t) row * p.s1);                     // shared by the block's two halves n: second reader hits L1
+        r.sc = ldg_u32(p.b2 + (uint64_t) row * p.s2);
+        r.d = ldg_u16(p.b3 + (uint64_t) row * p.s3);
+        return r;
+    }
+    // hsh = 4 n: the per-thread shift into its half of the high-bit plane (piece_aux)
+    __device__ static float dot(const WR & w, const XR & x, int hsh) {
+        const uint32_t q[4] = { w.q.x, w.q.y, w.q.z, w.q.w }, hm[4] = { w.hm.x, w.hm.y, w.hm.z, w.hm.w };
+        int i[4];
+#pragma unroll
+        for (int quad = 0; quad < 4; quad++) {
+            uint32_t cw[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++)                                      // unsigned code 0..7: low two bits | high bit moved to bit 2
+                cw[k] = ((q[k] >> (2 * quad)) & 0x03030303u) | (((hm[k] >> (hsh + quad)) << 2) & 0x04040404u);
+            i[quad] = dot16(cw[0], cw[1], cw[2], cw[3], x.x[quad]);         // <= 16 * 7 * 127 < 2^15
+        }
+        int isum = dp2a_lo_ss((i[0] & 0xffff) | (i[1] << 16), w.sc, 0);
+        isum = dp2a_hi_ss((i[2] & 0xffff) | (i[3] << 16), w.sc, isum);
+        int bsum = dp2a_lo_ss(x.bsA, w.sc, 0);                              // the -4 of every code: - 4 * sum_quad sc * bsum
+        bsum = dp2a_hi_ss(x.bsB, w.sc, bsum);
+        return (f16_bits_to_f32((uint16_t) w.d) * x.xd) * (float) (isum - 4 * bsum);
     }
 };
 
@@ -219,8 +283,13 @@ __device__ __forceinline__ L2PF l2pf_of(const WPlanes & W, int dist) {
 
 __device__ __forceinline__ void named_sync(int id, int n) { asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(n) : "memory"); }
 
+// per-thread constant some types need in their dot (Q3_K: the shift of its half of the high-bit plane)
+template <int TYPE> __device__ __forceinline__ int piece_aux(int g) { return TYPE == T_Q3_K ? 4 * ((g & 3) >> 1) : 0; }
+template <int TYPE> __device__ __forceinline__ float piece_dot(const typename FX<TYPE>::WR & w, const typename FX<TYPE>::XR & x, int aux) {
+    if constexpr (TYPE == T_Q3_K) return FX<TYPE>::dot(w, x, aux); else return FX<TYPE>::dot(w, x);
+}
 template <int TYPE> __device__ __forceinline__ typename FX<TYPE>::XR zero_xr() {
-    typename FX<TYPE>::XR r; r.xl = make_uint4(0, 0, 0, 0); r.xh = r.xl; r.bs = 0; r.xd = 0.f; return r;
+    typename FX<TYPE>::XR r{}; return r;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -242,16 +311,16 @@ __device__ __forceinline__ void ring_fill(typename FX<TYPE>::WR (&w)[D][J], cons
 template <int TYPE, int NTG, int J, int D, bool CHECKED, bool HASNEXT, class Store>
 __device__ __forceinline__ void ring_pass(typename FX<TYPE>::WR (&w)[D][J], const WP (&wp)[J], const int r0, const int nrows, const int npad, const int base,
                                           const WP (&wpn)[J], const int n0, const int n1,
-                                          const typename FX<TYPE>::XR (&xr)[J], float * partial, int & gcount, const int bar_id, const int tg, Store & store) {
+                                          const typename FX<TYPE>::XR (&xr)[J], const int (&aux)[J], float * partial, int & gcount, const int bar_id, const int tg, Store & store) {
     using T = FX<TYPE>;
     constexpr int NWG = NTG / 32, G = (D % 4 == 0) ? 4 : (D % 2 == 0) ? 2 : 1;
     const int lane = tg & 31, warp = tg >> 5;
     float acc[G];
 #pragma unroll
     for (int s = 0; s < D; s++) {
-        float a = T::dot(w[s][0], xr[0]);
+        float a = piece_dot<TYPE>(w[s][0], xr[0], aux[0]);
 #pragma unroll
-        for (int j = 1; j < J; j++) a += T::dot(w[s][j], xr[j]);
+        for (int j = 1; j < J; j++) a += piece_dot<TYPE>(w[s][j], xr[j], aux[j]);
         acc[s % G] = a;
         const int nxt = base + D + s;                                        // refill this slot D rows ahead
         if (!CHECKED || nxt < nrows) {
@@ -290,16 +359,16 @@ __device__ __forceinline__ void ring_pass(typename FX<TYPE>::WR (&w)[D][J], cons
 template <int TYPE, int NTG, int J, int D, bool HASNEXT, class Store, class Tail>
 __device__ __forceinline__ void ring_run(typename FX<TYPE>::WR (&w)[D][J], const WP (&wp)[J], const int r0, const int r1,
                                          const WP (&wpn)[J], const int n0, const int n1,
-                                         const typename FX<TYPE>::XR (&xr)[J], float * partial, int & gcount, const int bar_id, const int tg,
+                                         const typename FX<TYPE>::XR (&xr)[J], const int (&aux)[J], float * partial, int & gcount, const int bar_id, const int tg,
                                          Store store, Tail before_tail, const L2PF pf = L2PF{ { nullptr, nullptr, nullptr }, { 0, 0, 0 }, 0 }) {
     const int nrows = r1 - r0, npad = (nrows + D - 1) / D * D;
     if (npad == 0) { before_tail(); if (HASNEXT) ring_fill<TYPE, J, D>(w, wpn, n0, n1); return; }
     int base = 0;
     for (; base + 2 * D <= nrows; base += D) {
         if (pf.dist > 0 && tg == 0) l2_prefetch_rows(pf, min(r0 + base + D + pf.dist, r1), min(r0 + base + 2 * D + pf.dist, r1));
-        ring_pass<TYPE, NTG, J, D, false, false>(w, wp, r0, nrows, npad, base, wpn, n0, n1, xr, partial, gcount, bar_id, tg, store);
+        ring_pass<TYPE, NTG, J, D, false, false>(w, wp, r0, nrows, npad, base, wpn, n0, n1, xr, aux, partial, gcount, bar_id, tg, store);
     }
     before_tail();
     for (; base < npad; base += D)
-        ring_pass<TYPE, NTG, J, D, true, HASNEXT>(w, wp, r0, nrows, npad, base, wpn, n0, n1, xr, partial, gcount, bar_id, tg, store);
+        ring_pass<TYPE, NTG, J, D, true, HASNEXT>(w, wp, r0, nrows, npad, base, wpn, n0, n1, xr, aux, partial, gcount, bar_id, tg, store);
 }

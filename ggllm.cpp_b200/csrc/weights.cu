@@ -36,6 +36,8 @@ __global__ void repack_kernel(const uint8_t * __restrict__ src, WPlanes W, TypeS
                 int s0, m0, s1, m1; unpack_sm6(2 * pr, f, s0, m0); unpack_sm6(2 * pr + 1, f, s1, m1);
                 d[4 * pr] = (uint8_t) s0; d[4 * pr + 1] = (uint8_t) s1; d[4 * pr + 2] = (uint8_t) m0; d[4 * pr + 3] = (uint8_t) m1;
             }
+        } else if (ts.plane[p].kind == 2) {               // Q3_K scales, see PlaneSpec
+            for (int j = 0; j < 16; j++) d[4 * (2 * (j >> 3) + (j & 1)) + ((j >> 1) & 3)] = (uint8_t) (int8_t) (q3_scale(f, j) - 32);
         } else for (int i = 0; i < ts.plane[p].bytes; i++) d[i] = f[i];
     }
 }
@@ -106,6 +108,7 @@ __global__ void fill_random_kernel(WPlanes W, TypeSpec ts, uint64_t seed) {
             for (int i = 0; i < nbytes; i += 4) {
                 uint32_t v = mix32(seed ^ (((uint64_t) idx * 8 + p) << 20) ^ (uint64_t) i);
                 if (ts.plane[p].kind == 1) v &= 0x3f3f3f3fu;         // expanded 6-bit scales / mins
+                if (ts.plane[p].kind == 2) v = (((v & 0x3f3f3f3fu) | 0x80808080u) - 0x20202020u) ^ 0x80808080u;   // per byte: 6-bit value - 32 as int8 (borrow-free SWAR)
                 for (int k = 0; k < 4 && i + k < nbytes; k++) d[i + k] = (uint8_t) (v >> (8 * k));
             }
         }
