@@ -30,7 +30,7 @@ __device__ __forceinline__ void mmv_body(const WPlanes & W, const FastX & X, flo
     uint64_t * bar = reinterpret_cast<uint64_t *>(smem);
     float * partial = reinterpret_cast<float *>(smem + 16);           // [2][NW][G]
     double * red = reinterpret_cast<double *>(smem + 16 + 2 * NW * 4 * 4);      // [NW] block reduction scratch (mode 2)
-    int8_t * xq = reinterpret_cast<int8_t *>(smem + 16 + 2 * NW * 4 * 4 + NW * 8);
+    int8_t * xq = reinterpret_cast<int8_t *>(smem + ((16 + 2 * NW * 4 * 4 + NW * 8 + 15) & ~15));      // 16-byte aligned (TMA destination)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int P = W.nb * T::PPB;
     const ActQ & A = X.A;
@@ -202,12 +202,12 @@ static int fast_num_sms() {
 
 template <int TYPE, int NT, int J, int D, int MODE>
 static void launch_mode(const WPlanes & W, const FastX & X, float * y, int64_t y_stride, Epi epi, cudaStream_t stream) {
-    const size_t smem = 16 + 2 * (NT / 32) * 4 * 4 + (NT / 32) * 8 + (size_t) ((W.K + 15) & ~15);
+    const size_t smem = ((16 + 2 * (NT / 32) * 4 * 4 + (NT / 32) * 8 + 15) & ~15) + (size_t) ((W.K + 15) & ~15);
     static bool set = false;
     if (!set) { B200_CUDA_CHECK(cudaFuncSetAttribute(mmv_fast_kernel<TYPE, NT, J, D, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         // same L1/shared split as the small kernels of the other stream: an SM cannot host kernels with different carve-outs at once
         B200_CUDA_CHECK(cudaFuncSetAttribute(mmv_fast_kernel<TYPE, NT, J, D, MODE>, cudaFuncAttributePreferredSharedMemoryCarveout, B200_CARVEOUT)); set = true; }
-    int ctas = fast_num_sms() * (NT == 128 ? 4 : NT == 256 ? 2 : 1);
+    int ctas = fast_num_sms() * (NT == 128 ? 4 : NT == 160 ? 3 : NT == 256 ? 2 : 1);
     if (ctas > (W.M + 3) / 4) ctas = (W.M + 3) / 4;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned) ctas, (unsigned) X.N); cfg.blockDim = dim3(NT); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
@@ -234,6 +234,7 @@ static bool launch_type(const WPlanes & W, const FastX & X, float * y, int64_t y
     if (X.mode == 2 && P > 512) return false;                 // the fused LayerNorm needs the whole row inside one CTA pass (J == 1)
     constexpr int D1 = FX<TYPE>::D256;                        // ring depth for one piece per thread; D * J stays constant
     if (P <= 128 && D1 == 4) launch_cfg<TYPE, 128, 1, D1>(W, X, y, y_stride, epi, stream);       // 64-weight pieces (Q3_K): K = 8192 is 128 pieces
+    else if (P > 128 && P <= 160 && D1 == 8 && !getenv("B200_NO_NT160")) launch_cfg<TYPE, 160, 1, D1>(W, X, y, y_stride, epi, stream);   // Falcon-7B: K = 4544 is 142 pieces
     else if (P <= 256) launch_cfg<TYPE, 256, 1, D1>(W, X, y, y_stride, epi, stream);
     else if (P <= 512) launch_cfg<TYPE, 512, 1, D1>(W, X, y, y_stride, epi, stream);
     else if (P <= 1024) launch_cfg<TYPE, 512, 2, D1 / 2>(W, X, y, y_stride, epi, stream);

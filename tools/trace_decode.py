@@ -6,11 +6,12 @@ import ggllm_cpp_b200.binding as b
 import ggllm_cpp_b200.ggcc as ggcc
 
 layers = int(sys.argv[1]) if len(sys.argv) > 1 else 8
+model = sys.argv[2] if len(sys.argv) > 2 else "40b"
 b.init(0); L = b.lib()
 L.b200_trace_enable.argtypes = [C.c_int]; L.b200_trace_reset.argtypes = [C.c_void_p]; L.b200_trace_dump.argtypes = [C.c_void_p, C.c_void_p, C.c_int]; L.b200_trace_dump.restype = C.c_int
-hp = dict(n_vocab=65024, n_embd=8192, n_head=128, n_head_kv=8, n_layer=layers, falcon_type=40)
+hp = dict(n_vocab=65024, n_embd=8192, n_head=128, n_head_kv=8, n_layer=layers, falcon_type=40) if model == "40b" else dict(n_vocab=65024, n_embd=4544, n_head=71, n_head_kv=1, n_layer=layers, falcon_type=7)
 f = b.Falcon(hp, n_ctx=2048, n_batch=1)
-f.set_random(ggcc.falcon_shapes(hp), 12, seed=1234)
+f.set_random(ggcc.falcon_shapes(hp), 12 if model == "40b" else 2, seed=1234)
 L.b200_trace_enable(2048)                      # slots are claimed while the decode graph is captured
 tok = b.DevBuf(src=np.array([1234], np.int32))
 for pos in range(0, 6):
