@@ -21,7 +21,7 @@ PART_A = ["b200_event_create", "b200_event_destroy", "b200_event_record", "b200_
           "b200_gelu", "b200_add", "b200_rope_neox", "b200_attention"]
 PART_B = ["b200_falcon_create", "b200_falcon_set_tensor", "b200_falcon_set_tensor_random", "b200_falcon_load_ggcc",
           "b200_ggcc_read_hparams", "b200_falcon_free", "b200_falcon_weight_bytes", "b200_nccl_unique_id",
-          "b200_falcon_init_pipeline", "b200_falcon_eval", "b200_falcon_decode_dev", "b200_falcon_logits_dev",
+          "b200_falcon_init_pipeline", "b200_falcon_eval", "b200_falcon_decode_dev", "b200_falcon_logits_dev", "b200_falcon_generate_greedy",
           "b200_falcon_last_launches", "b200_falcon_last_ms", "b200_falcon_stream", "b200_falcon_profile_matvec"]
 
 
@@ -62,7 +62,7 @@ def lib():
             "b200_falcon_load_ggcc": (i32, [vp, C.c_char_p]), "b200_ggcc_read_hparams": (i32, [C.c_char_p, vp]),
             "b200_falcon_free": (None, [vp]), "b200_falcon_weight_bytes": (sz, [vp]),
             "b200_nccl_unique_id": (None, [vp]), "b200_falcon_init_pipeline": (None, [vp, vp]),
-            "b200_falcon_eval": (i32, [vp, vp, i32, i32, i32, vp, i32]), "b200_falcon_decode_dev": (None, [vp, vp, i32, i32]),
+            "b200_falcon_eval": (i32, [vp, vp, i32, i32, i32, vp, i32]), "b200_falcon_decode_dev": (None, [vp, vp, i32, i32]), "b200_falcon_generate_greedy": (i32, [vp, i32, i32, i32, i32, vp]),
             "b200_falcon_logits_dev": (vp, [vp]), "b200_falcon_last_launches": (i32, [vp]), "b200_falcon_last_ms": (f32, [vp]),
             "b200_falcon_stream": (vp, [vp]), "b200_falcon_profile_matvec": (f32, [vp, i32, vp, vp]),
         }
@@ -251,6 +251,13 @@ class Falcon:
         rc = self.L.b200_falcon_eval(self.h, _np_ptr(tokens), tokens.size, n_past, n_ctx_rope, _np_ptr(out), int(all_logits))
         if rc != 0:
             raise RuntimeError("b200_falcon_eval failed (rc=%d)" % rc)
+        return out
+
+    def generate_greedy(self, first_token, n_past, n_steps, n_ctx_rope=0):
+        out = np.zeros(n_steps, dtype=np.int32)
+        rc = self.L.b200_falcon_generate_greedy(self.h, int(first_token), n_past, n_steps, n_ctx_rope, _np_ptr(out))
+        if rc != 0:
+            raise RuntimeError("b200_falcon_generate_greedy failed (rc=%d)" % rc)
         return out
 
     def decode_dev(self, token_dev_ptr, n_past, n_ctx_rope=0):

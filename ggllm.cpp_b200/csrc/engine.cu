@@ -600,6 +600,26 @@ void b200_falcon_decode_dev(b200_falcon * f, const int32_t * token_dev, int n_pa
     f->launches = f->graph_launches;
 }
 const float * b200_falcon_logits_dev(const b200_falcon * f) { return f->logits; }
+
+// Greedy generation entirely on the device (single GPU): after every decode step one CTA takes the arg-max of the logits
+// (lowest index on ties, like a sequential scan) and writes it where the next step's embedding gather reads its token id,
+// so no logits and no token cross PCIe between steps.  First slice of SURVEY 8f-2 (the reference samples on the host from
+// a 260 KB logits row per token, falcon_main.cpp:897-980 with top_k = 1 / temp <= 0 -> llama_sample_token_greedy).
+int b200_falcon_generate_greedy(b200_falcon * f, int32_t first_token, int n_past, int n_steps, int n_ctx_rope, int32_t * tokens_out) {
+    if (!f->first || !f->last || n_steps <= 0 || n_past + n_steps > f->hp.n_ctx) return 1;
+    int32_t * hist = nullptr;
+    B200_CUDA_CHECK(cudaMalloc(&hist, (size_t) n_steps * 4));
+    B200_CUDA_CHECK(cudaMemcpyAsync(f->tokens_dev, &first_token, 4, cudaMemcpyHostToDevice, f->s_main));
+    B200_CUDA_CHECK(cudaStreamSynchronize(f->s_main));               // first_token is a stack value
+    for (int i = 0; i < n_steps; i++) {
+        b200_falcon_decode_dev(f, nullptr, n_past + i, n_ctx_rope);  // token id already in f->tokens_dev
+        launch_argmax(f->logits, f->V, f->tokens_dev, hist + i, f->s_main);
+    }
+    B200_CUDA_CHECK(cudaMemcpyAsync(tokens_out, hist, (size_t) n_steps * 4, cudaMemcpyDeviceToHost, f->s_main));
+    B200_CUDA_CHECK(cudaStreamSynchronize(f->s_main));
+    B200_CUDA_CHECK(cudaFree(hist));
+    return 0;
+}
 int b200_falcon_last_launches(const b200_falcon * f) { return f->launches; }
 float b200_falcon_last_ms(const b200_falcon * f) { return f->last_ms; }
 void * b200_falcon_stream(b200_falcon * f) { return (void *) f->s_main; }

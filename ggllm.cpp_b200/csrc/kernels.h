@@ -52,6 +52,7 @@ void   launch_decode_mega(int wtype, const void * layers_dev, int n_layer, float
 void   launch_layernorm(const float * x, int64_t x_stride, const float * g, const float * b, float * y, int64_t y_stride,
                         int n, int rows, cudaStream_t stream);              // y = norm(x)*g + b ; g,b may be null (plain ggml_norm)
 // [x = (ra + rb) + x, written back] ; A1 = Q(norm(x)*g1+b1) ; A2 = Q(norm(x)*g2+b2) (optional)
+void   launch_argmax(const float * x, int n, int32_t * out_a, int32_t * out_b, cudaStream_t stream);     // greedy sampling: lowest index on ties
 void   launch_layernorm_q(float * x, int64_t x_stride, const float * ra, const float * rb, int64_t r_stride,
                           const float * g1, const float * b1, const ActQ * A1,
                           const float * g2, const float * b2, const ActQ * A2, int n, int rows, cudaStream_t stream);

@@ -408,3 +408,31 @@ void launch_rope_kv_append(float * qkv, float * k_cache, float * v_cache, const 
     rope_kv_append_kernel<<<grid, p.head_dim / 2, 0, stream>>>(qkv, k_cache, v_cache, pt, theta_scale);
     B200_CUDA_CHECK(cudaGetLastError());
 }
+
+// ---------------------------------------------------------------------------------------------- greedy sampling
+// arg-max of one logits row; ties -> lowest index (what a sequential `if (x > best)` scan returns); writes the id to two places
+__global__ void __launch_bounds__(1024) argmax_kernel(const float * __restrict__ x, int n, int32_t * __restrict__ out_a, int32_t * __restrict__ out_b) {
+    __shared__ float sv[32]; __shared__ int si[32];
+    float best = -INFINITY; int bi = 0x7fffffff;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) { const float v = x[i]; if (v > best || (v == best && i < bi)) { best = v; bi = i; } }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, best, o); const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+    }
+    if ((threadIdx.x & 31) == 0) { sv[threadIdx.x >> 5] = best; si[threadIdx.x >> 5] = bi; }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        best = sv[threadIdx.x]; bi = si[threadIdx.x];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, best, o); const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+        }
+        if (threadIdx.x == 0) { if (out_a) *out_a = bi; if (out_b) *out_b = bi; }
+    }
+}
+void launch_argmax(const float * x, int n, int32_t * out_a, int32_t * out_b, cudaStream_t stream) {
+    argmax_kernel<<<1, 1024, 0, stream>>>(x, n, out_a, out_b);
+    B200_CUDA_CHECK(cudaGetLastError());
+}

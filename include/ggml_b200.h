@@ -164,6 +164,11 @@ int           b200_falcon_eval(b200_falcon * f, const int32_t * tokens, int n_to
  * device (b200_falcon_logits_dev).  Same kernels/graph as b200_falcon_eval minus the two PCIe copies. */
 void          b200_falcon_decode_dev(b200_falcon * f, const int32_t * token_dev, int n_past, int n_ctx_rope);
 const float * b200_falcon_logits_dev(const b200_falcon * f);
+/* greedy generation without leaving the device (single GPU): feeds `first_token` at position n_past, then n_steps times
+ * "decode, arg-max of the logits (lowest index on ties), use it as the next token".  tokens_out[i] = token sampled after
+ * step i.  What falcon_main does with top_k = 1 (llama_sample_token_greedy, libfalcon.cpp:3464-3473), minus the 260 KB
+ * logits D2H and the host scan per token.  Returns 0 on success. */
+int           b200_falcon_generate_greedy(b200_falcon * f, int32_t first_token, int n_past, int n_steps, int n_ctx_rope, int32_t * tokens_out);
 /* the cudaStream_t the eval path runs on (for event timing) */
 void *        b200_falcon_stream(b200_falcon * f);
 /* roofline probe: every resident quantised mat-vec of this rank (4 per layer + lm_head) launched back to back,

@@ -159,3 +159,22 @@ def test_alternative_decode_paths_match_oracle(gpu, hp, wt, env):
     assert_mostly_tight([assert_logits_close(got, want, "%s step %d" % (env, i)) for i, (got, want) in enumerate(outs)], env)
     if env == "B200_MEGA":
         assert launches <= 5          # embedding + the persistent kernel + final LayerNorm + lm_head
+
+
+def test_greedy_generation_on_device_equals_host_argmax_loop(gpu):
+    """b200_falcon_generate_greedy (arg-max and token feedback on the device) produces the token sequence of the host loop
+    eval -> np.argmax -> eval, and of the oracle's greedy loop while no reassociation-level tie occurs"""
+    hp = dict(TINY_40B)
+    tensors = synth_model(hp, po.Q4_K, seed=5)
+    a, b = gpu.Falcon(hp, n_ctx=64, n_batch=8), gpu.Falcon(hp, n_ctx=64, n_batch=8)
+    a.set_tensors(tensors); b.set_tensors(tensors)
+    prompt = np.array([11, 100, 101, 102], np.int32)
+    a.eval(prompt, 0); lg = b.eval(prompt, 0)
+    first = int(np.argmax(lg[0]))
+    dev = a.generate_greedy(first, len(prompt), 12)
+    host, tok = [], first
+    for i in range(12):
+        tok = int(np.argmax(b.eval(np.array([tok], np.int32), len(prompt) + i)[0]))
+        host.append(tok)
+    assert dev.tolist() == host
+    a.free(); b.free()

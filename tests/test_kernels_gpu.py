@@ -239,7 +239,8 @@ def test_attention(gpu, orc, n_head, n_head_kv, n_tok, n_past):
 
 
 @pytest.mark.parametrize("t,M,K,N,gelu", [(po.Q4_K, 256, 512, 40, 0), (po.Q4_K, 1000, 1024, 300, 0), (po.Q4_K, 384, 2048, 512, 1),
-                                          (po.Q4_0, 200, 256, 17, 0), (po.Q6_K, 128, 512, 64, 0), (po.Q4_K, 128, 8192, 9, 0), (po.Q4_K, 640, 1024, 512, 0)])
+                                          (po.Q4_0, 200, 256, 17, 0), (po.Q6_K, 128, 512, 64, 0), (po.Q4_K, 128, 8192, 9, 0), (po.Q4_K, 640, 1024, 512, 0),
+                                          (po.Q6_K, 300, 512, 260, 0), (po.Q4_K, 520, 2048, 400, 1)])      # N > 256: the 256-row x 256-token tile shape
 def test_tensor_core_gemm_matches_cuda_core_gemm(gpu, orc, t, M, K, N, gelu):
     """tcgen05 kernel vs the CUDA-core kernel on identical fp16 operands: only the fp32 accumulation order differs.
     Then both against the exact fp64 product of the fp16-rounded operands."""
