@@ -10,7 +10,7 @@
 //   warp 0      : TMA producer of the activation tile  B[N x 64] fp16 (cp.async.bulk.tensor.2d, SWIZZLE_128B), ring of SB stages
 //   warp 1      : allocates TMEM (512 columns), single elected thread issues tcgen05.mma.cta_group::1.kind::f16
 //                 (M = 128, N <= 256 per instruction, K = 16), tcgen05.commit releases the smem stages
-//   warps 2..9  : dequant producers: 2 threads per weight row, 32 weights each per 64-wide K block, written as
+//   warps 2..17 : dequant producers: 4 threads per weight row, 16 weights each per 64-wide K block, written as
 //                 8 halves per 16-byte chunk into the K-major SWIZZLE_128B layout (chunk c of row r at c ^ (r & 7)),
 //                 fence.proxy.async, mbarrier arrive; ring of SA stages.  After the main loop the same warps are the
 //                 epilogue: tcgen05.ld 32x32b.x32 -> (GELU) -> coalesced fp32 stores.
@@ -23,7 +23,8 @@ namespace {
 
 constexpr int BM = 128, BK = 64, SA = 4, SB = 2;
 constexpr int N_MAX = 512;
-constexpr int PRODUCER_THREADS = 256, THREADS = 64 + PRODUCER_THREADS;
+constexpr int PRODUCER_THREADS = 512, THREADS = 64 + PRODUCER_THREADS;      // 4 threads per weight row: the dequantisation is a chain of dependent
+                                                                            // fp32 ops per weight, 16 warps hide its latency (8 warps: 1.0 PFLOP/s)
 constexpr int A_STAGE = BM * BK * 2;                       // 16 KB
 
 __device__ __forceinline__ void mbar_arrive(uint64_t * bar) {
@@ -70,31 +71,29 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
     return *reinterpret_cast<const uint32_t *>(&h);
 }
 
-// ---- dequantisation of one thread's share of a 64-wide K block: segments [16h, 16h+16) and [32+16h, 32+16h+16) of the block,
-//      returned as 4 chunks of 8 halves: lo0, lo1 (first segment), hi0, hi1 (second segment)
-struct Chunks { uint4 c[4]; };
+// ---- dequantisation of one thread's share of a 64-wide K block: segments [8h, 8h+8) and [32+8h, 32+8h+8) of the block (h = 0..3),
+//      returned as 2 chunks of 8 halves
+struct Chunks { uint4 c[2]; };      // 8 halves each: elements 8h .. 8h+7 and 32 + 8h .. 32 + 8h+7 of the K block
 
 // generic: element-wise through the bit-exact dequantiser (any type)
 __device__ __forceinline__ Chunks dequant_generic(const WPlanes & W, size_t row, int k0, int h) {
     Chunks o;
 #pragma unroll
-    for (int s = 0; s < 2; s++)
+    for (int s = 0; s < 2; s++) {
+        const int e = k0 + 32 * s + 8 * h;
+        float v[8];
 #pragma unroll
-        for (int c = 0; c < 2; c++) {
-            const int e = k0 + 32 * s + 16 * h + 8 * c;
-            float v[8];
-#pragma unroll
-            for (int i = 0; i < 8; i++) v[i] = dequant_elem(W, row, e + i);
-            o.c[2 * s + c] = make_uint4(pack_h2(v[0], v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
-        }
+        for (int i = 0; i < 8; i++) v[i] = dequant_elem(W, row, e + i);
+        o.c[s] = make_uint4(pack_h2(v[0], v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
+    }
     return o;
 }
 // Q4_K: w = (d*sc)*q - dmin*m, computed in fp32 exactly like dequantize_row_q4_K (k_quants.c:607-631), one rounding to fp16
-struct RawQ4K { uint4 q; uint32_t sm, dd; };
-__device__ __forceinline__ RawQ4K load_q4k(const WPlanes & W, size_t row, int kb, int h) {
+struct RawQ4K { uint2 q; uint32_t sm, dd; };
+__device__ __forceinline__ RawQ4K load_q4k(const WPlanes & W, size_t row, int kb, int h) {      // h = 0..3: bytes 8h .. 8h+7 of the 32
     RawQ4K r;
     const int b = kb >> 2, p = kb & 3;
-    r.q = ldg_stream_v4(W.p[0] + row * W.stride[0] + (size_t) b * 128 + p * 32 + h * 16);
+    r.q = ldg_stream_v2(W.p[0] + row * W.stride[0] + (size_t) b * 128 + p * 32 + h * 8);
     r.sm = ldg_u32(W.p[1] + row * W.stride[1] + (size_t) b * 16 + p * 4);
     r.dd = ldg_u32(W.p[2] + row * W.stride[2] + (size_t) b * 4);
     return r;
@@ -103,10 +102,10 @@ __device__ __forceinline__ Chunks dequant_q4k(const RawQ4K & r) {
     const float2 dm = __half22float2(*reinterpret_cast<const __half2 *>(&r.dd));
     const float d0 = __fmul_rn(dm.x, (float) (r.sm & 0xff)), d1 = __fmul_rn(dm.x, (float) ((r.sm >> 8) & 0xff));
     const float m0 = __fmul_rn(dm.y, (float) ((r.sm >> 16) & 0xff)), m1 = __fmul_rn(dm.y, (float) (r.sm >> 24));
-    const uint32_t w[4] = { r.q.x, r.q.y, r.q.z, r.q.w };
-    float lo[16], hi[16];
+    const uint32_t w[2] = { r.q.x, r.q.y };
+    float lo[8], hi[8];
 #pragma unroll
-    for (int i = 0; i < 4; i++)
+    for (int i = 0; i < 2; i++)
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             const uint32_t byte = (w[i] >> (8 * j)) & 0xff;
@@ -115,9 +114,7 @@ __device__ __forceinline__ Chunks dequant_q4k(const RawQ4K & r) {
         }
     Chunks o;
     o.c[0] = make_uint4(pack_h2(lo[0], lo[1]), pack_h2(lo[2], lo[3]), pack_h2(lo[4], lo[5]), pack_h2(lo[6], lo[7]));
-    o.c[1] = make_uint4(pack_h2(lo[8], lo[9]), pack_h2(lo[10], lo[11]), pack_h2(lo[12], lo[13]), pack_h2(lo[14], lo[15]));
-    o.c[2] = make_uint4(pack_h2(hi[0], hi[1]), pack_h2(hi[2], hi[3]), pack_h2(hi[4], hi[5]), pack_h2(hi[6], hi[7]));
-    o.c[3] = make_uint4(pack_h2(hi[8], hi[9]), pack_h2(hi[10], hi[11]), pack_h2(hi[12], hi[13]), pack_h2(hi[14], hi[15]));
+    o.c[1] = make_uint4(pack_h2(hi[0], hi[1]), pack_h2(hi[2], hi[3]), pack_h2(hi[4], hi[5]), pack_h2(hi[6], hi[7]));
     return o;
 }
 
@@ -197,7 +194,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
         }
     } else {
         // ===== dequant producers (2 threads per weight row) =====
-        const int t = threadIdx.x - 64, r = t >> 1, h = t & 1;
+        const int t = threadIdx.x - 64, r = t >> 2, h = t & 3;
         const size_t row = (size_t) min(m0 + r, a.W.M - 1);                // rows past M are computed from row M-1 and never stored
         uint8_t * my_row = nullptr;
         RawQ4K raw;
@@ -212,10 +209,8 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
             if (kb >= SA) mbar_wait(a_empty + s, (uint32_t) ((kb / SA - 1) & 1));
             my_row = sA + (size_t) s * A_STAGE + r * 128;
             const int sw = r & 7;
-            *reinterpret_cast<uint4 *>(my_row + (((2 * h) ^ sw) << 4)) = ch.c[0];          // elements 16h .. 16h+7
-            *reinterpret_cast<uint4 *>(my_row + (((2 * h + 1) ^ sw) << 4)) = ch.c[1];      //          16h+8 .. 16h+15
-            *reinterpret_cast<uint4 *>(my_row + (((4 + 2 * h) ^ sw) << 4)) = ch.c[2];      // elements 32+16h ..
-            *reinterpret_cast<uint4 *>(my_row + (((5 + 2 * h) ^ sw) << 4)) = ch.c[3];
+            *reinterpret_cast<uint4 *>(my_row + ((h ^ sw) << 4)) = ch.c[0];                // elements 8h .. 8h+7
+            *reinterpret_cast<uint4 *>(my_row + (((4 + h) ^ sw) << 4)) = ch.c[1];          // elements 32+8h .. 32+8h+7
             fence_proxy_async();                                           // generic-proxy stores -> visible to the tensor core (async proxy)
             mbar_arrive(a_full + s);
         }
@@ -223,10 +218,10 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
         mbar_wait(acc_full, 0);
         tc_fence_after();
         const int q = warp & 3;                                            // TMEM lane quarter this warp may access
-        const int half_id = (warp - 2) >> 2;                               // two warps share a quarter: even / odd 32-column chunks
+        const int half_id = (warp - 2) >> 2;                               // four warps share a quarter: 32-column chunks c = id, id + 4, ...
         const int m = m0 + q * 32 + lane;
         const int nchunks = (a.NT + 31) / 32;
-        for (int c = half_id; c < nchunks; c += 2) {
+        for (int c = half_id; c < nchunks; c += PRODUCER_THREADS / 128) {
             uint32_t v[32];
             tmem_ld32(tmem_base + ((uint32_t) (q * 32) << 16) + (uint32_t) (c * 32), v);
             if (m < a.W.M) {
