@@ -328,3 +328,47 @@ def test_matvec_chain_quantises_output_for_next_matmul(gpu, orc, t, K, M):
         A_ref.quantize(yd.ptr)
         (q, d, _, bs), (q0, d0, _, bs0) = A_out.download(), A_ref.download()      # (the s plane exists for Q8_1 only)
         assert np.array_equal(q, q0) and np.array_equal(d, d0) and np.array_equal(bs, bs0)
+
+
+@pytest.mark.parametrize("t,K,M", [(po.Q4_K, 8192, 65024), (po.Q4_K, 32768, 8192), (po.Q4_K, 8192, 32768), (po.Q4_0, 4544, 65024),
+                                   (po.Q4_0, 18176, 4544), (po.Q3_K, 8192, 9216)])
+def test_full_size_matvec_all_rows(gpu, orc, t, K, M):
+    """BASELINE's real matrix shapes (Falcon-40B / 7B qkv, ffn, lm_head), every output row against the oracle's
+    mul_mat_q_f32 restatement.  Weights are well-formed random blocks (any byte pattern is a valid block), so the integer
+    block dots are exact on both sides and only the fp32 summation order differs."""
+    import ggllm_cpp_b200.ggcc as ggcc
+    rng = np.random.default_rng(K ^ M)
+    wq = ggcc.random_blocks(t, M, K, rng)
+    x = rng.standard_normal((1, K)).astype(np.float32)
+    W = gpu.Weight(t, K, M, wq)
+    xd, yd = gpu.DevBuf(src=x), gpu.DevBuf(M * 4)
+    A = gpu.ActQ(t, K, 1); A.quantize(xd.ptr)
+    gpu.lib().b200_mul_mat_vec_q(W.h, A.h, yd.ptr, M, 0, None, None)
+    got = yd.download(np.float32, (M,))
+    want = orc.mul_mat(t, wq, K, M, x)[0]
+    scale = float(np.abs(want).max())
+    assert np.isfinite(got).all() and scale > 0
+    assert np.abs(got - want).max() <= 2e-5 * scale, (float(np.abs(got - want).max()), scale)
+    assert np.median(np.abs(got - want)) <= 1e-6 * scale
+
+
+@pytest.mark.parametrize("K,M,N", [(8192, 32768, 512), (32768, 8192, 512), (8192, 9216, 384)])
+def test_full_size_gemm_tensor_core_vs_cuda_core(gpu, K, M, N):
+    """BASELINE config 3 shapes (Falcon-40B ffn_up / ffn_down / qkv at n_batch 512): the tcgen05 kernel and the CUDA-core
+    reference kernel read the same Q4_K blocks and the same fp16 activations; only the fp32 accumulation order differs."""
+    import ggllm_cpp_b200.ggcc as ggcc
+    rng = np.random.default_rng(K + M + N)
+    wq = ggcc.random_blocks(po.Q4_K, M, K, rng)
+    xh = rng.standard_normal((N, K)).astype(np.float16)
+    W = gpu.Weight(po.Q4_K, K, M, wq)
+    xd, y0, y1 = gpu.DevBuf(src=xh), gpu.DevBuf(N * M * 4), gpu.DevBuf(N * M * 4)
+    y1.zero()
+    assert gpu.lib().b200_mul_mat_f16(W.h, xd.ptr, K, N, y0.ptr, M, 0, 0) == 1
+    assert gpu.lib().b200_mul_mat_f16(W.h, xd.ptr, K, N, y1.ptr, M, 0, 1) == 1
+    a, b = y0.download(np.float32, (N, M)), y1.download(np.float32, (N, M))
+    scale = float(np.abs(a).max())
+    assert np.isfinite(b).all() and scale > 0
+    # fp32 reassociation over K products (and the two-way K split of the tcgen05 kernel): grows like sqrt(K)
+    grow = (K / 8192.0) ** 0.5
+    assert np.abs(a - b).max() <= 1e-4 * grow * scale, (float(np.abs(a - b).max()), scale)
+    assert np.median(np.abs(a - b)) <= 5e-6 * grow * scale, (float(np.median(np.abs(a - b))), scale)
