@@ -59,7 +59,10 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
     const __half2 h = __floats2half2_rn(a, b);
     return *reinterpret_cast<const uint32_t *>(&h);
 }
-__device__ __forceinline__ float exp_lut(float v) { return __half2float(__float2half_rn(expf(__half2float(__float2half_rn(v))))); }   // ggml.c:4281-4290
+// table_exp_f16[f16(v)] (ggml.c:4281-4290) with the fast exponential: ex2.approx is within 2 ulp (fp32) of expf, so the fp16-rounded
+// result differs from the table only when the exact value sits within ~1e-6 (relative) of an fp16 rounding boundary (about one
+// entry in a thousand, by one fp16 ulp) -- inside this path's fp16-operand tolerance; the decode kernels keep expf
+__device__ __forceinline__ float exp_lut(float v) { return __half2float(__float2half_rn(__expf(__half2float(__float2half_rn(v))))); }
 
 struct AttnTcArgs {
     const float * qkv; const float * kc; const float * vc; float * out;
@@ -98,6 +101,7 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attention_tc_kernel(const AttnT
     const int vis = row_ok ? a.n_past + tok + 1 : 0;                      // causal: keys < vis (ggml.c:12342-12348)
     const int t_last = (min(r0 + AT_M, a.rows) - 1) / a.G;
     const int kmax = a.n_past + t_last + 1, ntiles = (kmax + AT_N - 1) / AT_N;
+    const int vis_min = r0 + AT_M <= a.rows ? a.n_past + r0 / a.G + 1 : 0;   // keys visible to EVERY row of the tile (0 if it has padding rows)
     const float scale = 1.0f / sqrtf((float) AT_D);
 
     if (tt == 0) { mbar_init(bar_s, 1); mbar_init(bar_pv, 1); mbar_fence_init(); }
@@ -179,6 +183,7 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attention_tc_kernel(const AttnT
         if (tt == 0) s_mma();
         mbar_wait(bar_s, ns & 1); ns++;
         tc_fence_after();
+        const bool full = k0 + AT_N <= vis_min;                           // every key of the tile is visible to every row: no mask tests
 #pragma unroll
         for (int cc = 0; cc < 2; cc++) {
             const int c = 2 * hf + cc;
@@ -191,7 +196,7 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attention_tc_kernel(const AttnT
 #pragma unroll
                 for (int j = 0; j < 8; j++) {
                     const float s = __fmul_rn(__uint_as_float(v[8 * q + j]), scale);
-                    e[j] = (k0 + c * 32 + 8 * q + j < vis) ? exp_lut(__fsub_rn(s, m)) : 0.f;
+                    e[j] = (full || k0 + c * 32 + 8 * q + j < vis) ? exp_lut(__fsub_rn(s, m)) : 0.f;
                     l += e[j];
                 }
                 const int ci = (c & 1) * 4 + q;

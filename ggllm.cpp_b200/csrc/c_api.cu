@@ -203,8 +203,10 @@ void b200_attention(float * qkv, float * kc, float * vc, float * out, int n_head
     AttnParams p = { n_head, n_head_kv, head_dim, n_tok, n_past, nullptr, n_ctx, (int64_t) (n_head + 2 * n_head_kv) * head_dim, nullptr };
     launch_rope_kv_append(qkv, kc, vc, p, rope_theta_scale_host(head_dim, n_ctx_rope ? n_ctx_rope : n_ctx, 1, 2.0f, 0), g_stream);   // libfalcon.cpp:2231-2234
     if (n_tok > 1) {
-        float * sc = (float *) scratch(attention_prefill_scratch_bytes(n_head, n_tok, n_past + n_tok));
-        launch_attention_prefill(qkv, kc, vc, out, (int64_t) n_head * head_dim, p, sc, g_stream);
+        if (!launch_attention_tc(qkv, kc, vc, out, (int64_t) n_head * head_dim, p, g_stream)) {
+            float * sc = (float *) scratch(attention_prefill_scratch_bytes(n_head, n_tok, n_past + n_tok));
+            launch_attention_prefill(qkv, kc, vc, out, (int64_t) n_head * head_dim, p, sc, g_stream);
+        }
     } else {
         const size_t sb = attention_scratch_bytes(p);
         float * sc = sb ? (float *) scratch(sb) : nullptr;

@@ -504,8 +504,11 @@ static void enqueue_eval(b200_falcon * f, int N, int n_past, float theta_scale, 
         const size_t kvoff = (size_t) l * f->hp.n_ctx * f->HKV * f->D;
         launch_rope_kv_append(f->qkv, f->k_cache + kvoff, f->v_cache + kvoff, ap, theta_scale, sa);             // :2229-2281
         if (N > 1 && !graph_mode) {
-            if (!f->attn_scratch) B200_CUDA_CHECK(cudaMalloc(&f->attn_scratch, attention_prefill_scratch_bytes(f->H, f->hp.n_batch, f->hp.n_ctx)));
-            launch_attention_prefill(f->qkv, f->k_cache + kvoff, f->v_cache + kvoff, f->att, E, ap, f->attn_scratch, sa); f->launches++;
+            // tensor-core kernel (no scratch); the CUDA-core fallback (N <= 8 or head_dim != 64) materialises the score matrix
+            if (!launch_attention_tc(f->qkv, f->k_cache + kvoff, f->v_cache + kvoff, f->att, E, ap, sa)) {
+                if (!f->attn_scratch) B200_CUDA_CHECK(cudaMalloc(&f->attn_scratch, attention_prefill_scratch_bytes(f->H, f->hp.n_batch, f->hp.n_ctx)));
+                launch_attention_prefill(f->qkv, f->k_cache + kvoff, f->v_cache + kvoff, f->att, E, ap, f->attn_scratch, sa); f->launches++;
+            }
         } else launch_attention(f->qkv, f->k_cache + kvoff, f->v_cache + kvoff, f->att, E, ap, N == 1 ? f->attn_dec_scratch : nullptr, sa);     // :2285-2366
         launch_quantize_act(f->att, E, xatt, sa);
         f->launches += 3;
