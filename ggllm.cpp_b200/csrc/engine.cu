@@ -4,10 +4,12 @@
 // :1335-1385, graph builder falcon_eval_internal :2011-2588) plus one H2D + kernel + D2H + cudaDeviceSynchronize
 // round trip per MUL_MAT node (ggml-cuda.cu:2520-2820, 241 per 40B token) becomes:
 //   * weights uploaded once into planar device layout; KV cache and every activation live in HBM
-//   * one eval = ~9 kernels per layer on two streams (attention branch || MLP branch, which Falcon's parallel
-//     block makes independent, libfalcon.cpp:2166-2188 / 2382-2401); only token ids go H2D and logits D2H
+//   * a prompt eval (N > 1) = ~9 kernels per layer on two streams (attention branch || MLP branch, which Falcon's
+//     parallel block makes independent, libfalcon.cpp:2166-2188 / 2382-2401); only token ids go H2D and logits D2H
 //   * decode (N == 1) is captured once into a CUDA graph and replayed; n_past and the token id are read from
-//     device scalars so the same graph serves every position
+//     device scalars so the same graph serves every position.  For the types with a register-resident mat-vec the
+//     four mat-vecs of a layer run back to back on one stream, chained by programmatic dependent launch, with the
+//     small attention kernels beside ffn_up on the second stream (enqueue_decode_fused)
 //   * multi-GPU = contiguous layer ranges, one process per GPU; the residual stream [N x n_embd] f32 crosses each
 //     boundary with a single ncclSend/ncclRecv on the compute stream (replaces the row-split tensor parallelism of
 //     ggml-cuda.cu:2594-2601, 2719-2725, 2779-2788)
@@ -71,7 +73,6 @@ struct b200_falcon {
     void * gemm_ws_a = nullptr, * gemm_ws_b = nullptr; size_t gemm_ws_bytes = 0;
     float * attn_scratch = nullptr;
     float * attn_dec_scratch = nullptr;            // split-KV decode attention: counters + scores + partials (attention.cu)
-    float * inp2 = nullptr, * ao2 = nullptr, * dn2 = nullptr;      // ping-pong partners of inp / ao / dn for the fused decode path
     int32_t * tokens_dev = nullptr; int * n_past_dev = nullptr;
     int32_t * tokens_h = nullptr; int * n_past_h = nullptr; float * logits_h = nullptr; size_t logits_h_floats = 0;
     cudaStream_t s_main = nullptr, s_mlp = nullptr;
@@ -178,7 +179,6 @@ b200_falcon * b200_falcon_create(const b200_falcon_params * p) {
     B200_CUDA_CHECK(cudaMalloc(&f->att, NB * f->E * 4)); B200_CUDA_CHECK(cudaMalloc(&f->ao, NB * f->E * 4));
     B200_CUDA_CHECK(cudaMalloc(&f->up, NB * f->FF * 4)); B200_CUDA_CHECK(cudaMalloc(&f->dn, NB * f->E * 4));
     B200_CUDA_CHECK(cudaMalloc(&f->logits, NB * f->V * 4));
-    B200_CUDA_CHECK(cudaMalloc(&f->inp2, (size_t) f->E * 4)); B200_CUDA_CHECK(cudaMalloc(&f->ao2, (size_t) f->E * 4)); B200_CUDA_CHECK(cudaMalloc(&f->dn2, (size_t) f->E * 4));
     B200_CUDA_CHECK(cudaMalloc(&f->tokens_dev, NB * 4)); B200_CUDA_CHECK(cudaMalloc(&f->n_past_dev, 4));
     B200_CUDA_CHECK(cudaMallocHost(&f->tokens_h, NB * 4)); B200_CUDA_CHECK(cudaMallocHost(&f->n_past_h, 4));
     f->logits_h_floats = (size_t) f->V; B200_CUDA_CHECK(cudaMallocHost(&f->logits_h, f->logits_h_floats * 4));
@@ -324,7 +324,7 @@ void b200_falcon_free(b200_falcon * f) {
     wplanes_free(f->tok_emb); wplanes_free(f->lm_head);
     cudaFree(f->lnf_g); cudaFree(f->lnf_b); cudaFree(f->k_cache); cudaFree(f->v_cache);
     cudaFree(f->inp); cudaFree(f->qkv); cudaFree(f->att); cudaFree(f->ao); cudaFree(f->up); cudaFree(f->dn); cudaFree(f->logits);
-    cudaFree(f->inp2); cudaFree(f->ao2); cudaFree(f->dn2); cudaFree(f->attn_scratch); cudaFree(f->actq_mem); cudaFree(f->xh_a); cudaFree(f->xh_b); cudaFree(f->gemm_ws_a); cudaFree(f->gemm_ws_b);
+    cudaFree(f->attn_scratch); cudaFree(f->actq_mem); cudaFree(f->xh_a); cudaFree(f->xh_b); cudaFree(f->gemm_ws_a); cudaFree(f->gemm_ws_b);
     cudaFree(f->tokens_dev); cudaFree(f->n_past_dev); cudaFree(f->mega_layers); cudaFree(f->mega_flags); cudaFree(f->q_ctr); cudaFree(f->ln_ctr); cudaFree(f->attn_dec_scratch);
     cudaFreeHost(f->tokens_h); cudaFreeHost(f->n_past_h); cudaFreeHost(f->logits_h);
     for (int i = 0; i < 2; i++) if (f->graph[i]) cudaGraphExecDestroy(f->graph[i]);
