@@ -4,9 +4,10 @@
 #include "formats.cuh"
 
 // Each lane owns 8 consecutive values v[0..8) starting at element k0 of activation row n; a 256-block is one
-// full warp, a 32-block is 4 consecutive lanes.  All lanes of a block must call this together.
+// full warp, a 32-block is 4 consecutive lanes.  All lanes of a WARP must call this together (the shuffles name every lane);
+// blocks whose lanes pass store == false (whole blocks past the end of a row) compute on their zeros and write nothing.
 template <int TYPE>
-__device__ __forceinline__ void quantize_chunk8(const float (&v)[8], int lane, const ActQ & A, int n, int k0) {
+__device__ __forceinline__ void quantize_chunk8(const float (&v)[8], int lane, const ActQ & A, int n, int k0, bool store = true) {
     constexpr int LANES = TYPE == T_Q8_K ? 32 : 4;                  // lanes per block
     float amax = 0.f, vmax = 0.f; int imax = 0;
 #pragma unroll
@@ -40,16 +41,16 @@ __device__ __forceinline__ void quantize_chunk8(const float (&v)[8], int lane, c
     }
     const uint32_t lo = (q[0] & 0xff) | ((q[1] & 0xff) << 8) | ((q[2] & 0xff) << 16) | ((uint32_t) (q[3] & 0xff) << 24);
     const uint32_t hi = (q[4] & 0xff) | ((q[5] & 0xff) << 8) | ((q[6] & 0xff) << 16) | ((uint32_t) (q[7] & 0xff) << 24);
-    *reinterpret_cast<uint2 *>(A.q + (size_t) n * A.K + k0) = make_uint2(lo, hi);
+    if (store) *reinterpret_cast<uint2 *>(A.q + (size_t) n * A.K + k0) = make_uint2(lo, hi);
 
     if (TYPE == T_Q8_K) {
         const int s16 = sum + __shfl_xor_sync(0xffffffffu, sum, 1);              // 16 codes = 2 lanes
-        if ((lane & 1) == 0) A.bs[(size_t) n * (A.K / 16) + k0 / 16] = (int16_t) s16;
-        if (lane == 0) A.d[(size_t) n * (A.K / 256) + k0 / 256] = d;
+        if (store && (lane & 1) == 0) A.bs[(size_t) n * (A.K / 16) + k0 / 16] = (int16_t) s16;
+        if (store && lane == 0) A.d[(size_t) n * (A.K / 256) + k0 / 256] = d;
     } else {
         int s32 = sum + __shfl_xor_sync(0xffffffffu, sum, 1);
         s32 += __shfl_xor_sync(0xffffffffu, s32, 2);
-        if ((lane & 3) == 0) {
+        if (store && (lane & 3) == 0) {
             A.d[(size_t) n * (A.K / 32) + k0 / 32] = d;
             A.bs[(size_t) n * (A.K / 32) + k0 / 32] = (int16_t) s32;     // not part of block_q8_0/1: lets the mat-vec fold the -8 / -16 code offsets
             if (TYPE == T_Q8_1) A.s[(size_t) n * (A.K / 32) + k0 / 32] = __fmul_rn(d, (float) s32);

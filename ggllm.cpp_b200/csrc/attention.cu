@@ -16,6 +16,7 @@
 // v1 kernel: one CTA per (query head, query token); scores live in shared memory (T floats).  Exact oracle
 // semantics (global max before exp).  Fine for decode; the prompt path gets a tiled tensor-core kernel later.
 #include "kernels.h"
+#include "actquant.cuh"
 
 #define ATT_THREADS 128
 
@@ -110,6 +111,7 @@ struct AttnDecArgs {
     float * S; float * pmax; double * psum; float * opart; unsigned * ctr;
     int n_head, n_head_kv, G, n_past; const int * n_past_dev; int n_ctx; int64_t qkv_stride;
     unsigned long long * trace;
+    ActQ qA; int has_q;          // optional quantised copy of the output row (see AttnParams::qout)
 };
 
 // 16 per-lane values -> lane l ends up with the warp total of value (l >> 1)
@@ -279,17 +281,18 @@ __global__ void __launch_bounds__(AD_THREADS, 6) attn_dec_values_kernel(const At
     // 16 x 64 outputs as 256 float4 items, two per thread, every split's partial read once: batches of 8 splits x 2 items in
     // flight (this tail is the fixed cost of the kernel, keep it short)
     {
-        const int i0 = tid, i1 = tid + AD_THREADS;                          // item = (head, 4 dims): head = i / 16, dims 4 * (i % 16)
+        const int i0 = 2 * tid, i1 = 2 * tid + 1;                           // float4 items: thread = 8 consecutive outputs of head tid / 8
         float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0;
         const float * base = a.opart + (size_t) h0 * 64;
+        const int hA = tid / 8;
 #pragma unroll 1
         for (int sp = 0; sp < AD_SPLITS; sp += 8) {
             float4 t0[8], t1[8];
 #pragma unroll
             for (int u = 0; u < 8; u++) {
                 const float * ps = base + (size_t) (sp + u) * a.n_head * 64;
-                t0[u] = i0 / 16 < G ? __ldcg(reinterpret_cast<const float4 *>(ps) + i0) : make_float4(0.f, 0.f, 0.f, 0.f);
-                t1[u] = i1 / 16 < G ? __ldcg(reinterpret_cast<const float4 *>(ps) + i1) : make_float4(0.f, 0.f, 0.f, 0.f);
+                t0[u] = hA < G ? __ldcg(reinterpret_cast<const float4 *>(ps) + i0) : make_float4(0.f, 0.f, 0.f, 0.f);
+                t1[u] = hA < G ? __ldcg(reinterpret_cast<const float4 *>(ps) + i1) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
 #pragma unroll
             for (int u = 0; u < 8; u++) {                                   // fixed split order: deterministic
@@ -297,9 +300,19 @@ __global__ void __launch_bounds__(AD_THREADS, 6) attn_dec_values_kernel(const At
                 r1.x += t1[u].x; r1.y += t1[u].y; r1.z += t1[u].z; r1.w += t1[u].w;
             }
         }
-        const int hA = i0 / 16, hB = i1 / 16;
-        if (hA < G) { const float s = inv_s[hA]; *(reinterpret_cast<float4 *>(a.out + (size_t) h0 * 64) + i0) = make_float4(__fmul_rn(r0.x, s), __fmul_rn(r0.y, s), __fmul_rn(r0.z, s), __fmul_rn(r0.w, s)); }
-        if (hB < G) { const float s = inv_s[hB]; *(reinterpret_cast<float4 *>(a.out + (size_t) h0 * 64) + i1) = make_float4(__fmul_rn(r1.x, s), __fmul_rn(r1.y, s), __fmul_rn(r1.z, s), __fmul_rn(r1.w, s)); }
+        const float s = hA < G ? inv_s[hA] : 0.f;
+        const float y[8] = { __fmul_rn(r0.x, s), __fmul_rn(r0.y, s), __fmul_rn(r0.z, s), __fmul_rn(r0.w, s),
+                             __fmul_rn(r1.x, s), __fmul_rn(r1.y, s), __fmul_rn(r1.z, s), __fmul_rn(r1.w, s) };
+        if (hA < G) {
+            float4 * dst = reinterpret_cast<float4 *>(a.out + (size_t) h0 * 64) + i0;
+            dst[0] = make_float4(y[0], y[1], y[2], y[3]); dst[1] = make_float4(y[4], y[5], y[6], y[7]);
+        }
+        if (a.has_q) {                                                      // wo's activation quantisation, here instead of in a kernel of its own
+            const int k0 = h0 * 64 + 8 * tid;                               // a warp = 256 consecutive outputs = 4 heads
+            if (a.qA.type == T_Q8_K) quantize_chunk8<T_Q8_K>(y, lane, a.qA, 0, k0, hA < G);
+            else if (a.qA.type == T_Q8_1) quantize_chunk8<T_Q8_1>(y, lane, a.qA, 0, k0, hA < G);
+            else quantize_chunk8<T_Q8_0>(y, lane, a.qA, 0, k0, hA < G);
+        }
     }
     trace_end(a.trace);
 }
@@ -329,6 +342,10 @@ static bool launch_attention_split(const float * qkv, const float * k_cache, con
     a.qkv = qkv; a.kc = k_cache; a.vc = v_cache; a.out = out;
     a.n_head = p.n_head; a.n_head_kv = p.n_head_kv; a.G = p.n_head / p.n_head_kv; a.n_past = p.n_past; a.n_past_dev = p.n_past_dev; a.n_ctx = p.n_ctx;
     a.qkv_stride = p.qkv_stride;
+    // Q8_K blocks are 256 outputs = 4 heads: they must not straddle the 16-head groups the CTAs combine
+    a.has_q = p.qout != nullptr && (p.qout->type != T_Q8_K || G % 4 == 0);
+    if (a.has_q) a.qA = *p.qout;
+    B200_ASSERT(p.qout == nullptr || a.has_q);
     static bool set = false;
     if (!set) {
         B200_CUDA_CHECK(cudaFuncSetAttribute(attn_dec_values_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
@@ -351,6 +368,7 @@ int launch_attention(const float * qkv, const float * k_cache, const float * v_c
                       const AttnParams & p, float * scratch, cudaStream_t stream) {
     if (p.n_tok <= 0) return 0;
     if (launch_attention_split(qkv, k_cache, v_cache, out, p, scratch, stream)) return 2;
+    B200_ASSERT(p.qout == nullptr && "attention: a quantised output copy needs the split-KV kernels");
     B200_ASSERT(p.head_dim % 4 == 0 && ATT_THREADS % p.head_dim == 0);
     // shared memory is sized for the worst case so that a captured graph stays valid while n_past grows
     const int t_max = p.n_past_dev ? p.n_ctx : p.n_past + p.n_tok;

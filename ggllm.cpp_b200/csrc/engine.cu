@@ -438,8 +438,12 @@ static void enqueue_decode_fused(b200_falcon * f, int n_past, float theta_scale,
         const size_t kvoff = (size_t) l * f->hp.n_ctx * f->HKV * f->D;
         if (!skip("attn")) {
         launch_rope_kv_append(f->qkv, f->k_cache + kvoff, f->v_cache + kvoff, ap, theta_scale, sb);             // :2229-2281
+        // wo's activation quantisation: done by the attention kernel's combine step when its blocks fit the head groups,
+        // else by a kernel of its own; either way off the critical path
+        const bool fold_q = f->attn_dec_scratch && f->D == 64 && !getenv("B200_ATTN_NOSPLIT") && !getenv("B200_ATTN_NOFOLD") && (xatt.type != T_Q8_K || (f->H / f->HKV) % 4 == 0);
+        if (fold_q) ap.qout = &xatt;
         f->launches += launch_attention(f->qkv, f->k_cache + kvoff, f->v_cache + kvoff, f->att, E, ap, f->attn_dec_scratch, sb) - 1; // :2285-2366
-        launch_quantize_act(f->att, E, xatt, sb);                                                               // wo's INIT pass, off the critical path
+        if (!fold_q) launch_quantize_act(f->att, E, xatt, sb); else f->launches--;
         }
         B200_CUDA_CHECK(cudaEventRecord(f->e_join, sb));
         if (!skip("up")) launch_mmv(L.up, xm, f->up, f->FF, gelu, sa);                                           // :2389-2392

@@ -77,6 +77,7 @@ struct AttnParams {
     int n_ctx;                  // KV capacity (row count of the cache)
     int64_t qkv_stride;         // floats between consecutive tokens in the fused QKV buffer
     unsigned long long * trace; // optional timeline slot (debug)
+    const ActQ * qout;          // optional (split-KV decode kernels): also emit the output row quantised for the wo mat-mul (its INIT pass)
 };
 // fused: rope(Q), rope(K) -> K cache append, V cache append      (libfalcon.cpp:2229-2281)
 void   launch_rope_kv_append(float * qkv, float * k_cache, float * v_cache, const AttnParams & p, float theta_scale, cudaStream_t stream);

@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(LNR_THREADS) layernorm_q_reg_kernel(float * __
     trace_end(trace);
 }
 
-// Decode (one row): the same LayerNorm + quantisation spread over a thread-block CLUSTER of n / 1024 CTAs x 128 threads,
+// Decode (one row): the same LayerNorm + quantisation spread over a thread-block CLUSTER of ceil(n / 1024) <= 8 CTAs x 128 threads,
 // 8 values per thread.  The 1024-thread single-CTA kernel above needs a whole SM's registers, so it cannot become resident
 // before the previous mat-vec has drained, and its ~64 registers per thread leave no room to have gamma / beta in flight
 // early: 7 us between the end of wo and the first qkv row (profiles/r1_decode_timeline.md).  Here every CTA is small enough
@@ -209,20 +209,26 @@ __global__ void __launch_bounds__(LNC_THREADS) layernorm_q_cluster_kernel(float 
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, C = gridDim.x;
     const int e = ((int) blockIdx.x * LNC_THREADS + threadIdx.x) * 8;
+    const bool ok = e < n;                                            // the last CTA of a row that is not a multiple of 1024 has idle lanes
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
     // weights first: they do not depend on the previous kernel
-    const float4 ga = __ldg(reinterpret_cast<const float4 *>(g1 + e)), gb = __ldg(reinterpret_cast<const float4 *>(g1 + e + 4));
-    const float4 ba = __ldg(reinterpret_cast<const float4 *>(b1 + e)), bb = __ldg(reinterpret_cast<const float4 *>(b1 + e + 4));
+    float4 ga = z4, gb = z4, ba = z4, bb = z4;
+    if (ok) { ga = __ldg(reinterpret_cast<const float4 *>(g1 + e)); gb = __ldg(reinterpret_cast<const float4 *>(g1 + e + 4));
+              ba = __ldg(reinterpret_cast<const float4 *>(b1 + e)); bb = __ldg(reinterpret_cast<const float4 *>(b1 + e + 4)); }
     float4 ha = ga, hb = gb, ca = ba, cb = bb;
-    if (has2) { ha = __ldg(reinterpret_cast<const float4 *>(g2 + e)); hb = __ldg(reinterpret_cast<const float4 *>(g2 + e + 4));
-                ca = __ldg(reinterpret_cast<const float4 *>(b2 + e)); cb = __ldg(reinterpret_cast<const float4 *>(b2 + e + 4)); }
+    if (has2 && ok) { ha = __ldg(reinterpret_cast<const float4 *>(g2 + e)); hb = __ldg(reinterpret_cast<const float4 *>(g2 + e + 4));
+                      ca = __ldg(reinterpret_cast<const float4 *>(b2 + e)); cb = __ldg(reinterpret_cast<const float4 *>(b2 + e + 4)); }
     asm volatile("griddepcontrol.wait;" ::: "memory");
-    float4 p = *reinterpret_cast<const float4 *>(x + e), q = *reinterpret_cast<const float4 *>(x + e + 4);
-    if (ra) {
-        const float4 a0 = *reinterpret_cast<const float4 *>(ra + e), a1 = *reinterpret_cast<const float4 *>(ra + e + 4);
-        const float4 c0 = *reinterpret_cast<const float4 *>(rb + e), c1 = *reinterpret_cast<const float4 *>(rb + e + 4);
-        p.x = __fadd_rn(__fadd_rn(a0.x, c0.x), p.x); p.y = __fadd_rn(__fadd_rn(a0.y, c0.y), p.y); p.z = __fadd_rn(__fadd_rn(a0.z, c0.z), p.z); p.w = __fadd_rn(__fadd_rn(a0.w, c0.w), p.w);
-        q.x = __fadd_rn(__fadd_rn(a1.x, c1.x), q.x); q.y = __fadd_rn(__fadd_rn(a1.y, c1.y), q.y); q.z = __fadd_rn(__fadd_rn(a1.z, c1.z), q.z); q.w = __fadd_rn(__fadd_rn(a1.w, c1.w), q.w);
-        *reinterpret_cast<float4 *>(x + e) = p; *reinterpret_cast<float4 *>(x + e + 4) = q;
+    float4 p = z4, q = z4;
+    if (ok) {
+        p = *reinterpret_cast<const float4 *>(x + e); q = *reinterpret_cast<const float4 *>(x + e + 4);
+        if (ra) {
+            const float4 a0 = *reinterpret_cast<const float4 *>(ra + e), a1 = *reinterpret_cast<const float4 *>(ra + e + 4);
+            const float4 c0 = *reinterpret_cast<const float4 *>(rb + e), c1 = *reinterpret_cast<const float4 *>(rb + e + 4);
+            p.x = __fadd_rn(__fadd_rn(a0.x, c0.x), p.x); p.y = __fadd_rn(__fadd_rn(a0.y, c0.y), p.y); p.z = __fadd_rn(__fadd_rn(a0.z, c0.z), p.z); p.w = __fadd_rn(__fadd_rn(a0.w, c0.w), p.w);
+            q.x = __fadd_rn(__fadd_rn(a1.x, c1.x), q.x); q.y = __fadd_rn(__fadd_rn(a1.y, c1.y), q.y); q.z = __fadd_rn(__fadd_rn(a1.z, c1.z), q.z); q.w = __fadd_rn(__fadd_rn(a1.w, c1.w), q.w);
+            *reinterpret_cast<float4 *>(x + e) = p; *reinterpret_cast<float4 *>(x + e + 4) = q;
+        }
     }
     float v[8] = { p.x, p.y, p.z, p.w, q.x, q.y, q.z, q.w };
     auto cluster_total = [&](double t, int slot) -> double {
@@ -237,22 +243,22 @@ __global__ void __launch_bounds__(LNC_THREADS) layernorm_q_cluster_kernel(float 
     };
     double s = 0.0;
 #pragma unroll
-    for (int i = 0; i < 8; i++) s += (double) v[i];
+    for (int i = 0; i < 8; i++) s += (double) v[i];                   // idle lanes hold zeros
     const float mean = (float) (cluster_total(s, 0) / n);
     double s2 = 0.0;
 #pragma unroll
-    for (int i = 0; i < 8; i++) { v[i] = __fsub_rn(v[i], mean); s2 += (double) __fmul_rn(v[i], v[i]); }
+    for (int i = 0; i < 8; i++) { v[i] = __fsub_rn(v[i], mean); if (ok) s2 += (double) __fmul_rn(v[i], v[i]); }
     const float scale = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn((float) (cluster_total(s2, 1) / n), 1e-5f)));
     float y[8];
     const float gg[8] = { ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w }, bv[8] = { ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w };
 #pragma unroll
-    for (int i = 0; i < 8; i++) y[i] = __fadd_rn(__fmul_rn(__fmul_rn(v[i], scale), gg[i]), bv[i]);
-    quantize_chunk8<ATYPE>(y, lane, A1, 0, e);
+    for (int i = 0; i < 8; i++) y[i] = ok ? __fadd_rn(__fmul_rn(__fmul_rn(v[i], scale), gg[i]), bv[i]) : 0.f;
+    quantize_chunk8<ATYPE>(y, lane, A1, 0, e, ok);
     if (has2) {
         const float g2v[8] = { ha.x, ha.y, ha.z, ha.w, hb.x, hb.y, hb.z, hb.w }, b2v[8] = { ca.x, ca.y, ca.z, ca.w, cb.x, cb.y, cb.z, cb.w };
 #pragma unroll
-        for (int i = 0; i < 8; i++) y[i] = __fadd_rn(__fmul_rn(__fmul_rn(v[i], scale), g2v[i]), b2v[i]);
-        quantize_chunk8<ATYPE>(y, lane, A2, 0, e);
+        for (int i = 0; i < 8; i++) y[i] = ok ? __fadd_rn(__fmul_rn(__fmul_rn(v[i], scale), g2v[i]), b2v[i]) : 0.f;
+        quantize_chunk8<ATYPE>(y, lane, A2, 0, e, ok);
     }
     cluster_sync_all();                                               // nobody leaves while a peer may still read its `part`
     trace_end(trace);
@@ -264,10 +270,11 @@ void launch_layernorm_q(float * x, int64_t x_stride, const float * ra, const flo
     if (rows <= 0) return;
     const ActQ a2 = A2 ? *A2 : *A1;
     B200_ASSERT(!A2 || A2->type == A1->type);
-    if (rows == 1 && n % (LNC_THREADS * 8) == 0 && n / (LNC_THREADS * 8) <= 8 && !getenv("B200_LN_NOCLUSTER")) {
+    const int qblk = A1->type == T_Q8_K ? 256 : 32;                  // whole quantisation blocks per row: idle lanes come in whole blocks
+    if (rows == 1 && n % qblk == 0 && (n + LNC_THREADS * 8 - 1) / (LNC_THREADS * 8) <= 8 && !getenv("B200_LN_NOCLUSTER")) {
         unsigned long long * tr = b200_trace_slot("layernorm_q");
         cudaLaunchConfig_t cfg{};
-        cfg.gridDim = dim3((unsigned) (n / (LNC_THREADS * 8))); cfg.blockDim = dim3(LNC_THREADS); cfg.stream = stream;
+        cfg.gridDim = dim3((unsigned) ((n + LNC_THREADS * 8 - 1) / (LNC_THREADS * 8))); cfg.blockDim = dim3(LNC_THREADS); cfg.stream = stream;
         cudaLaunchAttribute attr[2];
         attr[0].id = cudaLaunchAttributeClusterDimension; attr[0].val.clusterDim.x = cfg.gridDim.x; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
         attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[1].val.programmaticStreamSerializationAllowed = 1;
