@@ -97,6 +97,10 @@ int    b200_mul_mat_vec_fused(const b200_weight * w, const float * x_dev, const 
  * libfalcon.cpp:2389-2394).  a_out must have K == rows of w and the activation type of the next weight.
  * returns 0 if the type / shape is not covered (rows % 256 != 0, or not Q4_K / Q4_0). */
 int    b200_mul_mat_vec_q_chain(const b200_weight * w, const b200_actq * a_in, float * y_dev, int epilogue, b200_actq * a_out);
+/* fp32 -> weight blocks in the FILE layout (18 B per 32 for Q4_0, 144 B per 256 for Q4_K) on the device, bit for bit what
+ * quantize_row_q4_0_reference (ggml.c:927-962) / quantize_row_q4_K_reference (k_quants.c:542-605) write.
+ * Returns 0 for a type without a device quantiser (quantise on the host then), 1 on success. */
+int    b200_quantize_weights(int ggml_type, const float * x_dev, void * blocks_dev, int64_t n_elems);
 int    b200_mmv_max_n(void);
 /* the GEMM half alone, on fp16 activations x[n][k] already on the device (what b200_mul_mat does after quantising):
  * impl 1 = tcgen05 tensor-core kernel (returns 0 if the shape is not covered: N > 512 or K % 64 != 0),

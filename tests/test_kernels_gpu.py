@@ -372,3 +372,20 @@ def test_full_size_gemm_tensor_core_vs_cuda_core(gpu, K, M, N):
     grow = (K / 8192.0) ** 0.5
     assert np.abs(a - b).max() <= 1e-4 * grow * scale, (float(np.abs(a - b).max()), scale)
     assert np.median(np.abs(a - b)) <= 5e-6 * grow * scale, (float(np.median(np.abs(a - b))), scale)
+
+
+@pytest.mark.parametrize("t", [po.Q4_0, po.Q4_K])
+def test_device_weight_quantiser_bit_exact(gpu, orc, t):
+    """b200_quantize_weights writes the reference quantiser's blocks bit for bit (ggml.c:927-962, k_quants.c:542-605):
+    normal, tiny, huge, zero, constant, one-sided and the reference test's 0.1 + 2 cos(i) data (tests/test-quantize-fns.cpp:26-32)"""
+    K, rng = 4096, np.random.default_rng(t)
+    rows = [rng.standard_normal(K), 1e-8 * rng.standard_normal(K), 1e8 * rng.standard_normal(K), np.zeros(K), np.full(K, 0.37),
+            np.abs(rng.standard_normal(K)), -np.abs(rng.standard_normal(K)), 0.1 + 2.0 * np.cos(np.arange(K)),
+            0.02 * rng.standard_normal(K), rng.standard_normal(K) * (rng.random(K) < 0.05)]
+    w = np.stack(rows).astype(np.float32)
+    want = orc.quantize(t, w)
+    xd, out = gpu.DevBuf(src=w), gpu.DevBuf(want.nbytes)
+    assert gpu.lib().b200_quantize_weights(t, xd.ptr, out.ptr, w.size) == 1
+    got = out.download(np.uint8, want.shape)
+    assert np.array_equal(got, want), int((got != want).sum())
+    assert gpu.lib().b200_quantize_weights(po.Q6_K, xd.ptr, out.ptr, w.size) == 0       # no device quantiser for this type yet
