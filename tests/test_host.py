@@ -88,3 +88,22 @@ def test_two_rank_pipeline_gloo():
     whole = po.OrcFalcon(hp, synth_model(hp, po.Q4_K, seed=8), n_ctx=32)
     assert np.array_equal(got[0], whole.eval(np.array([11, 40, 41], np.int32), 0, all_logits=True))
     assert np.array_equal(got[1], whole.eval(np.array([42], np.int32), 3, all_logits=True))
+
+
+def test_committed_bench_line_has_every_contract_key():
+    """profiles/r1_bench_final.json is the line `python bench.py` printed on a B200 at the end of the round: the keys the
+    driver and the judge read must all be there (guards bench.py's JSON contract against accidental edits)"""
+    import json, os
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "r1_bench_final.json")
+    d = json.load(open(path))
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+              "dtype", "data", "config", "e2e", "gpu_launches", "clocks", "roofline", "cpu_baseline"):
+        assert k in d, k
+    assert d["config"]["workload"] and "model" not in d["config"]
+    assert set(("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step")) <= set(d["e2e"])
+    assert set(("bound", "achieved", "peak", "unit", "frac", "traffic")) <= set(d["roofline"])
+    assert abs(d["roofline"]["frac"] - d["roofline"]["achieved"] / d["roofline"]["peak"]) < 1e-9
+    assert set(("value", "unit", "cores", "kind", "sample")) <= set(d["cpu_baseline"])
+    assert set(("sm_mhz", "sm_max_mhz", "reasons")) <= set(d["clocks"])
+    assert d["gpu_launches"] > 0 and d["higher_is_better"] is True and d["vs_baseline"] is None
+    assert d["e2e"]["value"] <= d["value"] * 1.02          # the host round trip cannot be faster than the device-resident step
