@@ -178,3 +178,24 @@ def test_greedy_generation_on_device_equals_host_argmax_loop(gpu):
         host.append(tok)
     assert dev.tolist() == host
     a.free(); b.free()
+
+
+def test_eval_rejects_out_of_range_requests(gpu):
+    """the reference asserts on these (libfalcon.cpp:2031-2040: N > 0, n_past + N <= n_ctx); the C ABI returns non-zero before
+    any kernel is launched, and a valid eval afterwards is unaffected"""
+    hp = dict(TINY_40B)
+    f = gpu.Falcon(hp, n_ctx=16, n_batch=4)
+    f.set_tensors(synth_model(hp, po.Q4_K, seed=9))
+    for toks, n_past in ((np.zeros(0, np.int32), 0),            # empty batch
+                         (np.arange(5, dtype=np.int32) + 20, 0),    # more tokens than n_batch
+                         (np.array([11, 12], np.int32), 15),        # runs past n_ctx
+                         (np.array([11], np.int32), 16)):           # starts at n_ctx
+        with pytest.raises(RuntimeError):
+            f.eval(toks, n_past)
+    with pytest.raises(RuntimeError):
+        f.generate_greedy(11, 10, 7)                                # 10 + 7 > n_ctx
+    a = f.eval(np.array([11, 12, 13], np.int32), 0)
+    assert np.isfinite(a).all()
+    b = f.eval(np.array([14], np.int32), 15)                        # the last slot of the context is usable
+    assert np.isfinite(b).all()
+    f.free()
