@@ -18,11 +18,12 @@ PART_A = ["b200_event_create", "b200_event_destroy", "b200_event_record", "b200_
           "b200_memcpy_d2h", "b200_memset", "b200_host_malloc", "b200_host_free", "b200_weight_upload", "b200_weight_random",
           "b200_weight_free", "b200_weight_device_bytes", "b200_dequantize_rows", "b200_actq_alloc", "b200_actq_free",
           "b200_quantize_act", "b200_actq_download", "b200_mul_mat", "b200_mul_mat_f16", "b200_mul_mat_vec_fused", "b200_mul_mat_vec_q", "b200_mul_mat_vec_q_chain", "b200_quantize_weights", "b200_mmv_max_n", "b200_layernorm",
-          "b200_gelu", "b200_add", "b200_rope_neox", "b200_attention"]
+          "b200_gelu", "b200_add", "b200_rope_neox", "b200_attention", "b200_layernorm_q", "b200_attention_decode"]
 PART_B = ["b200_falcon_create", "b200_falcon_set_tensor", "b200_falcon_set_tensor_random", "b200_falcon_load_ggcc",
           "b200_ggcc_read_hparams", "b200_falcon_free", "b200_falcon_weight_bytes", "b200_nccl_unique_id",
           "b200_falcon_init_pipeline", "b200_falcon_eval", "b200_falcon_decode_dev", "b200_falcon_logits_dev", "b200_falcon_generate_greedy",
-          "b200_falcon_last_launches", "b200_falcon_last_ms", "b200_falcon_stream", "b200_falcon_profile_matvec"]
+          "b200_falcon_last_launches", "b200_falcon_last_ms", "b200_falcon_stream", "b200_falcon_profile_matvec",
+          "b200_falcon_kv_read", "b200_falcon_kv_write", "b200_falcon_kv_fill_random"]
 
 
 def build(verbose=False):
@@ -57,12 +58,16 @@ def lib():
             "b200_layernorm": (None, [vp, i64, vp, vp, vp, i64, i32, i32]), "b200_gelu": (None, [vp, vp, i64]), "b200_add": (None, [vp, vp, vp, i64]),
             "b200_rope_neox": (None, [vp, i32, i32, i32, i64, i32, i32, i32, f32, i32]),
             "b200_attention": (None, [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32]),
+            "b200_layernorm_q": (None, [vp, i64, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32]),
+            "b200_attention_decode": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]),
+            "b200_falcon_kv_read": (i32, [vp, i32, i32, i32, vp, vp]), "b200_falcon_kv_write": (i32, [vp, i32, i32, i32, vp, vp]),
+            "b200_falcon_kv_fill_random": (i32, [vp, i32, i32, C.c_uint64]),
             "b200_falcon_create": (vp, [vp]), "b200_falcon_set_tensor": (None, [vp, C.c_char_p, i32, i32, vp, vp]),
             "b200_falcon_set_tensor_random": (None, [vp, C.c_char_p, i32, C.c_uint64]),
             "b200_falcon_load_ggcc": (i32, [vp, C.c_char_p]), "b200_ggcc_read_hparams": (i32, [C.c_char_p, vp]),
             "b200_falcon_free": (None, [vp]), "b200_falcon_weight_bytes": (sz, [vp]),
             "b200_nccl_unique_id": (None, [vp]), "b200_falcon_init_pipeline": (None, [vp, vp]),
-            "b200_falcon_eval": (i32, [vp, vp, i32, i32, i32, vp, i32]), "b200_falcon_decode_dev": (None, [vp, vp, i32, i32]), "b200_falcon_generate_greedy": (i32, [vp, i32, i32, i32, i32, vp]),
+            "b200_falcon_eval": (i32, [vp, vp, i32, i32, i32, vp, i32]), "b200_falcon_decode_dev": (i32, [vp, vp, i32, i32]), "b200_falcon_generate_greedy": (i32, [vp, i32, i32, i32, i32, vp]),
             "b200_falcon_logits_dev": (vp, [vp]), "b200_falcon_last_launches": (i32, [vp]), "b200_falcon_last_ms": (f32, [vp]),
             "b200_falcon_stream": (vp, [vp]), "b200_falcon_profile_matvec": (f32, [vp, i32, vp, vp]),
         }
@@ -261,7 +266,25 @@ class Falcon:
         return out
 
     def decode_dev(self, token_dev_ptr, n_past, n_ctx_rope=0):
-        self.L.b200_falcon_decode_dev(self.h, token_dev_ptr, n_past, n_ctx_rope)
+        if self.L.b200_falcon_decode_dev(self.h, token_dev_ptr, n_past, n_ctx_rope) != 0:
+            raise RuntimeError("b200_falcon_decode_dev: n_past %d outside [0, n_ctx)" % n_past)
+
+    def kv_read(self, layer, pos, n):
+        """-> (K, V) rows [pos, pos + n) of `layer`, each float32 [n][n_head_kv * head_dim]"""
+        w = self.hp["n_head_kv"] * (self.hp["n_embd"] // self.hp["n_head"])
+        k, v = np.empty((n, w), np.float32), np.empty((n, w), np.float32)
+        if self.L.b200_falcon_kv_read(self.h, layer, pos, n, _np_ptr(k), _np_ptr(v)) != 0:
+            raise RuntimeError("b200_falcon_kv_read: bad layer / range")
+        return k, v
+
+    def kv_write(self, layer, pos, k, v):
+        k, v = np.ascontiguousarray(k, np.float32), np.ascontiguousarray(v, np.float32)
+        if self.L.b200_falcon_kv_write(self.h, layer, pos, k.shape[0], _np_ptr(k), _np_ptr(v)) != 0:
+            raise RuntimeError("b200_falcon_kv_write: bad layer / range")
+
+    def kv_fill_random(self, pos, n, seed=1):
+        if self.L.b200_falcon_kv_fill_random(self.h, pos, n, seed) != 0:
+            raise RuntimeError("b200_falcon_kv_fill_random: bad range")
 
     def logits_dev(self):
         return self.L.b200_falcon_logits_dev(self.h)

@@ -215,4 +215,30 @@ void b200_attention(float * qkv, float * kc, float * vc, float * out, int n_head
     }
 }
 
+// the decode step's LayerNorm node exactly as the engine launches it (cluster kernel for one row of <= 8192 values, register
+// kernel otherwise): [x = (ra + rb) + x] ; a1 = Q(norm(x) * g1 + b1) ; a2 = Q(norm(x) * g2 + b2) (a2 optional)
+void b200_layernorm_q(float * x, int64_t x_stride, const float * ra, const float * rb, const float * g1, const float * b1, b200_actq * a1,
+                      const float * g2, const float * b2, b200_actq * a2, int n, int rows) {
+    ActQ A1 = a1->A; A1.N = rows;
+    ActQ A2{}; if (a2) { A2 = a2->A; A2.N = rows; }
+    launch_layernorm_q(x, x_stride, ra, rb, x_stride, g1, b1, &A1, g2, b2, a2 ? &A2 : nullptr, n, rows, g_stream);
+}
+// the decode step's attention node as the engine launches it: RoPE + KV append, split-KV scores / values kernels, and the output row
+// also quantised for the wo mat-mul -- by the attention combine step when the Q8 blocks fit the head groups (returns 1), else by
+// quantize_act (returns 0); the results are the same either way
+int b200_attention_decode(float * qkv, float * kc, float * vc, float * out, int n_head, int n_head_kv, int head_dim, int n_past, int n_ctx,
+                          int n_ctx_rope, b200_actq * qout) {
+    AttnParams p = { n_head, n_head_kv, head_dim, 1, n_past, nullptr, n_ctx, (int64_t) (n_head + 2 * n_head_kv) * head_dim, nullptr, nullptr };
+    launch_rope_kv_append(qkv, kc, vc, p, rope_theta_scale_host(head_dim, n_ctx_rope ? n_ctx_rope : n_ctx, 1, 2.0f, 0), g_stream);
+    const size_t sb = attention_scratch_bytes(p);
+    float * sc = sb ? (float *) scratch(sb) : nullptr;
+    if (sc) B200_CUDA_CHECK(cudaMemsetAsync(sc, 0, 4096, g_stream));
+    ActQ Q{}; if (qout) { Q = qout->A; Q.N = 1; }
+    const bool fold = qout && sc && head_dim == 64 && (Q.type != T_Q8_K || (n_head / n_head_kv) % 4 == 0);
+    if (fold) p.qout = &Q;
+    launch_attention(qkv, kc, vc, out, (int64_t) n_head * head_dim, p, sc, g_stream);
+    if (qout && !fold) launch_quantize_act(out, (int64_t) n_head * head_dim, Q, g_stream);
+    return fold ? 1 : 0;
+}
+
 } // extern "C"

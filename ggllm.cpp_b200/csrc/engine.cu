@@ -14,7 +14,6 @@
 //     boundary with a single ncclSend/ncclRecv on the compute stream (replaces the row-split tensor parallelism of
 //     ggml-cuda.cu:2594-2601, 2719-2725, 2779-2788)
 #include "kernels.h"
-#include "ln_tail.cuh"
 #include "../../include/ggml_b200.h"
 #include <nccl.h>
 #include <dlfcn.h>
@@ -80,9 +79,7 @@ struct b200_falcon {
     // decode graphs: [0] = device-resident step, [1] = host-to-host step (token H2D + logits D2H nodes inside)
     cudaGraphExec_t graph[2] = { nullptr, nullptr }; float graph_theta[2] = { -1.f, -1.f }; int graph_launches = 0;
     int act_type = -1;
-    unsigned * ln_ctr = nullptr;                // arrival counter of the LayerNorm tail (last CTA of wo)
     unsigned * q_ctr = nullptr;                 // chunk counters of the quantise-on-completion epilogue (ffn_up -> ffn_down)
-    void * mega_layers = nullptr; unsigned * mega_flags = nullptr; int mega_state = 0;     // persistent decode kernel: 0 = not decided, 1 = on, -1 = off
     ncclComm_t comm = nullptr;
     int launches = 0; float last_ms = 0.f;
     size_t weight_bytes = 0;
@@ -144,6 +141,15 @@ static void expected_shape(const b200_falcon * f, const Slot & s, int64_t & K, i
     }
 }
 
+// the instantiated decode graphs bake in device pointers (weights, LayerNorm vectors, the pinned logits buffer):
+// whenever one of those is replaced the graphs are dropped and rebuilt by the next decode
+static void invalidate_graphs(b200_falcon * f) {
+    for (int i = 0; i < 2; i++) if (f->graph[i]) {
+        B200_CUDA_CHECK(cudaStreamSynchronize(f->s_main));
+        B200_CUDA_CHECK(cudaGraphExecDestroy(f->graph[i])); f->graph[i] = nullptr; f->graph_theta[i] = -1.f;
+    }
+}
+
 static void note_act_type(b200_falcon * f, int wtype) {
     const int at = act_type_for(wtype);
     if (at < 0) return;                           // f16 / f32 weights: no quantised activations
@@ -191,7 +197,6 @@ static void ensure_actq(b200_falcon * f) {
         const size_t sb = attention_scratch_bytes(ap);
         if (sb) { B200_CUDA_CHECK(cudaMalloc(&f->attn_dec_scratch, sb)); B200_CUDA_CHECK(cudaMemset(f->attn_dec_scratch, 0, sb)); }
     }
-    if (!f->ln_ctr) { B200_CUDA_CHECK(cudaMalloc(&f->ln_ctr, sizeof(unsigned))); B200_CUDA_CHECK(cudaMemset(f->ln_ctr, 0, sizeof(unsigned))); }
     if (!f->q_ctr) { B200_CUDA_CHECK(cudaMalloc(&f->q_ctr, (size_t) (f->FF / 256 + 1) * sizeof(unsigned))); B200_CUDA_CHECK(cudaMemset(f->q_ctr, 0, (size_t) (f->FF / 256 + 1) * sizeof(unsigned))); }
     if (f->actq_mem || f->act_type < 0) return;
     const int at = f->act_type; const int NB = f->hp.n_batch > 0 ? f->hp.n_batch : 1;
@@ -216,8 +221,9 @@ static void place_tensor(b200_falcon * f, const Slot & s, int type, const void *
     if ((s.kind == 1 || s.kind == 2 || s.kind == 3) && !f->last) return;
     int64_t K, M; expected_shape(f, s, K, M);
     cudaStream_t st = f->s_main;
+    invalidate_graphs(f);
     auto matrix = [&](WPlanes & W) {
-        if (W.p[0]) wplanes_free(W);
+        if (W.p[0]) { if (s.kind != 0) f->weight_bytes -= algorithmic_bytes(W.type, W.K, W.M); wplanes_free(W); }
         if (random) wplanes_alloc_random(W, type, (int) K, (int) M, seed, st);
         else wplanes_upload(W, type, (int) K, (int) M, host_data, st);
         if (s.kind != 0) { f->weight_bytes += algorithmic_bytes(type, K, M); note_act_type(f, type); }
@@ -325,7 +331,7 @@ void b200_falcon_free(b200_falcon * f) {
     cudaFree(f->lnf_g); cudaFree(f->lnf_b); cudaFree(f->k_cache); cudaFree(f->v_cache);
     cudaFree(f->inp); cudaFree(f->qkv); cudaFree(f->att); cudaFree(f->ao); cudaFree(f->up); cudaFree(f->dn); cudaFree(f->logits);
     cudaFree(f->attn_scratch); cudaFree(f->actq_mem); cudaFree(f->xh_a); cudaFree(f->xh_b); cudaFree(f->gemm_ws_a); cudaFree(f->gemm_ws_b);
-    cudaFree(f->tokens_dev); cudaFree(f->n_past_dev); cudaFree(f->mega_layers); cudaFree(f->mega_flags); cudaFree(f->q_ctr); cudaFree(f->ln_ctr); cudaFree(f->attn_dec_scratch);
+    cudaFree(f->tokens_dev); cudaFree(f->n_past_dev); cudaFree(f->q_ctr); cudaFree(f->attn_dec_scratch);
     cudaFreeHost(f->tokens_h); cudaFreeHost(f->n_past_h); cudaFreeHost(f->logits_h);
     for (int i = 0; i < 2; i++) if (f->graph[i]) cudaGraphExecDestroy(f->graph[i]);
     if (f->comm) nccl().CommDestroy(f->comm);
@@ -356,48 +362,6 @@ static void mm(b200_falcon * f, const WPlanes & W, const ActQ & A, int N, float 
 // residual adds + LayerNorm + activation quantisation in the prologue of qkv / ffn_up / lm_head (FastX mode 2),
 // activation quantisation in the prologue of wo / ffn_down (mode 1), GELU in ffn_up's epilogue.  6 kernels per layer:
 //   s_main: qkv -> rope+kv append -> attention -> wo          s_mlp: ffn_up(+GELU) -> ffn_down
-// One persistent kernel for all local layers of a decode step (decode_mega.cu) when every layer has the shape / type it covers
-static bool mega_decode_ok(b200_falcon * f) {
-    if (f->mega_state) return f->mega_state > 0;
-    f->mega_state = -1;
-    // opt-in (B200_MEGA=1): correct and tested, but slower than the per-node path so far
-    if (!getenv("B200_MEGA") || f->NL == 0 || f->act_type < 0) return false;
-    const int t = f->layers[0].wqkv.type;
-    for (const auto & L : f->layers) if (L.wqkv.type != t || L.wo.type != t || L.up.type != t || L.down.type != t) return false;
-    int dev, nsm; B200_CUDA_CHECK(cudaGetDevice(&dev)); B200_CUDA_CHECK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
-    if (!decode_mega_supports(t, f->E, f->FF, f->H, f->HKV, f->D, f->hp.n_ctx, nsm)) return false;
-    const size_t lb = decode_mega_layer_bytes();
-    std::vector<uint8_t> host(lb * f->NL);
-    for (int l = 0; l < f->NL; l++) {
-        const Layer & L = f->layers[l];
-        const size_t kvoff = (size_t) l * f->hp.n_ctx * f->HKV * f->D;
-        const bool dual = f->hp.falcon_type == 40;
-        decode_mega_fill_layer(host.data() + lb * l, L.wqkv, L.up, L.down, L.wo, dual ? L.ln_attn_g : L.ln_mlp_g, dual ? L.ln_attn_b : L.ln_mlp_b,
-                               L.ln_mlp_g, L.ln_mlp_b, f->k_cache + kvoff, f->v_cache + kvoff);
-    }
-    B200_CUDA_CHECK(cudaMalloc(&f->mega_layers, host.size()));
-    B200_CUDA_CHECK(cudaMemcpy(f->mega_layers, host.data(), host.size(), cudaMemcpyHostToDevice));
-    B200_CUDA_CHECK(cudaMalloc(&f->mega_flags, (size_t) f->NL * 4 * sizeof(unsigned)));
-    f->mega_state = 1;
-    return true;
-}
-// embedding (or the previous rank's row) -> persistent layer kernel -> final LayerNorm + lm_head (or send to the next rank)
-static void enqueue_decode_mega(b200_falcon * f, int n_past, float theta_scale, bool graph_mode) {
-    cudaStream_t sa = f->s_main;
-    const int E = f->E;
-    ensure_actq(f);
-    ActQ xf = f->xf; xf.N = 1;
-    if (f->first) { launch_dequant_rows(f->tok_emb, f->tokens_dev, 1, f->inp, E, sa); f->launches++; }
-    else B200_NCCL_CHECK(nccl().Recv(f->inp, (size_t) E, ncclFloat, f->hp.rank - 1, f->comm, sa));
-    launch_decode_mega(f->layers[0].wqkv.type, f->mega_layers, f->NL, f->inp, f->qkv, f->up, f->att, f->mega_flags,
-                       graph_mode ? f->n_past_dev : nullptr, n_past, f->hp.n_ctx, E, f->FF, f->H, f->HKV, f->D, f->hp.falcon_type == 40, theta_scale, sa);
-    f->launches++;
-    if (f->last) {
-        launch_layernorm_q(f->inp, E, nullptr, nullptr, 0, f->lnf_g, f->lnf_b, &xf, nullptr, nullptr, nullptr, E, 1, sa);      // :2422-2431
-        launch_mmv(f->lm_head, xf, f->logits, f->V, { EPI_NONE, nullptr, nullptr }, sa); f->launches += 2;                     // :2440
-    } else B200_NCCL_CHECK(nccl().Send(f->inp, (size_t) E, ncclFloat, f->hp.rank + 1, f->comm, sa));
-}
-
 static bool fused_decode_ok(const b200_falcon * f) {
     if (getenv("B200_NO_FUSED_DECODE")) return false;
     for (const auto & L : f->layers)
@@ -413,22 +377,19 @@ static void enqueue_decode_fused(b200_falcon * f, int n_past, float theta_scale,
     ActQ xa = f->xa, xm = f->xm, xf = f->xf, xup = f->xup, xatt = f->xatt; xa.N = xm.N = xf.N = xup.N = xatt.N = 1;
     if (f->first) { launch_dequant_rows(f->tok_emb, f->tokens_dev, 1, f->inp, E, sa); f->launches++; }
     else B200_NCCL_CHECK(nccl().Recv(f->inp, (size_t) E, ncclFloat, f->hp.rank - 1, f->comm, sa));
-    const MmvEpilogue none = { EPI_NONE, nullptr, nullptr, nullptr, nullptr, nullptr };
+    const MmvEpilogue none = { EPI_NONE, nullptr, nullptr, nullptr, nullptr };
     // ffn_up applies GELU and, chunk by chunk as CTAs finish, quantises its output row for ffn_down (no INIT pass, no prologue work there)
-    const MmvEpilogue gelu = { EPI_GELU, nullptr, nullptr, &xup, f->q_ctr, nullptr };
+    const MmvEpilogue gelu = { EPI_GELU, nullptr, nullptr, &xup, f->q_ctr };
     // debugging aid for timing experiments only (results are wrong when anything is skipped): B200_DBG_SKIP=ln,qkv,attn,up,down,wo
     const char * dbg = getenv("B200_DBG_SKIP");
     auto skip = [&](const char * what) { return dbg && strstr(dbg, what) != nullptr; };
     // All four mat-vecs of a layer go back to back on ONE stream (each is launched with programmatic dependent launch,
     // so its weight prefetch overlaps the previous one's tail); the small attention kernels run beside ffn_up on the
     // second stream:   s_main: LN -> qkv -> ffn_up(+GELU) -> ffn_down -> wo        s_mlp: rope+kv append -> attention
-    // The residual adds that close layer l and the LayerNorm(s) of layer l+1 (or the final one) are run by the last CTA
-    // of layer l's wo mat-vec (ln_tail.cuh); only the first local layer needs the stand-alone kernel.
-    const bool tail = E % 256 == 0 && getenv("B200_LN_TAIL") && !dbg;       // opt-in: correct, but the single-CTA tail is still slower than the kernel it replaces
     for (int l = 0; l < f->NL; l++) {
         const Layer & L = f->layers[l];
         const float * ra = l > 0 ? f->dn : nullptr, * rb = l > 0 ? f->ao : nullptr;
-        if (skip("ln") || (tail && l > 0)) {}
+        if (skip("ln")) {}
         else if (dual) launch_layernorm_q(f->inp, E, ra, rb, E, L.ln_attn_g, L.ln_attn_b, &xa, L.ln_mlp_g, L.ln_mlp_b, &xm, E, 1, sa);
         else      launch_layernorm_q(f->inp, E, ra, rb, E, L.ln_mlp_g, L.ln_mlp_b, &xm, nullptr, nullptr, nullptr, E, 1, sa);
         if (!skip("qkv")) launch_mmv(L.wqkv, dual ? xa : xm, f->qkv, f->QKV, none, sa);                         // libfalcon.cpp:2192
@@ -449,23 +410,12 @@ static void enqueue_decode_fused(b200_falcon * f, int n_past, float theta_scale,
         if (!skip("up")) launch_mmv(L.up, xm, f->up, f->FF, gelu, sa);                                           // :2389-2392
         if (!skip("down")) launch_mmv(L.down, xup, f->dn, E, none, sa);                                         // :2394
         B200_CUDA_CHECK(cudaStreamWaitEvent(sa, f->e_join, 0));
-        LnTail lt{}; MmvEpilogue wo_epi = none;
-        if (tail && (l + 1 < f->NL || f->last)) {
-            lt.x = f->inp; lt.ra = f->dn; lt.n = E; lt.ctr = f->ln_ctr;
-            if (l + 1 < f->NL) {
-                const Layer & Ln = f->layers[l + 1];
-                if (dual) { lt.g1 = Ln.ln_attn_g; lt.b1 = Ln.ln_attn_b; lt.A1 = xa; lt.g2 = Ln.ln_mlp_g; lt.b2 = Ln.ln_mlp_b; lt.A2 = xm; lt.has2 = 1; }
-                else      { lt.g1 = Ln.ln_mlp_g; lt.b1 = Ln.ln_mlp_b; lt.A1 = xm; lt.A2 = xm; lt.has2 = 0; }
-            } else { lt.g1 = f->lnf_g; lt.b1 = f->lnf_b; lt.A1 = xf; lt.A2 = xf; lt.has2 = 0; }                      // :2422-2431
-            wo_epi.ln = &lt;
-        }
-        if (!skip("wo")) launch_mmv(L.wo, xatt, f->ao, E, wo_epi, sa);                                          // :2370
-        f->launches += (tail && l > 0) ? 7 : 8;
+        if (!skip("wo")) launch_mmv(L.wo, xatt, f->ao, E, none, sa);                                          // :2370
+        f->launches += 8;
     }
     if (f->last) {
-        if (!(tail && f->NL > 0))
-            launch_layernorm_q(f->inp, E, f->NL > 0 ? f->dn : nullptr, f->NL > 0 ? f->ao : nullptr, E, f->lnf_g, f->lnf_b, &xf, nullptr, nullptr, nullptr, E, 1, sa);   // :2399-2400, 2422-2431
-        launch_mmv(f->lm_head, xf, f->logits, f->V, none, sa); f->launches += (tail && f->NL > 0) ? 1 : 2;      // :2440
+        launch_layernorm_q(f->inp, E, f->NL > 0 ? f->dn : nullptr, f->NL > 0 ? f->ao : nullptr, E, f->lnf_g, f->lnf_b, &xf, nullptr, nullptr, nullptr, E, 1, sa);   // :2399-2400, 2422-2431
+        launch_mmv(f->lm_head, xf, f->logits, f->V, none, sa); f->launches += 2;      // :2440
     } else {
         if (f->NL > 0) { launch_add3(f->dn, f->ao, f->inp, f->inp, E, sa); f->launches++; }
         B200_NCCL_CHECK(nccl().Send(f->inp, (size_t) E, ncclFloat, f->hp.rank + 1, f->comm, sa));
@@ -474,7 +424,6 @@ static void enqueue_decode_fused(b200_falcon * f, int n_past, float theta_scale,
 
 // Enqueue one eval of N tokens on (s_main, s_mlp).  Device scalars carry n_past when `graph_mode`.
 static void enqueue_eval(b200_falcon * f, int N, int n_past, float theta_scale, bool graph_mode, int logits_rows_from) {
-    if (N == 1 && mega_decode_ok(f)) { enqueue_decode_mega(f, n_past, theta_scale, graph_mode); return; }
     if (N == 1 && fused_decode_ok(f)) { enqueue_decode_fused(f, n_past, theta_scale, graph_mode); return; }
     cudaStream_t sa = f->s_main, sb = f->s_mlp;
     const int E = f->E, FF = f->FF;
@@ -560,7 +509,11 @@ static void build_decode_graph(b200_falcon * f, int which, float theta_scale) {
 extern "C" {
 
 int b200_falcon_eval(b200_falcon * f, const int32_t * tokens, int n_tokens, int n_past, int n_ctx_rope, float * logits, int all_logits) {
-    if (n_tokens <= 0 || n_past + n_tokens > f->hp.n_ctx || n_tokens > (f->hp.n_batch > 0 ? f->hp.n_batch : 1)) return 1;
+    if (n_tokens <= 0 || n_past < 0 || n_past + n_tokens > f->hp.n_ctx || n_tokens > (f->hp.n_batch > 0 ? f->hp.n_batch : 1)) return 1;
+    if (f->first) {                                  // token ids index the embedding matrix: reject anything outside it (ggml_get_rows asserts, ggml.c:11990)
+        if (!tokens) return 1;
+        for (int i = 0; i < n_tokens; i++) if (tokens[i] < 0 || tokens[i] >= f->V) return 2;
+    }
     const float theta = rope_theta_scale_host(f->D, n_ctx_rope ? n_ctx_rope : f->hp.n_ctx, 1, 2.0f, 0);         // libfalcon.cpp:2229-2234
     if (n_tokens == 1) {
         f->tokens_h[0] = tokens ? tokens[0] : 0; *f->n_past_h = n_past;
@@ -581,7 +534,10 @@ int b200_falcon_eval(b200_falcon * f, const int32_t * tokens, int n_tokens, int 
         B200_CUDA_CHECK(cudaEventRecord(f->e_t1, f->s_main));
         if (f->last && logits) {
             const size_t nfl = (size_t) (n_tokens - r0) * f->V;
-            if (nfl > f->logits_h_floats) { B200_CUDA_CHECK(cudaFreeHost(f->logits_h)); f->logits_h_floats = nfl; B200_CUDA_CHECK(cudaMallocHost(&f->logits_h, nfl * 4)); }
+            if (nfl > f->logits_h_floats) {          // graph[1] copies its logits row into this buffer: rebuild it around the new one
+                invalidate_graphs(f);
+                B200_CUDA_CHECK(cudaFreeHost(f->logits_h)); f->logits_h_floats = nfl; B200_CUDA_CHECK(cudaMallocHost(&f->logits_h, nfl * 4));
+            }
             B200_CUDA_CHECK(cudaMemcpyAsync(f->logits_h, f->logits, nfl * 4, cudaMemcpyDeviceToHost, f->s_main));
             B200_CUDA_CHECK(cudaStreamSynchronize(f->s_main));
             memcpy(logits, f->logits_h, nfl * 4);
@@ -591,7 +547,8 @@ int b200_falcon_eval(b200_falcon * f, const int32_t * tokens, int n_tokens, int 
     return 0;
 }
 
-void b200_falcon_decode_dev(b200_falcon * f, const int32_t * token_dev, int n_past, int n_ctx_rope) {
+int b200_falcon_decode_dev(b200_falcon * f, const int32_t * token_dev, int n_past, int n_ctx_rope) {
+    if (n_past < 0 || n_past >= f->hp.n_ctx) return 1;                       // the KV append would leave this layer's cache slice
     const float theta = rope_theta_scale_host(f->D, n_ctx_rope ? n_ctx_rope : f->hp.n_ctx, 1, 2.0f, 0);
     if (!f->graph[0] || f->graph_theta[0] != theta) {
         set_i32_kernel<<<1, 1, 0, f->s_main>>>(f->n_past_dev, n_past);
@@ -602,9 +559,10 @@ void b200_falcon_decode_dev(b200_falcon * f, const int32_t * token_dev, int n_pa
     // as a kernel argument, so the host may run ahead by any number of steps)
     set_i32_kernel<<<1, 1, 0, f->s_main>>>(f->n_past_dev, n_past);
     if (f->first && token_dev) B200_CUDA_CHECK(cudaMemcpyAsync(f->tokens_dev, token_dev, 4, cudaMemcpyDeviceToDevice, f->s_main));
-    if (getenv("B200_NO_GRAPH")) { f->launches = 0; enqueue_eval(f, 1, 0, theta, true, 0); return; }   // timing experiments: eager launches
+    if (getenv("B200_NO_GRAPH")) { f->launches = 0; enqueue_eval(f, 1, 0, theta, true, 0); return 0; }   // timing experiments: eager launches
     B200_CUDA_CHECK(cudaGraphLaunch(f->graph[0], f->s_main));
     f->launches = f->graph_launches;
+    return 0;
 }
 const float * b200_falcon_logits_dev(const b200_falcon * f) { return f->logits; }
 
@@ -613,18 +571,51 @@ const float * b200_falcon_logits_dev(const b200_falcon * f) { return f->logits; 
 // so no logits and no token cross PCIe between steps.  First slice of SURVEY 8f-2 (the reference samples on the host from
 // a 260 KB logits row per token, falcon_main.cpp:897-980 with top_k = 1 / temp <= 0 -> llama_sample_token_greedy).
 int b200_falcon_generate_greedy(b200_falcon * f, int32_t first_token, int n_past, int n_steps, int n_ctx_rope, int32_t * tokens_out) {
-    if (!f->first || !f->last || n_steps <= 0 || n_past + n_steps > f->hp.n_ctx) return 1;
+    if (!f->first || !f->last || n_steps <= 0 || n_past < 0 || n_past + n_steps > f->hp.n_ctx || first_token < 0 || first_token >= f->V) return 1;
     int32_t * hist = nullptr;
     B200_CUDA_CHECK(cudaMalloc(&hist, (size_t) n_steps * 4));
     B200_CUDA_CHECK(cudaMemcpyAsync(f->tokens_dev, &first_token, 4, cudaMemcpyHostToDevice, f->s_main));
     B200_CUDA_CHECK(cudaStreamSynchronize(f->s_main));               // first_token is a stack value
     for (int i = 0; i < n_steps; i++) {
-        b200_falcon_decode_dev(f, nullptr, n_past + i, n_ctx_rope);  // token id already in f->tokens_dev
+        if (b200_falcon_decode_dev(f, nullptr, n_past + i, n_ctx_rope) != 0) { B200_CUDA_CHECK(cudaFree(hist)); return 1; }  // token id already in f->tokens_dev
         launch_argmax(f->logits, f->V, f->tokens_dev, hist + i, f->s_main);
     }
     B200_CUDA_CHECK(cudaMemcpyAsync(tokens_out, hist, (size_t) n_steps * 4, cudaMemcpyDeviceToHost, f->s_main));
     B200_CUDA_CHECK(cudaStreamSynchronize(f->s_main));
     B200_CUDA_CHECK(cudaFree(hist));
+    return 0;
+}
+// ---- KV cache access (session state).  The reference serialises its KV cache with the context
+// (falcon_copy_state_data / falcon_set_state_data, libfalcon.cpp:4313-4490: n_tokens x n_embd_kv floats per layer for K and V);
+// here the cache is device-resident [layer][n_ctx][n_head_kv][head_dim] f32 and rows are copied straight out of / into HBM.
+int b200_falcon_kv_read(b200_falcon * f, int layer, int pos, int n, float * k_out, float * v_out) {
+    if (layer < f->hp.layer_first || layer >= f->hp.layer_last || pos < 0 || n < 0 || pos + n > f->hp.n_ctx) return 1;
+    const size_t row = (size_t) f->HKV * f->D, off = ((size_t) (layer - f->hp.layer_first) * f->hp.n_ctx + pos) * row;
+    B200_CUDA_CHECK(cudaStreamSynchronize(f->s_main));
+    if (k_out) B200_CUDA_CHECK(cudaMemcpy(k_out, f->k_cache + off, (size_t) n * row * 4, cudaMemcpyDeviceToHost));
+    if (v_out) B200_CUDA_CHECK(cudaMemcpy(v_out, f->v_cache + off, (size_t) n * row * 4, cudaMemcpyDeviceToHost));
+    return 0;
+}
+int b200_falcon_kv_write(b200_falcon * f, int layer, int pos, int n, const float * k_in, const float * v_in) {
+    if (layer < f->hp.layer_first || layer >= f->hp.layer_last || pos < 0 || n < 0 || pos + n > f->hp.n_ctx) return 1;
+    const size_t row = (size_t) f->HKV * f->D, off = ((size_t) (layer - f->hp.layer_first) * f->hp.n_ctx + pos) * row;
+    B200_CUDA_CHECK(cudaStreamSynchronize(f->s_main));
+    if (k_in) B200_CUDA_CHECK(cudaMemcpy(f->k_cache + off, k_in, (size_t) n * row * 4, cudaMemcpyHostToDevice));
+    if (v_in) B200_CUDA_CHECK(cudaMemcpy(f->v_cache + off, v_in, (size_t) n * row * 4, cudaMemcpyHostToDevice));
+    return 0;
+}
+// random K / V rows generated on the device for positions [pos, pos + n) of every local layer: pre-fills a long context
+// for throughput runs (BASELINE config 5: decode at 8k context) without evaluating 8k tokens first
+int b200_falcon_kv_fill_random(b200_falcon * f, int pos, int n, uint64_t seed) {
+    if (pos < 0 || n < 0 || pos + n > f->hp.n_ctx) return 1;
+    const size_t row = (size_t) f->HKV * f->D;
+    for (int l = 0; l < f->NL; l++) {
+        const size_t off = ((size_t) l * f->hp.n_ctx + pos) * row;
+        fill_f32_kernel<<<296, 256, 0, f->s_main>>>(f->k_cache + off, (int64_t) ((size_t) n * row), 0.f, 1.f, seed + 2 * l);
+        fill_f32_kernel<<<296, 256, 0, f->s_main>>>(f->v_cache + off, (int64_t) ((size_t) n * row), 0.f, 1.f, seed + 2 * l + 1);
+    }
+    B200_CUDA_CHECK(cudaGetLastError());
+    B200_CUDA_CHECK(cudaStreamSynchronize(f->s_main));
     return 0;
 }
 int b200_falcon_last_launches(const b200_falcon * f) { return f->launches; }

@@ -21,9 +21,7 @@ enum { EPI_NONE = 0, EPI_GELU = 1, EPI_ADD2 = 2 };
 struct MmvEpilogue { int kind; const float * r1; const float * r2;         // ADD2: y = (dot + r1[m]) + r2[m]
     // optional (fast kernel, N == 1, M % 256 == 0): the output row is also quantised for the NEXT mat-mul (its INIT pass,
     // ggml.c:11462-11476) by whichever CTA completes a 256-value chunk; qctr = M / 256 zero-initialised, self-resetting counters
-    const ActQ * qout; unsigned * qctr;
-    // optional (fast kernel, N == 1): the last CTA to finish runs the layer-closing residual adds + next LayerNorm(s) + quantisation
-    const struct LnTail * ln; };
+    const ActQ * qout; unsigned * qctr; };
 void   launch_mmv(const WPlanes & W, const ActQ & A, float * y, int64_t y_stride, MmvEpilogue epi, cudaStream_t stream);
 void   launch_mmv_f(const WPlanes & W, const float * x, int64_t x_stride, int N, float * y, int64_t y_stride, cudaStream_t stream); // f16/f32 weights
 
@@ -40,14 +38,6 @@ struct FastX {
 };
 bool   launch_mmv_fast_x(const WPlanes & W, const FastX & X, float * y, int64_t y_stride, MmvEpilogue e, cudaStream_t stream);
 bool   mmv_fast_supports(int wtype, int K, int mode);
-// decode_mega.cu: every layer of one decode step in a single persistent kernel
-bool   decode_mega_supports(int wtype, int E, int FF, int H, int HKV, int D, int n_ctx, int n_sm);
-size_t decode_mega_layer_bytes();
-void   decode_mega_fill_layer(void * dst_host, const WPlanes & qkv, const WPlanes & up, const WPlanes & down, const WPlanes & wo,
-                              const float * ga, const float * ba, const float * gm, const float * bm, float * kc, float * vc);
-void   launch_decode_mega(int wtype, const void * layers_dev, int n_layer, float * x, float * qkv, float * up, float * att, unsigned * flags,
-                          const int * n_past_dev, int n_past, int n_ctx, int E, int FF, int H, int HKV, int D, int dual, float theta_scale, cudaStream_t stream);
-
 // ---- ops.cu
 void   launch_layernorm(const float * x, int64_t x_stride, const float * g, const float * b, float * y, int64_t y_stride,
                         int n, int rows, cudaStream_t stream);              // y = norm(x)*g + b ; g,b may be null (plain ggml_norm)

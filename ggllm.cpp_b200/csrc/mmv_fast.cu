@@ -50,7 +50,6 @@ __device__ __forceinline__ void mmv_body(const WPlanes & W, const FastX & X, flo
 
     typename T::WR w[D][J];
     ring_fill<TYPE, J, D>(w, wp, row0, row1);                                // weights are in flight before the activation arrives
-    if (epi.ln.ctr && cta == 0) ln_tail_prefetch(epi.ln);
     const L2PF pf = l2pf_of(W, X.l2_dist);
     if (pf.dist > 0 && tid == 0) l2_prefetch_rows(pf, min(row0 + D, row1), min(row0 + D + pf.dist, row1));
 
@@ -172,17 +171,6 @@ __device__ __forceinline__ void mmv_body(const WPlanes & W, const FastX & X, flo
             }
         }
     }
-    if (epi.ln.ctr) {
-        __shared__ int s_last;
-        __threadfence();
-        __syncthreads();
-        if (tid == 0) { const unsigned old = atomicAdd(epi.ln.ctr, 1u); s_last = old == (unsigned) nctas - 1; if (s_last) *epi.ln.ctr = 0; }
-        __syncthreads();
-        if (s_last) {
-            __threadfence();
-            ln_tail_run<NT>(epi.ln, y + (size_t) n * y_stride, red);
-        }
-    }
     trace_end(epi.trace);
 }
 
@@ -246,11 +234,7 @@ static bool launch_type(const WPlanes & W, const FastX & X, float * y, int64_t y
 // returns false if the shape / type is not covered (the caller then uses the generic ring kernel of mmv.cu)
 bool launch_mmv_fast_x(const WPlanes & W, const FastX & X, float * y, int64_t y_stride, MmvEpilogue e, cudaStream_t stream) {
     const char * nm = W.M > 40000 ? "mmv_lmhead" : W.K > 16384 ? "mmv_down" : W.M > 16384 ? "mmv_up" : W.M > 8192 ? "mmv_qkv" : "mmv_wo";
-    Epi epi = { e.kind, e.r1, e.r2, b200_trace_slot(nm), ActQ{}, nullptr, LnTail{} };
-    if (e.ln && e.ln->ctr) {
-        B200_ASSERT(X.N == 1 && e.ln->n == W.M && W.M % 256 == 0 && W.M <= 256 * 8 * 8);
-        epi.ln = *e.ln;
-    }
+    Epi epi = { e.kind, e.r1, e.r2, b200_trace_slot(nm), ActQ{}, nullptr };
     if (e.qout && e.qctr) {
         B200_ASSERT(X.N == 1 && W.M % 256 == 0 && e.qout->K == W.M && (e.qout->type == T_Q8_K || e.qout->type == T_Q8_0));
         epi.qA = *e.qout; epi.qctr = e.qctr;

@@ -1,10 +1,9 @@
-// mmv_fast.cuh -- per-type pieces of the register-resident decode mat-vec (used by mmv_fast.cu and decode_mega.cu)
+// mmv_fast.cuh -- per-type pieces of the register-resident decode mat-vec (used by mmv_fast.cu)
 #pragma once
 #include "kernels.h"
 #include "actquant.cuh"
-#include "ln_tail.cuh"
 
-struct Epi { int kind; const float * r1; const float * r2; unsigned long long * trace; ActQ qA; unsigned * qctr; LnTail ln; };
+struct Epi { int kind; const float * r1; const float * r2; unsigned long long * trace; ActQ qA; unsigned * qctr; };
 
 // Where the activation row comes from (FastX, kernels.h):
 //   mode 0: already quantised (ActQ, written by quantize_act / layernorm_q)
@@ -293,7 +292,7 @@ template <int TYPE> __device__ __forceinline__ typename FX<TYPE>::XR zero_xr() {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// The row loop shared by mmv_fast.cu and decode_mega.cu.  A group of NTG threads (a CTA, or half of one) owns rows
+// The row loop of mmv_fast.cu.  A group of NTG threads (a CTA, or half of one) owns rows
 // [r0, r1) of a matrix; every thread keeps D rows x J pieces of weights in flight in registers (D * J = 8).
 template <int TYPE, int J, int D>
 __device__ __forceinline__ void ring_fill(typename FX<TYPE>::WR (&w)[D][J], const WP (&wp)[J], int r0, int r1) {

@@ -149,7 +149,8 @@ void wplanes_alloc_random(WPlanes & W, int type, int K, int M, uint64_t seed, cu
 // standalone bit-exactness checker.  rows == nullptr means rows 0..nrows-1.
 __global__ void dequant_rows_kernel(WPlanes W, const int32_t * __restrict__ rows, int nrows, float * __restrict__ dst, int64_t dst_stride) {
     const int r = blockIdx.y;
-    const size_t row = rows ? (size_t) rows[r] : (size_t) r;
+    // device-side row ids (token ids fed back by the on-device samplers) cannot be checked by the host: clamp into the matrix
+    const size_t row = rows ? (size_t) min(max(rows[r], 0), W.M - 1) : (size_t) r;
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < W.K; e += gridDim.x * blockDim.x)
         dst[(size_t) r * dst_stride + e] = dequant_elem(W, row, e);
 }

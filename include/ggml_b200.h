@@ -123,6 +123,18 @@ void   b200_rope_neox(float * x_dev, int n_tok, int n_head, int head_dim, int64_
 void   b200_attention(float * qkv_dev, float * k_cache_dev, float * v_cache_dev, float * out_dev,
                       int n_head, int n_head_kv, int head_dim, int n_tok, int n_past, int n_ctx, int n_ctx_rope);
 
+/* ---- the two fused decode-step nodes exactly as the eval path launches them (per-operator parity tests at the real model widths)
+ * [x = (ra + rb) + x, written back when ra != NULL] ; a1 = Q(norm(x) * g1 + b1) ; a2 = Q(norm(x) * g2 + b2) (a2 / g2 / b2 optional):
+ * residual adds (libfalcon.cpp:2399-2400) + LayerNorm(s) (ggml.c:10540-10599, libfalcon.cpp:2166-2185) + the next mat-mul's INIT
+ * pass (ggml.c:11462-11476).  rows == 1 and n <= 8192: thread-block-cluster kernel; otherwise one CTA per row. */
+void   b200_layernorm_q(float * x_dev, int64_t x_stride, const float * ra_dev, const float * rb_dev,
+                        const float * g1_dev, const float * b1_dev, b200_actq * a1,
+                        const float * g2_dev, const float * b2_dev, b200_actq * a2, int n, int rows);
+/* b200_attention for ONE new token with the split-KV decode kernels; qout (optional) also receives the output row quantised for
+ * the wo mat-mul.  Returns 1 when that quantisation ran inside the attention combine step, 0 when it needed its own kernel. */
+int    b200_attention_decode(float * qkv_dev, float * k_cache_dev, float * v_cache_dev, float * out_dev,
+                             int n_head, int n_head_kv, int head_dim, int n_past, int n_ctx, int n_ctx_rope, b200_actq * qout);
+
 /* ========================================= part B: Falcon eval path ====================================== */
 
 typedef struct b200_falcon b200_falcon;
@@ -166,13 +178,20 @@ int           b200_falcon_eval(b200_falcon * f, const int32_t * tokens, int n_to
                                float * logits, int all_logits);
 /* device-resident decode step for throughput measurement: token id already on the device, logits stay on the
  * device (b200_falcon_logits_dev).  Same kernels/graph as b200_falcon_eval minus the two PCIe copies. */
-void          b200_falcon_decode_dev(b200_falcon * f, const int32_t * token_dev, int n_past, int n_ctx_rope);
+int           b200_falcon_decode_dev(b200_falcon * f, const int32_t * token_dev, int n_past, int n_ctx_rope);   /* 0 = ok, 1 = n_past outside [0, n_ctx) */
 const float * b200_falcon_logits_dev(const b200_falcon * f);
 /* greedy generation without leaving the device (single GPU): feeds `first_token` at position n_past, then n_steps times
  * "decode, arg-max of the logits (lowest index on ties), use it as the next token".  tokens_out[i] = token sampled after
  * step i.  What falcon_main does with top_k = 1 (llama_sample_token_greedy, libfalcon.cpp:3464-3473), minus the 260 KB
  * logits D2H and the host scan per token.  Returns 0 on success. */
 int           b200_falcon_generate_greedy(b200_falcon * f, int32_t first_token, int n_past, int n_steps, int n_ctx_rope, int32_t * tokens_out);
+/* KV cache rows [pos, pos + n) of one (global) layer index, host buffers of n * n_head_kv * head_dim floats each (either may be NULL).
+ * The building block of session save / restore (falcon_copy_state_data / falcon_set_state_data, libfalcon.cpp:4313-4490) over the
+ * device-resident cache.  Return 0 on success, 1 if the layer is not on this rank or the range leaves [0, n_ctx). */
+int           b200_falcon_kv_read(b200_falcon * f, int layer, int pos, int n, float * k_out, float * v_out);
+int           b200_falcon_kv_write(b200_falcon * f, int layer, int pos, int n, const float * k_in, const float * v_in);
+/* pseudo-random K / V rows for positions [pos, pos + n) of every local layer, generated on the device (long-context throughput runs) */
+int           b200_falcon_kv_fill_random(b200_falcon * f, int pos, int n, uint64_t seed);
 /* the cudaStream_t the eval path runs on (for event timing) */
 void *        b200_falcon_stream(b200_falcon * f);
 /* roofline probe: every resident quantised mat-vec of this rank (4 per layer + lm_head) launched back to back,

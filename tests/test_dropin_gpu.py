@@ -30,5 +30,8 @@ def test_reference_eval_runs_on_our_operator_surface(gpu, tmp_path, hp, wt, ftyp
         tok = np.array([200 + i], np.int32)
         g, w = ref.eval(tok, 12 + i, n_threads=2), o.eval(tok, 12 + i, all_logits=True)
         assert np.abs(g - w).max() <= 3e-2 * S and np.median(np.abs(g - w)) <= 5e-3 * S
-        tight.append(np.median(np.abs(g - w)) <= 2e-5 * S)
+        tight.append(bool(np.median(np.abs(g - w)) <= 2e-5 * S))
+    # decode goes through the integer mat-vec: at least half of the steps sit at the fp32-reassociation level (the prompt before
+    # them went through the fp16-operand GEMM, so a flipped activation code may already be in the KV cache)
+    assert sum(tight) * 2 >= len(tight), tight
     ref.close()

@@ -145,11 +145,11 @@ def test_against_reference_golden_logits(gpu, name):
     f.free()
 
 
-@pytest.mark.parametrize("env", ["B200_MEGA", "B200_LN_TAIL", "B200_NO_FUSED_DECODE"])
+@pytest.mark.parametrize("env", ["B200_NO_FUSED_DECODE", "B200_ATTN_NOFOLD", "B200_LN_NOCLUSTER"])
 @pytest.mark.parametrize("hp,wt", [(TINY_40B, po.Q4_K), (TINY_7B, po.Q4_0)])
 def test_alternative_decode_paths_match_oracle(gpu, hp, wt, env):
-    """the opt-in decode paths (persistent all-layers kernel, LayerNorm run by the last CTA of wo) and the generic
-    per-node path compute the same function as the default fused path"""
+    """the generic two-stream per-node decode path, the decode attention without the folded Q8 hand-over and the single-CTA
+    LayerNorm compute the same function as the default fused path"""
     tensors = synth_model(hp, wt, seed=1234)
     os.environ[env] = "1"
     try:
@@ -157,8 +157,7 @@ def test_alternative_decode_paths_match_oracle(gpu, hp, wt, env):
     finally:
         del os.environ[env]
     assert_mostly_tight([assert_logits_close(got, want, "%s step %d" % (env, i)) for i, (got, want) in enumerate(outs)], env)
-    if env == "B200_MEGA":
-        assert launches <= 5          # embedding + the persistent kernel + final LayerNorm + lm_head
+    assert launches > 0
 
 
 def test_greedy_generation_on_device_equals_host_argmax_loop(gpu):
@@ -194,8 +193,80 @@ def test_eval_rejects_out_of_range_requests(gpu):
             f.eval(toks, n_past)
     with pytest.raises(RuntimeError):
         f.generate_greedy(11, 10, 7)                                # 10 + 7 > n_ctx
+    for toks, n_past in ((np.array([11], np.int32), -1),            # negative position (would index before the cache)
+                         (np.array([11, 12], np.int32), -2),
+                         (np.array([hp["n_vocab"]], np.int32), 0),   # token id outside the embedding matrix
+                         (np.array([11, -5, 12], np.int32), 0)):
+        with pytest.raises(RuntimeError):
+            f.eval(toks, n_past)
+    tok_dev = gpu.DevBuf(src=np.array([11], np.int32))
+    for n_past in (-1, 16, 1000):                                   # the device-resident step checks its position too
+        with pytest.raises(RuntimeError):
+            f.decode_dev(tok_dev.ptr, n_past)
+    with pytest.raises(RuntimeError):
+        f.generate_greedy(hp["n_vocab"] + 3, 0, 2)
     a = f.eval(np.array([11, 12, 13], np.int32), 0)
     assert np.isfinite(a).all()
     b = f.eval(np.array([14], np.int32), 15)                        # the last slot of the context is usable
     assert np.isfinite(b).all()
     f.free()
+
+
+def test_decode_then_logits_all_batch_then_decode(gpu):
+    """the host-to-host decode graph copies its logits into a pinned buffer; a later logits_all batch that needs a larger buffer
+    must not leave that graph pointing at freed memory (order: 1-token warm-up eval -> logits_all prompt -> decode)"""
+    hp = dict(TINY_40B)
+    tensors = synth_model(hp, po.Q4_K, seed=21)
+    f = gpu.Falcon(hp, n_ctx=64, n_batch=8)
+    f.set_tensors(tensors)
+    o = po.OrcFalcon(hp, tensors, n_ctx=64)
+    flags = [assert_logits_close(f.eval(np.array([11], np.int32), 0), o.eval(np.array([11], np.int32), 0), "warm-up decode")]
+    prompt = np.array([11, 100, 101, 102, 103, 104], np.int32)
+    flags.append(assert_logits_close(f.eval(prompt, 0, all_logits=True), o.eval(prompt, 0, all_logits=True), "logits_all prompt"))
+    for i in range(3):
+        tok = np.array([150 + i], np.int32)
+        flags.append(assert_logits_close(f.eval(tok, 6 + i), o.eval(tok, 6 + i), "decode %d after the batch" % i))
+    assert_mostly_tight(flags)
+    f.free()
+
+
+def test_reloading_a_tensor_after_decoding_takes_effect(gpu):
+    """replacing a weight after the decode graph exists rebuilds the graph around the new device copy, and the resident-byte count
+    does not double"""
+    hp = dict(TINY_40B)
+    t1, t2 = synth_model(hp, po.Q4_K, seed=31), synth_model(hp, po.Q4_K, seed=32)
+    f = gpu.Falcon(hp, n_ctx=32, n_batch=4)
+    f.set_tensors(t1)
+    wb = f.weight_bytes()
+    tok = np.array([11], np.int32)
+    a1 = f.eval(tok, 0)
+    name = "transformer.h.1.mlp.dense_4h_to_h.weight"
+    f.set_tensor(name, *t2[name])
+    assert f.weight_bytes() == wb
+    mixed = dict(t1); mixed[name] = t2[name]
+    want = po.OrcFalcon(hp, mixed, n_ctx=32).eval(tok, 0)
+    got = f.eval(tok, 0)
+    assert not np.array_equal(got, a1)
+    assert_logits_close(got, want, "after reload")
+    f.free()
+
+
+def test_session_state_roundtrip_over_device_kv(gpu):
+    """KV rows read out of one engine and written into a fresh one (b200_falcon_kv_read / kv_write: what falcon_copy_state_data /
+    falcon_set_state_data do with the host cache, libfalcon.cpp:4313-4490) continue the sequence with the same bits"""
+    hp = dict(TINY_40B)
+    tensors = synth_model(hp, po.Q4_K, seed=41)
+    a, b = gpu.Falcon(hp, n_ctx=48, n_batch=8), gpu.Falcon(hp, n_ctx=48, n_batch=8)
+    a.set_tensors(tensors); b.set_tensors(tensors)
+    prompt = np.array([11, 60, 61, 62, 63], np.int32)
+    a.eval(prompt, 0)
+    a.eval(np.array([64], np.int32), 5)
+    for l in range(hp["n_layer"]):
+        k, v = a.kv_read(l, 0, 6)
+        b.kv_write(l, 0, k, v)
+    assert np.array_equal(a.eval(np.array([65], np.int32), 6), b.eval(np.array([65], np.int32), 6))
+    with pytest.raises(RuntimeError):
+        a.kv_read(hp["n_layer"], 0, 1)
+    with pytest.raises(RuntimeError):
+        a.kv_read(0, 40, 9)
+    a.free(); b.free()
