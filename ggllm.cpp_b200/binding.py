@@ -215,10 +215,10 @@ def layer_range(n_layer, rank, world):
 class Falcon:
     """The Falcon eval path (include/ggml_b200.h part B)."""
 
-    def __init__(self, hp, n_ctx, n_batch=1, rank=0, world=1):
+    def __init__(self, hp, n_ctx, n_batch=1, rank=0, world=1, layers=None):
         self.L = lib()
         self.hp = dict(hp)
-        lf, ll = layer_range(hp["n_layer"], rank, world)
+        lf, ll = layers if layers is not None else layer_range(hp["n_layer"], rank, world)      # layers: an explicit (first, last) range, e.g. balanced by bytes
         self.params = FalconParams(hp["n_vocab"], hp["n_embd"], hp["n_head"], hp["n_head_kv"], hp["n_layer"], hp["falcon_type"],
                                    n_ctx, n_batch, lf, ll, rank, world)
         self.layer_first, self.layer_last, self.rank, self.world = lf, ll, rank, world

@@ -77,7 +77,10 @@ struct b200_falcon {
     cudaStream_t s_main = nullptr, s_mlp = nullptr;
     cudaEvent_t e_fork = nullptr, e_join = nullptr, e_t0 = nullptr, e_t1 = nullptr;
     // decode graphs: [0] = device-resident step, [1] = host-to-host step (token H2D + logits D2H nodes inside)
-    cudaGraphExec_t graph[2] = { nullptr, nullptr }; float graph_theta[2] = { -1.f, -1.f }; int graph_launches = 0;
+    // [2] = generation step: [0] plus the sampler; in a pipeline the sampled id travels last rank -> rank 0 by ncclSend/ncclRecv
+    cudaGraphExec_t graph[3] = { nullptr, nullptr, nullptr }; float graph_theta[3] = { -1.f, -1.f, -1.f }; int graph_launches = 0;
+    bool ring_mode = false;                     // set while the generation-step graph is being captured
+    int32_t * tok_next = nullptr, * gen_hist = nullptr; int * gen_step = nullptr;   // sampled id, ids so far, step counter (device)
     int act_type = -1;
     unsigned * q_ctr = nullptr;                 // chunk counters of the quantise-on-completion epilogue (ffn_up -> ffn_down)
     ncclComm_t comm = nullptr;
@@ -144,7 +147,7 @@ static void expected_shape(const b200_falcon * f, const Slot & s, int64_t & K, i
 // the instantiated decode graphs bake in device pointers (weights, LayerNorm vectors, the pinned logits buffer):
 // whenever one of those is replaced the graphs are dropped and rebuilt by the next decode
 static void invalidate_graphs(b200_falcon * f) {
-    for (int i = 0; i < 2; i++) if (f->graph[i]) {
+    for (int i = 0; i < 3; i++) if (f->graph[i]) {
         B200_CUDA_CHECK(cudaStreamSynchronize(f->s_main));
         B200_CUDA_CHECK(cudaGraphExecDestroy(f->graph[i])); f->graph[i] = nullptr; f->graph_theta[i] = -1.f;
     }
@@ -186,6 +189,8 @@ b200_falcon * b200_falcon_create(const b200_falcon_params * p) {
     B200_CUDA_CHECK(cudaMalloc(&f->up, NB * f->FF * 4)); B200_CUDA_CHECK(cudaMalloc(&f->dn, NB * f->E * 4));
     B200_CUDA_CHECK(cudaMalloc(&f->logits, NB * f->V * 4));
     B200_CUDA_CHECK(cudaMalloc(&f->tokens_dev, NB * 4)); B200_CUDA_CHECK(cudaMalloc(&f->n_past_dev, 4));
+    B200_CUDA_CHECK(cudaMalloc(&f->tok_next, 4)); B200_CUDA_CHECK(cudaMalloc(&f->gen_step, 4));
+    B200_CUDA_CHECK(cudaMalloc(&f->gen_hist, (size_t) (p->n_ctx > 0 ? p->n_ctx : 1) * 4));
     B200_CUDA_CHECK(cudaMallocHost(&f->tokens_h, NB * 4)); B200_CUDA_CHECK(cudaMallocHost(&f->n_past_h, 4));
     f->logits_h_floats = (size_t) f->V; B200_CUDA_CHECK(cudaMallocHost(&f->logits_h, f->logits_h_floats * 4));
     return f;
@@ -333,7 +338,8 @@ void b200_falcon_free(b200_falcon * f) {
     cudaFree(f->attn_scratch); cudaFree(f->actq_mem); cudaFree(f->xh_a); cudaFree(f->xh_b); cudaFree(f->gemm_ws_a); cudaFree(f->gemm_ws_b);
     cudaFree(f->tokens_dev); cudaFree(f->n_past_dev); cudaFree(f->q_ctr); cudaFree(f->attn_dec_scratch);
     cudaFreeHost(f->tokens_h); cudaFreeHost(f->n_past_h); cudaFreeHost(f->logits_h);
-    for (int i = 0; i < 2; i++) if (f->graph[i]) cudaGraphExecDestroy(f->graph[i]);
+    for (int i = 0; i < 3; i++) if (f->graph[i]) cudaGraphExecDestroy(f->graph[i]);
+    cudaFree(f->tok_next); cudaFree(f->gen_hist); cudaFree(f->gen_step);
     if (f->comm) nccl().CommDestroy(f->comm);
     cudaEventDestroy(f->e_fork); cudaEventDestroy(f->e_join); cudaEventDestroy(f->e_t0); cudaEventDestroy(f->e_t1);
     cudaStreamDestroy(f->s_main); cudaStreamDestroy(f->s_mlp);
@@ -362,6 +368,20 @@ static void mm(b200_falcon * f, const WPlanes & W, const ActQ & A, int N, float 
 // residual adds + LayerNorm + activation quantisation in the prologue of qkv / ffn_up / lm_head (FastX mode 2),
 // activation quantisation in the prologue of wo / ffn_down (mode 1), GELU in ffn_up's epilogue.  6 kernels per layer:
 //   s_main: qkv -> rope+kv append -> attention -> wo          s_mlp: ffn_up(+GELU) -> ffn_down
+// Generation step (graph [2]): where the token id comes from and where the sampled one goes.
+//   rank 0 of a pipeline receives the id the last rank sampled in the previous step (one 4-byte ncclRecv, in-graph);
+//   the last rank samples from its logits on the device, records the id and sends it to rank 0 (single GPU: writes it
+//   straight into the embedding gather's input).  No logits and no token id touch the host between steps.
+static void ring_token_in(b200_falcon * f) {
+    if (f->ring_mode && f->hp.world > 1) B200_NCCL_CHECK(nccl().Recv(f->tokens_dev, 1, ncclInt32, f->hp.world - 1, f->comm, f->s_main));
+}
+static void ring_token_out(b200_falcon * f) {
+    if (!f->ring_mode) return;
+    int32_t * dst = f->hp.world > 1 ? f->tok_next : f->tokens_dev;
+    launch_argmax_hist(f->logits, f->V, dst, f->gen_hist, f->gen_step, f->s_main); f->launches++;
+    if (f->hp.world > 1) B200_NCCL_CHECK(nccl().Send(f->tok_next, 1, ncclInt32, 0, f->comm, f->s_main));
+}
+
 static bool fused_decode_ok(const b200_falcon * f) {
     if (getenv("B200_NO_FUSED_DECODE")) return false;
     for (const auto & L : f->layers)
@@ -375,7 +395,7 @@ static void enqueue_decode_fused(b200_falcon * f, int n_past, float theta_scale,
     const bool dual = f->hp.falcon_type == 40;
     ensure_actq(f);
     ActQ xa = f->xa, xm = f->xm, xf = f->xf, xup = f->xup, xatt = f->xatt; xa.N = xm.N = xf.N = xup.N = xatt.N = 1;
-    if (f->first) { launch_dequant_rows(f->tok_emb, f->tokens_dev, 1, f->inp, E, sa); f->launches++; }
+    if (f->first) { ring_token_in(f); launch_dequant_rows(f->tok_emb, f->tokens_dev, 1, f->inp, E, sa); f->launches++; }
     else B200_NCCL_CHECK(nccl().Recv(f->inp, (size_t) E, ncclFloat, f->hp.rank - 1, f->comm, sa));
     const MmvEpilogue none = { EPI_NONE, nullptr, nullptr, nullptr, nullptr };
     // ffn_up applies GELU and, chunk by chunk as CTAs finish, quantises its output row for ffn_down (no INIT pass, no prologue work there)
@@ -416,6 +436,7 @@ static void enqueue_decode_fused(b200_falcon * f, int n_past, float theta_scale,
     if (f->last) {
         launch_layernorm_q(f->inp, E, f->NL > 0 ? f->dn : nullptr, f->NL > 0 ? f->ao : nullptr, E, f->lnf_g, f->lnf_b, &xf, nullptr, nullptr, nullptr, E, 1, sa);   // :2399-2400, 2422-2431
         launch_mmv(f->lm_head, xf, f->logits, f->V, none, sa); f->launches += 2;      // :2440
+        ring_token_out(f);
     } else {
         if (f->NL > 0) { launch_add3(f->dn, f->ao, f->inp, f->inp, E, sa); f->launches++; }
         B200_NCCL_CHECK(nccl().Send(f->inp, (size_t) E, ncclFloat, f->hp.rank + 1, f->comm, sa));
@@ -433,7 +454,7 @@ static void enqueue_eval(b200_falcon * f, int N, int n_past, float theta_scale, 
     ActQ xa = f->xa, xm = f->xm, xatt = f->xatt, xup = f->xup, xf = f->xf;
     xa.N = xm.N = xatt.N = xup.N = xf.N = N;
 
-    if (f->first) { launch_dequant_rows(f->tok_emb, f->tokens_dev, N, f->inp, E, sa); f->launches++; }           // libfalcon.cpp:2120
+    if (f->first) { ring_token_in(f); launch_dequant_rows(f->tok_emb, f->tokens_dev, N, f->inp, E, sa); f->launches++; }           // libfalcon.cpp:2120
     else B200_NCCL_CHECK(nccl().Recv(f->inp, (size_t) N * E, ncclFloat, f->hp.rank - 1, f->comm, sa));
 
     for (int l = 0; l < f->NL; l++) {
@@ -476,6 +497,7 @@ static void enqueue_eval(b200_falcon * f, int N, int n_past, float theta_scale, 
         launch_layernorm_q(f->inp + (size_t) r0 * E, E, nullptr, nullptr, 0, f->lnf_g, f->lnf_b, &xfr, nullptr, nullptr, nullptr, E, nr, sa);   // :2422-2431
         f->launches++;
         mm(f, f->lm_head, xfr, nr, f->logits, f->V, EPI_NONE, nullptr, nullptr, f->xh_a, f->gemm_ws_a, sa);     // :2440
+        ring_token_out(f);
     } else B200_NCCL_CHECK(nccl().Send(f->inp, (size_t) N * E, ncclFloat, f->hp.rank + 1, f->comm, sa));
 }
 
@@ -498,7 +520,9 @@ static void build_decode_graph(b200_falcon * f, int which, float theta_scale) {
         B200_CUDA_CHECK(cudaMemcpyAsync(f->n_past_dev, f->n_past_h, 4, cudaMemcpyHostToDevice, f->s_main));
         if (f->first) B200_CUDA_CHECK(cudaMemcpyAsync(f->tokens_dev, f->tokens_h, 4, cudaMemcpyHostToDevice, f->s_main));
     }
+    f->ring_mode = which == 2;                 // (the eager pass above ran without it: every rank must issue the same NCCL calls there)
     enqueue_eval(f, 1, 0, theta_scale, true, 0);
+    f->ring_mode = false;
     if (which == 1 && f->last) B200_CUDA_CHECK(cudaMemcpyAsync(f->logits_h, f->logits, (size_t) f->V * 4, cudaMemcpyDeviceToHost, f->s_main));
     B200_CUDA_CHECK(cudaStreamEndCapture(f->s_main, &g));
     B200_CUDA_CHECK(cudaGraphInstantiate(&f->graph[which], g, 0));
@@ -566,23 +590,36 @@ int b200_falcon_decode_dev(b200_falcon * f, const int32_t * token_dev, int n_pas
 }
 const float * b200_falcon_logits_dev(const b200_falcon * f) { return f->logits; }
 
-// Greedy generation entirely on the device (single GPU): after every decode step one CTA takes the arg-max of the logits
-// (lowest index on ties, like a sequential scan) and writes it where the next step's embedding gather reads its token id,
-// so no logits and no token cross PCIe between steps.  First slice of SURVEY 8f-2 (the reference samples on the host from
-// a 260 KB logits row per token, falcon_main.cpp:897-980 with top_k = 1 / temp <= 0 -> llama_sample_token_greedy).
+// Greedy generation without the host in the loop.  After every decode step the last rank takes the arg-max of its logits on
+// the device (lowest index on ties, like a sequential scan) and hands the id to the embedding gather of the next step -- directly
+// on one GPU, through one 4-byte ncclSend/ncclRecv (last rank -> rank 0) in a layer pipeline -- so no logits and no token id cross
+// PCIe between steps: this is the strict autoregressive single-stream rate.  First slice of SURVEY 8f-2 (the reference samples on
+// the host from a 260 KB logits row per token, falcon_main.cpp:897-980 with top_k = 1 / temp <= 0 -> llama_sample_token_greedy,
+// libfalcon.cpp:3464-3473).  Every rank of a pipeline calls it with the same arguments; tokens_out is written on the last rank.
 int b200_falcon_generate_greedy(b200_falcon * f, int32_t first_token, int n_past, int n_steps, int n_ctx_rope, int32_t * tokens_out) {
-    if (!f->first || !f->last || n_steps <= 0 || n_past < 0 || n_past + n_steps > f->hp.n_ctx || first_token < 0 || first_token >= f->V) return 1;
-    int32_t * hist = nullptr;
-    B200_CUDA_CHECK(cudaMalloc(&hist, (size_t) n_steps * 4));
-    B200_CUDA_CHECK(cudaMemcpyAsync(f->tokens_dev, &first_token, 4, cudaMemcpyHostToDevice, f->s_main));
-    B200_CUDA_CHECK(cudaStreamSynchronize(f->s_main));               // first_token is a stack value
+    if (n_steps <= 0 || n_past < 0 || n_past + n_steps > f->hp.n_ctx || first_token < 0 || first_token >= f->V) return 1;
+    const float theta = rope_theta_scale_host(f->D, n_ctx_rope ? n_ctx_rope : f->hp.n_ctx, 1, 2.0f, 0);
+    cudaStream_t st = f->s_main;
+    set_i32_kernel<<<1, 1, 0, st>>>(f->n_past_dev, n_past);
+    if (f->first) { set_i32_kernel<<<1, 1, 0, st>>>((int *) f->tokens_dev, first_token); }
+    // both step graphs on every rank, built in the same order (each build runs one eager pass with the pipeline's send / recv pairs)
+    if (!f->graph[0] || f->graph_theta[0] != theta) build_decode_graph(f, 0, theta);
+    if (!f->graph[2] || f->graph_theta[2] != theta) build_decode_graph(f, 2, theta);
+    set_i32_kernel<<<1, 1, 0, st>>>(f->gen_step, 0);
+    if (f->first) { set_i32_kernel<<<1, 1, 0, st>>>((int *) f->tokens_dev, first_token); }
+    B200_CUDA_CHECK(cudaEventRecord(f->e_t0, st));
     for (int i = 0; i < n_steps; i++) {
-        if (b200_falcon_decode_dev(f, nullptr, n_past + i, n_ctx_rope) != 0) { B200_CUDA_CHECK(cudaFree(hist)); return 1; }  // token id already in f->tokens_dev
-        launch_argmax(f->logits, f->V, f->tokens_dev, hist + i, f->s_main);
+        set_i32_kernel<<<1, 1, 0, st>>>(f->n_past_dev, n_past + i);
+        // rank 0 of a pipeline takes its first id from the caller and every later one from the last rank
+        const int which = (f->last || (f->first && i > 0)) ? 2 : 0;
+        B200_CUDA_CHECK(cudaGraphLaunch(f->graph[(f->first && f->hp.world > 1 && i == 0) ? 0 : which], st));
     }
-    B200_CUDA_CHECK(cudaMemcpyAsync(tokens_out, hist, (size_t) n_steps * 4, cudaMemcpyDeviceToHost, f->s_main));
-    B200_CUDA_CHECK(cudaStreamSynchronize(f->s_main));
-    B200_CUDA_CHECK(cudaFree(hist));
+    if (f->first && f->hp.world > 1) B200_NCCL_CHECK(nccl().Recv(f->tokens_dev, 1, ncclInt32, f->hp.world - 1, f->comm, st));   // the id sampled after the last step
+    B200_CUDA_CHECK(cudaEventRecord(f->e_t1, st));
+    if (f->last && tokens_out) B200_CUDA_CHECK(cudaMemcpyAsync(tokens_out, f->gen_hist, (size_t) n_steps * 4, cudaMemcpyDeviceToHost, st));
+    B200_CUDA_CHECK(cudaStreamSynchronize(st));
+    B200_CUDA_CHECK(cudaEventElapsedTime(&f->last_ms, f->e_t0, f->e_t1));
+    f->launches = f->graph_launches;
     return 0;
 }
 // ---- KV cache access (session state).  The reference serialises its KV cache with the context

@@ -43,6 +43,7 @@ void   launch_layernorm(const float * x, int64_t x_stride, const float * g, cons
                         int n, int rows, cudaStream_t stream);              // y = norm(x)*g + b ; g,b may be null (plain ggml_norm)
 // [x = (ra + rb) + x, written back] ; A1 = Q(norm(x)*g1+b1) ; A2 = Q(norm(x)*g2+b2) (optional)
 void   launch_argmax(const float * x, int n, int32_t * out_a, int32_t * out_b, cudaStream_t stream);     // greedy sampling: lowest index on ties
+void   launch_argmax_hist(const float * x, int n, int32_t * out, int32_t * hist, int * step, cudaStream_t stream);  // + hist[(*step)++] = id (graph-replayable)
 void   launch_layernorm_q(float * x, int64_t x_stride, const float * ra, const float * rb, int64_t r_stride,
                           const float * g1, const float * b1, const ActQ * A1,
                           const float * g2, const float * b2, const ActQ * A2, int n, int rows, cudaStream_t stream);

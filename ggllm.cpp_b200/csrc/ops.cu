@@ -439,6 +439,32 @@ __global__ void __launch_bounds__(1024) argmax_kernel(const float * __restrict__
         if (threadIdx.x == 0) { if (out_a) *out_a = bi; if (out_b) *out_b = bi; }
     }
 }
+// graph-replayable form: the id also goes to hist[*step], and the step counter advances
+__global__ void __launch_bounds__(1024) argmax_hist_kernel(const float * __restrict__ x, int n, int32_t * __restrict__ out, int32_t * __restrict__ hist, int * __restrict__ step) {
+    __shared__ float sv[32]; __shared__ int si[32];
+    float best = -INFINITY; int bi = 0x7fffffff;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) { const float v = x[i]; if (v > best || (v == best && i < bi)) { best = v; bi = i; } }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, best, o); const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+    }
+    if ((threadIdx.x & 31) == 0) { sv[threadIdx.x >> 5] = best; si[threadIdx.x >> 5] = bi; }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        best = sv[threadIdx.x]; bi = si[threadIdx.x];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, best, o); const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+        }
+        if (threadIdx.x == 0) { *out = bi; const int k = *step; hist[k] = bi; *step = k + 1; }
+    }
+}
+void launch_argmax_hist(const float * x, int n, int32_t * out, int32_t * hist, int * step, cudaStream_t stream) {
+    argmax_hist_kernel<<<1, 1024, 0, stream>>>(x, n, out, hist, step);
+    B200_CUDA_CHECK(cudaGetLastError());
+}
 void launch_argmax(const float * x, int n, int32_t * out_a, int32_t * out_b, cudaStream_t stream) {
     argmax_kernel<<<1, 1024, 0, stream>>>(x, n, out_a, out_b);
     B200_CUDA_CHECK(cudaGetLastError());

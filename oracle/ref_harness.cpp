@@ -56,6 +56,42 @@ int refh_quantize(const char * in, const char * out, int ftype, int nthread) {
     return falcon_model_quantize(in, out, &qp);
 }
 
+// BASELINE config 1: Y = W x for n_mats rotating Q4_0 weight matrices [M rows][K] and ONE f32 activation column, through the
+// reference's own ggml_mul_mat + ggml_graph_compute -- the graph examples/benchmark/benchmark-matmult.cpp:181-202 builds, with the
+// shape as a parameter and the caller's blocks instead of ggml_quantize_q4_0(1.0f) (its sum check is numerically broken).
+// `blocks` holds n_mats * M * K/32 block_q4_0 (18 B each).  Every iteration computes all n_mats graphs once, so consecutive calls
+// never reuse a matrix out of cache when n_mats * M * K * 0.5625 B exceeds the LLC.  Returns the mean microseconds per mat-vec;
+// *best_us = the fastest single call; y_out (M floats) = the product with matrix 0.
+double refh_matvec_bench(int K, int M, int n_mats, int iters, int n_threads, const void * blocks, const float * x, float * y_out, double * best_us) {
+    ggml_time_init();
+    const size_t wbytes = (size_t) M * (K / 32) * 18;
+    struct ggml_init_params ip = { (size_t) n_mats * (wbytes + (size_t) M * 4 + 4096) + (size_t) K * 4 + (64u << 20), NULL, false };
+    struct ggml_context * ctx = ggml_init(ip);
+    if (!ctx) return -1.0;
+    struct ggml_tensor * xt = ggml_new_tensor_2d(ctx, GGML_TYPE_F32, K, 1);
+    memcpy(xt->data, x, (size_t) K * 4);
+    std::vector<struct ggml_cgraph> graphs(n_mats);
+    for (int i = 0; i < n_mats; i++) {
+        struct ggml_tensor * w = ggml_new_tensor_2d(ctx, GGML_TYPE_Q4_0, K, M);
+        memcpy(w->data, (const char *) blocks + (size_t) i * wbytes, wbytes);
+        graphs[i] = ggml_build_forward(ggml_mul_mat(ctx, w, xt));
+        graphs[i].n_threads = n_threads;
+    }
+    for (int i = 0; i < n_mats; i++) ggml_graph_compute(ctx, &graphs[i]);      // warm-up: thread pool, work buffer
+    memcpy(y_out, graphs[0].nodes[graphs[0].n_nodes - 1]->data, (size_t) M * 4);
+    double total = 0.0, best = 1e30;
+    for (int it = 0; it < iters; it++)
+        for (int i = 0; i < n_mats; i++) {
+            const int64_t t0 = ggml_time_us();
+            ggml_graph_compute(ctx, &graphs[i]);
+            const double us = (double) (ggml_time_us() - t0);
+            total += us; if (us < best) best = us;
+        }
+    if (best_us) *best_us = best;
+    ggml_free(ctx);
+    return total / ((double) iters * n_mats);
+}
+
 // the reference's own timing table (libfalcon.cpp:4700-4714)
 void refh_print_timings(void * h) { falcon_print_timings((falcon_context *) h); }
 

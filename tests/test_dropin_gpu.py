@@ -21,17 +21,26 @@ def test_reference_eval_runs_on_our_operator_surface(gpu, tmp_path, hp, wt, ftyp
     gpu.lib()                                      # libggml_b200.so is in the global symbol scope (RTLD_GLOBAL)
     ref = po.RefFalcon(path, n_ctx=64, n_batch=16, logits_all=True, hook=True, n_gpu_layers=99)
     o = po.OrcFalcon(hp, tensors, n_ctx=64)
-    prompt = np.array([11] + list(range(100, 111)), np.int32)          # 12 tokens: the N > 8 (GEMM) branch of the hook
-    got, want = ref.eval(prompt, 0, n_threads=2), o.eval(prompt, 0, all_logits=True)
+    # (1) batches of <= 8 tokens and decode steps take the hook's integer mat-vec branch: same integers as the CPU, so most evals must
+    #     sit at the fp32-reassociation level ("tight", tests/test_falcon_gpu.py), every one inside the loose bound
+    short = np.array([11, 100, 101, 102, 103, 104], np.int32)
+    got, want = ref.eval(short, 0, n_threads=2), o.eval(short, 0, all_logits=True)
     S = np.abs(want).max()
-    assert np.abs(got - want).max() <= 3e-2 * S and np.median(np.abs(got - want)) <= 5e-3 * S
-    tight = []
-    for i in range(4):                                                  # decode: the mat-vec branch
+    assert np.abs(got - want).max() <= 2e-2 * S and np.median(np.abs(got - want)) <= 2e-3 * S
+    tight = [bool(np.median(np.abs(got - want)) <= 2e-5 * S)]
+    for i in range(4):
         tok = np.array([200 + i], np.int32)
+        g, w = ref.eval(tok, 6 + i, n_threads=2), o.eval(tok, 6 + i, all_logits=True)
+        assert np.abs(g - w).max() <= 2e-2 * S and np.median(np.abs(g - w)) <= 2e-3 * S
+        tight.append(bool(np.median(np.abs(g - w)) <= 2e-5 * S))
+    assert sum(tight) * 2 >= len(tight), tight
+    # (2) 12 tokens: the N > 8 (tcgen05 GEMM, fp16 operands) branch of the hook, then decode over the KV cache it wrote.
+    #     Tolerance: the GEMM-path bound (max 3e-2 * S, median 5e-3 * S)
+    prompt = np.array([11] + list(range(100, 111)), np.int32)
+    got, want = ref.eval(prompt, 0, n_threads=2), o.eval(prompt, 0, all_logits=True)
+    assert np.abs(got - want).max() <= 3e-2 * S and np.median(np.abs(got - want)) <= 5e-3 * S
+    for i in range(3):
+        tok = np.array([300 + i], np.int32)
         g, w = ref.eval(tok, 12 + i, n_threads=2), o.eval(tok, 12 + i, all_logits=True)
         assert np.abs(g - w).max() <= 3e-2 * S and np.median(np.abs(g - w)) <= 5e-3 * S
-        tight.append(bool(np.median(np.abs(g - w)) <= 2e-5 * S))
-    # decode goes through the integer mat-vec: at least half of the steps sit at the fp32-reassociation level (the prompt before
-    # them went through the fp16-operand GEMM, so a flipped activation code may already be in the KV cache)
-    assert sum(tight) * 2 >= len(tight), tight
     ref.close()
