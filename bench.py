@@ -197,10 +197,12 @@ def reference_cpu_decode(model, wtype, steps, warmup, n_ctx_rope=129):
         run(11, 0, min(cores, 32))                      # the reference's own warm-up eval (falcon_main.cpp:662-673): also faults the file in
         # thread count: ggml's spin-barrier pool does not scale monotonically with threads (README.md:137) -- probe, keep the fastest
         pos, best_t, probe = 1, min(cores, 32), {}
-        for t in sorted(set(min(cores, c) for c in (16, 32, 64, 128))):
+        for t in sorted(set(min(cores, c) for c in (8, 16, 32, 64, 128))):
             t1 = time.time()
             run(50 + t, pos, t); pos += 1
             probe[t] = time.time() - t1
+            if probe[t] > 1.5 * min(probe.values()):      # past the knee (128 spinning threads: 30 s per token): stop probing
+                break
         best_t = min(probe, key=probe.get)
         for i in range(warmup):
             run(100 + i, pos, best_t); pos += 1

@@ -203,7 +203,19 @@ void b200_attention(float * qkv, float * kc, float * vc, float * out, int n_head
     AttnParams p = { n_head, n_head_kv, head_dim, n_tok, n_past, nullptr, n_ctx, (int64_t) (n_head + 2 * n_head_kv) * head_dim, nullptr };
     launch_rope_kv_append(qkv, kc, vc, p, rope_theta_scale_host(head_dim, n_ctx_rope ? n_ctx_rope : n_ctx, 1, 2.0f, 0), g_stream);   // libfalcon.cpp:2231-2234
     if (n_tok > 1) {
-        if (!launch_attention_tc(qkv, kc, vc, out, (int64_t) n_head * head_dim, p, g_stream)) {
+        // the warp-specialised tcgen05 kernel reads an fp16 shadow of the cache: built here from the caller's fp32 cache (the engine
+        // keeps one up to date token by token instead)
+        static __half * sh = nullptr; static size_t sh_halves = 0;
+        const size_t need = head_dim == 64 ? attention_shadow_halves(n_head_kv, n_ctx) : 0;
+        if (need > sh_halves) { if (sh) { B200_CUDA_CHECK(cudaStreamSynchronize(g_stream)); B200_CUDA_CHECK(cudaFree(sh)); }
+            B200_CUDA_CHECK(cudaMalloc(&sh, 2 * need * sizeof(__half))); sh_halves = need; }
+        if (need) {
+            B200_CUDA_CHECK(cudaMemsetAsync(sh, 0, 2 * need * sizeof(__half), g_stream));
+            p.k16 = sh; p.vt16 = sh + need;
+            launch_kv_shadow_refresh(kc, vc, p.k16, p.vt16, n_head_kv, n_ctx, 0, n_past + n_tok, g_stream);
+        }
+        if (launch_attention_ws(qkv, out, (int64_t) n_head * head_dim, p, g_stream)) {}
+        else if (!launch_attention_tc(qkv, kc, vc, out, (int64_t) n_head * head_dim, p, g_stream)) {
             float * sc = (float *) scratch(attention_prefill_scratch_bytes(n_head, n_tok, n_past + n_tok));
             launch_attention_prefill(qkv, kc, vc, out, (int64_t) n_head * head_dim, p, sc, g_stream);
         }

@@ -65,6 +65,7 @@ struct b200_falcon {
     WPlanes tok_emb{}, lm_head{};
     float * lnf_g = nullptr, * lnf_b = nullptr;
     float * k_cache = nullptr, * v_cache = nullptr;
+    __half * k16 = nullptr, * vt16 = nullptr; size_t shadow_layer = 0;      // fp16 shadow of the cache for the prompt kernel (attention_ws.cu); only when n_batch > 8
     // activation arena
     float * inp = nullptr, * qkv = nullptr, * att = nullptr, * ao = nullptr, * up = nullptr, * dn = nullptr, * logits = nullptr;
     void * actq_mem = nullptr; ActQ xa{}, xm{}, xatt{}, xup{}, xf{};
@@ -184,6 +185,12 @@ b200_falcon * b200_falcon_create(const b200_falcon_params * p) {
     const size_t kv = (size_t) f->NL * p->n_ctx * f->HKV * f->D * sizeof(float);
     B200_CUDA_CHECK(cudaMalloc(&f->k_cache, kv ? kv : 4)); B200_CUDA_CHECK(cudaMalloc(&f->v_cache, kv ? kv : 4));
     B200_CUDA_CHECK(cudaMemset(f->k_cache, 0, kv)); B200_CUDA_CHECK(cudaMemset(f->v_cache, 0, kv));
+    if (p->n_batch > b200_mmv_max_n() && f->D == 64 && f->NL > 0) {
+        f->shadow_layer = attention_shadow_halves(f->HKV, p->n_ctx);
+        const size_t sb = (size_t) f->NL * f->shadow_layer * sizeof(__half);
+        B200_CUDA_CHECK(cudaMalloc(&f->k16, sb)); B200_CUDA_CHECK(cudaMalloc(&f->vt16, sb));
+        B200_CUDA_CHECK(cudaMemset(f->k16, 0, sb)); B200_CUDA_CHECK(cudaMemset(f->vt16, 0, sb));
+    }
     B200_CUDA_CHECK(cudaMalloc(&f->inp, NB * f->E * 4)); B200_CUDA_CHECK(cudaMalloc(&f->qkv, NB * f->QKV * 4));
     B200_CUDA_CHECK(cudaMalloc(&f->att, NB * f->E * 4)); B200_CUDA_CHECK(cudaMalloc(&f->ao, NB * f->E * 4));
     B200_CUDA_CHECK(cudaMalloc(&f->up, NB * f->FF * 4)); B200_CUDA_CHECK(cudaMalloc(&f->dn, NB * f->E * 4));
@@ -333,7 +340,7 @@ void b200_falcon_free(b200_falcon * f) {
     for (auto & L : f->layers) { wplanes_free(L.wqkv); wplanes_free(L.wo); wplanes_free(L.up); wplanes_free(L.down);
         cudaFree(L.ln_attn_g); cudaFree(L.ln_attn_b); cudaFree(L.ln_mlp_g); cudaFree(L.ln_mlp_b); }
     wplanes_free(f->tok_emb); wplanes_free(f->lm_head);
-    cudaFree(f->lnf_g); cudaFree(f->lnf_b); cudaFree(f->k_cache); cudaFree(f->v_cache);
+    cudaFree(f->lnf_g); cudaFree(f->lnf_b); cudaFree(f->k_cache); cudaFree(f->v_cache); cudaFree(f->k16); cudaFree(f->vt16);
     cudaFree(f->inp); cudaFree(f->qkv); cudaFree(f->att); cudaFree(f->ao); cudaFree(f->up); cudaFree(f->dn); cudaFree(f->logits);
     cudaFree(f->attn_scratch); cudaFree(f->actq_mem); cudaFree(f->xh_a); cudaFree(f->xh_b); cudaFree(f->gemm_ws_a); cudaFree(f->gemm_ws_b);
     cudaFree(f->tokens_dev); cudaFree(f->n_past_dev); cudaFree(f->q_ctr); cudaFree(f->attn_dec_scratch);
@@ -417,6 +424,7 @@ static void enqueue_decode_fused(b200_falcon * f, int n_past, float theta_scale,
         B200_CUDA_CHECK(cudaStreamWaitEvent(sb, f->e_fork, 0));
         AttnParams ap = { f->H, f->HKV, f->D, 1, n_past, graph_mode ? f->n_past_dev : nullptr, f->hp.n_ctx, (int64_t) f->QKV, nullptr };
         const size_t kvoff = (size_t) l * f->hp.n_ctx * f->HKV * f->D;
+        if (f->k16) { ap.k16 = f->k16 + (size_t) l * f->shadow_layer; ap.vt16 = f->vt16 + (size_t) l * f->shadow_layer; }
         if (!skip("attn")) {
         launch_rope_kv_append(f->qkv, f->k_cache + kvoff, f->v_cache + kvoff, ap, theta_scale, sb);             // :2229-2281
         // wo's activation quantisation: done by the attention kernel's combine step when its blocks fit the head groups,
@@ -476,10 +484,12 @@ static void enqueue_eval(b200_falcon * f, int N, int n_past, float theta_scale, 
         mm(f, L.wqkv, attn_in, N, f->qkv, f->QKV, EPI_NONE, nullptr, nullptr, f->xh_a, f->gemm_ws_a, sa);      // :2192
         AttnParams ap = { f->H, f->HKV, f->D, N, n_past, graph_mode ? f->n_past_dev : nullptr, f->hp.n_ctx, (int64_t) f->QKV, nullptr };
         const size_t kvoff = (size_t) l * f->hp.n_ctx * f->HKV * f->D;
+        if (f->k16) { ap.k16 = f->k16 + (size_t) l * f->shadow_layer; ap.vt16 = f->vt16 + (size_t) l * f->shadow_layer; }
         launch_rope_kv_append(f->qkv, f->k_cache + kvoff, f->v_cache + kvoff, ap, theta_scale, sa);             // :2229-2281
         if (N > 1 && !graph_mode) {
             // tensor-core kernel (no scratch); the CUDA-core fallback (N <= 8 or head_dim != 64) materialises the score matrix
-            if (!launch_attention_tc(f->qkv, f->k_cache + kvoff, f->v_cache + kvoff, f->att, E, ap, sa)) {
+            if (launch_attention_ws(f->qkv, f->att, E, ap, sa)) {}
+            else if (!launch_attention_tc(f->qkv, f->k_cache + kvoff, f->v_cache + kvoff, f->att, E, ap, sa)) {
                 if (!f->attn_scratch) B200_CUDA_CHECK(cudaMalloc(&f->attn_scratch, attention_prefill_scratch_bytes(f->H, f->hp.n_batch, f->hp.n_ctx)));
                 launch_attention_prefill(f->qkv, f->k_cache + kvoff, f->v_cache + kvoff, f->att, E, ap, f->attn_scratch, sa); f->launches++;
             }
@@ -639,6 +649,11 @@ int b200_falcon_kv_write(b200_falcon * f, int layer, int pos, int n, const float
     B200_CUDA_CHECK(cudaStreamSynchronize(f->s_main));
     if (k_in) B200_CUDA_CHECK(cudaMemcpy(f->k_cache + off, k_in, (size_t) n * row * 4, cudaMemcpyHostToDevice));
     if (v_in) B200_CUDA_CHECK(cudaMemcpy(f->v_cache + off, v_in, (size_t) n * row * 4, cudaMemcpyHostToDevice));
+    if (f->k16) {
+        const int l = layer - f->hp.layer_first; const size_t lo = (size_t) l * f->hp.n_ctx * row;
+        launch_kv_shadow_refresh(f->k_cache + lo, f->v_cache + lo, f->k16 + (size_t) l * f->shadow_layer, f->vt16 + (size_t) l * f->shadow_layer, f->HKV, f->hp.n_ctx, pos, n, f->s_main);
+        B200_CUDA_CHECK(cudaStreamSynchronize(f->s_main));
+    }
     return 0;
 }
 // random K / V rows generated on the device for positions [pos, pos + n) of every local layer: pre-fills a long context
@@ -650,6 +665,8 @@ int b200_falcon_kv_fill_random(b200_falcon * f, int pos, int n, uint64_t seed) {
         const size_t off = ((size_t) l * f->hp.n_ctx + pos) * row;
         fill_f32_kernel<<<296, 256, 0, f->s_main>>>(f->k_cache + off, (int64_t) ((size_t) n * row), 0.f, 1.f, seed + 2 * l);
         fill_f32_kernel<<<296, 256, 0, f->s_main>>>(f->v_cache + off, (int64_t) ((size_t) n * row), 0.f, 1.f, seed + 2 * l + 1);
+        if (f->k16) { const size_t lo = (size_t) l * f->hp.n_ctx * row;
+            launch_kv_shadow_refresh(f->k_cache + lo, f->v_cache + lo, f->k16 + (size_t) l * f->shadow_layer, f->vt16 + (size_t) l * f->shadow_layer, f->HKV, f->hp.n_ctx, pos, n, f->s_main); }
     }
     B200_CUDA_CHECK(cudaGetLastError());
     B200_CUDA_CHECK(cudaStreamSynchronize(f->s_main));

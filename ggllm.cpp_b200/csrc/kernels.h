@@ -69,6 +69,9 @@ struct AttnParams {
     int64_t qkv_stride;         // floats between consecutive tokens in the fused QKV buffer
     unsigned long long * trace; // optional timeline slot (debug)
     const ActQ * qout;          // optional (split-KV decode kernels): also emit the output row quantised for the wo mat-mul (its INIT pass)
+    // optional fp16 shadow of this layer's cache for the prompt kernel (attention_ws.cu): k16 [n_ctx][n_head_kv][64],
+    // vt16 [n_head_kv][64][attention_ctx_pad(n_ctx)] (V transposed); rope_kv_append keeps it in step with the fp32 cache
+    __half * k16; __half * vt16;
 };
 // fused: rope(Q), rope(K) -> K cache append, V cache append      (libfalcon.cpp:2229-2281)
 void   launch_rope_kv_append(float * qkv, float * k_cache, float * v_cache, const AttnParams & p, float theta_scale, cudaStream_t stream);
@@ -77,6 +80,11 @@ int    launch_attention(const float * qkv, const float * k_cache, const float * 
                         const AttnParams & p, float * scratch, cudaStream_t stream);
 size_t attention_scratch_bytes(const AttnParams & p);
 // N > 1 (prompt): tiled two-kernel version with a score scratch matrix (attention_prefill.cu)
+// attention_ws.cu: N > 8 on tcgen05, warp-specialised, over the fp16 shadow (p.k16 / p.vt16); false = not covered
+bool   launch_attention_ws(const float * qkv, float * out, int64_t out_stride, const AttnParams & p, cudaStream_t stream);
+int    attention_ctx_pad(int n_ctx);
+size_t attention_shadow_halves(int n_head_kv, int n_ctx);           // halves per layer, for k16 and for vt16 each
+void   launch_kv_shadow_refresh(const float * k_cache, const float * v_cache, __half * k16, __half * vt16, int n_head_kv, int n_ctx, int pos, int n, cudaStream_t stream);
 bool   launch_attention_tc(const float * qkv, const float * k_cache, const float * v_cache, float * out, int64_t out_stride,
                            const AttnParams & p, cudaStream_t stream);       // attention_tc.cu: N > 1 on tcgen05 (head_dim 64)
 size_t attention_prefill_scratch_bytes(int n_head, int n_tok, int T);

@@ -403,6 +403,11 @@ __global__ void rope_kv_append_kernel(float * __restrict__ qkv, float * __restri
         const int kvh = slot - p.n_head - (is_k ? 0 : p.n_head_kv);
         float * dst = (is_k ? kc : vc) + ((size_t) pos * p.n_head_kv + kvh) * D;
         dst[i] = v[i]; dst[i + half] = v[i + half];
+        if (p.k16) {                                                          // fp16 shadow for the prompt kernel, written once per token
+            if (is_k) { __half * d16 = p.k16 + ((size_t) pos * p.n_head_kv + kvh) * D; d16[i] = __float2half_rn(v[i]); d16[i + half] = __float2half_rn(v[i + half]); }
+            else { const size_t cp = (size_t) ((p.n_ctx + 63) / 64 * 64); __half * d16 = p.vt16 + (size_t) kvh * D * cp + pos;
+                   d16[(size_t) i * cp] = __float2half_rn(v[i]); d16[(size_t) (i + half) * cp] = __float2half_rn(v[i + half]); }
+        }
     }
     trace_end(p.trace);
 }
