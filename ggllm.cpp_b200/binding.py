@@ -74,6 +74,7 @@ def lib():
         for name, (res, args) in sig.items():
             fn = getattr(L, name)
             fn.restype, fn.argtypes = res, args
+        L.b200_surface_takeover_evals.restype, L.b200_surface_takeover_evals.argtypes = C.c_long, []      # ggml_surface.cu test hook
         _lib = L
     return _lib
 

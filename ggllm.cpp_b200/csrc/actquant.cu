@@ -24,7 +24,7 @@ void actq_bind(ActQ & A, int t, int K, int N, void * base) {
     A.type = t; A.K = K; A.N = N;
     A.q = (int8_t *) p; p += round_up((size_t) N * K, 256);
     A.d = (float *) p;  p += round_up((size_t) N * (K / blk) * 4, 256);
-    A.s = nullptr; A.bs = nullptr;
+    A.s = nullptr; A.bs = nullptr; A.h = nullptr;
     if (t == T_Q8_1) { A.s = (float *) p; p += round_up((size_t) N * (K / 32) * 4, 256); }
     A.bs = (int16_t *) p;
 }

@@ -42,6 +42,12 @@ __device__ __forceinline__ void quantize_chunk8(const float (&v)[8], int lane, c
     const uint32_t lo = (q[0] & 0xff) | ((q[1] & 0xff) << 8) | ((q[2] & 0xff) << 16) | ((uint32_t) (q[3] & 0xff) << 24);
     const uint32_t hi = (q[4] & 0xff) | ((q[5] & 0xff) << 8) | ((q[6] & 0xff) << 16) | ((uint32_t) (q[7] & 0xff) << 24);
     if (store) *reinterpret_cast<uint2 *>(A.q + (size_t) n * A.K + k0) = make_uint2(lo, hi);
+    if (A.h && store) {                                           // GEMM operand: d * q rounded once to fp16 (what actq_to_f16_kernel computes)
+        __half2 hh[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) hh[j] = __floats2half2_rn(__fmul_rn(d, (float) q[2 * j]), __fmul_rn(d, (float) q[2 * j + 1]));
+        *reinterpret_cast<uint4 *>(A.h + (size_t) n * A.K + k0) = *reinterpret_cast<const uint4 *>(hh);
+    }
 
     if (TYPE == T_Q8_K) {
         const int s16 = sum + __shfl_xor_sync(0xffffffffu, sum, 1);              // 16 codes = 2 lanes

@@ -16,12 +16,13 @@
 //   * warp 0 streams the tiles with TMA (cp.async.bulk.tensor, 3-D maps) into a 3-deep K ring and a 2-deep V^T ring
 //   * warp 1 issues every tcgen05.mma; S is double-buffered in tensor memory, so Q K^T of tile i+1 runs while the softmax warps
 //     work on tile i, and P V of tile i-1 runs behind it
-//   * warps 2..9 (two threads per query row) only do the softmax: tcgen05.ld S, e = LUT(s - max), P written as fp16 into the
-//     swizzled operand layout (double-buffered); the row sums come out of the tensor core too (a row of ones appended to V^T,
-//     accumulator column 64), so the CUDA cores never add probabilities
+//   * warps 2..17 (four threads per query row, 32 score columns each) only do the softmax: tcgen05.ld S, e = LUT(s - max), P written
+//     as fp16 into the swizzled operand layout (double-buffered); the row sums come out of the tensor core too (a row of ones
+//     appended to V^T, accumulator column 64), so the CUDA cores never add probabilities.  Sixteen warps = four per scheduler: the
+//     softmax is what bounds the kernel (one MUFU.EX2 per score, 16 lanes / clk / SM), so its latencies have to overlap
 // One CTA = 128 query rows of one KV head (row = token * G + head_in_group: the G query heads that share the KV head are stacked,
 // a K / V tile serves all of them) x all visible keys in tiles of 128; CTAs with the most key tiles are scheduled first.
-// Tensor memory: S0 [0,128) S1 [128,256) O [256,336); shared memory 169 KB -> one CTA per SM.
+// Tensor memory: S0 [0,128) S1 [128,256) O [256,336); shared memory 171 KB -> one CTA per SM (18 warps).
 // Precision: Q, K, V rounded to fp16, fp32 accumulation, P exact; the row sum is an fp32 sum (the CPU's is double).  Tolerance:
 // tests/test_kernels_gpu.py::test_attention (atol 5e-3, median 5e-4), logits inside the GEMM-path bound.
 #include "kernels.h"
@@ -35,9 +36,9 @@ constexpr int KST = 3, VST = 2;
 constexpr int V_SUB = 10240;                        // one 64-key half of a V^T stage: 64 dims x 128 B from TMA + 16 rows (ones, zeros) = 80 rows
 constexpr int V_STAGE = 2 * V_SUB;
 constexpr int SQ = 0, SK = 16384, SV = SK + KST * 16384, SP = SV + VST * V_STAGE, SBAR = SP + 2 * 32768, SX = SBAR + 256;
-constexpr size_t SMEM_BYTES = 1024 + SX + 2 * 128 * 4;
+constexpr size_t SMEM_BYTES = 1024 + SX + 4 * 128 * 4;
 constexpr int N_O = 80;                             // accumulator columns of P V: 64 dims + the ones row (row sum) + 15 unused
-constexpr int SOFTMAX_THREADS = 256, THREADS = 64 + SOFTMAX_THREADS;
+constexpr int SOFTMAX_THREADS = 512, THREADS = 64 + SOFTMAX_THREADS;
 constexpr uint32_t TM_S = 0, TM_O = 256, TM_COLS = 512;
 
 __device__ __forceinline__ void mbar_arrive(uint64_t * bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory"); }
@@ -80,6 +81,13 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
     return *reinterpret_cast<const uint32_t *>(&h);
 }
 __device__ __forceinline__ void softmax_sync() { asm volatile("bar.sync 1, %0;" :: "n"(SOFTMAX_THREADS) : "memory"); }
+// e^x for x <= 0 as the LUT computes it up to the final fp16 rounding: ex2.approx.ftz (2 ulp fp32); results below 2^-126 flush to zero,
+// which the fp16 rounding would do anyway (the plain __expf wraps the same instruction in denormal rescaling: 3 extra instructions)
+__device__ __forceinline__ float exp_fast(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x * 1.4426950408889634f));
+    return y;
+}
 
 struct WsArgs {
     const float * qkv; float * out;
@@ -87,19 +95,39 @@ struct WsArgs {
     int64_t qkv_stride, out_stride;
 };
 
-// 32 fp32 values (half h of a 64-value row, or zeros) -> half of one 128-byte row of a K-major SWIZZLE_128B tile
-__device__ __forceinline__ void store_half_row_f16(uint8_t * tile, int r, const float * src, bool valid, int h) {
+// 16 fp32 values (quarter h of a 64-value row, or zeros) -> a quarter of one 128-byte row of a K-major SWIZZLE_128B tile
+__device__ __forceinline__ void store_quarter_row_f16(uint8_t * tile, int r, const float * src, bool valid, int h) {
     uint8_t * row = tile + r * 128;
     const int sw = r & 7;
 #pragma unroll
-    for (int cc = 0; cc < 4; cc++) {
-        const int c = 4 * h + cc;
+    for (int cc = 0; cc < 2; cc++) {
+        const int c = 2 * h + cc;
         uint4 v = make_uint4(0, 0, 0, 0);
         if (valid) {
             const float4 a = __ldg(reinterpret_cast<const float4 *>(src) + 2 * c), b = __ldg(reinterpret_cast<const float4 *>(src) + 2 * c + 1);
             v = make_uint4(pack_h2(a.x, a.y), pack_h2(a.z, a.w), pack_h2(b.x, b.y), pack_h2(b.z, b.w));
         }
         *reinterpret_cast<uint4 *>(row + ((c ^ sw) << 4)) = v;
+    }
+}
+
+// one 32-column slice of an S tile -> P (fp16) in the A-operand layout.  MASKED: keys >= vis are zeroed (tiles on the causal diagonal)
+template <bool MASKED>
+__device__ __forceinline__ void softmax_slice(const uint32_t (&v)[32], uint8_t * prow, int c, int t, float scale, float neg_m, int key0, int vis) {
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        uint32_t pk[4];
+#pragma unroll
+        for (int jj = 0; jj < 4; jj++) {
+            // s - max with ONE rounding: the product with 0.125 is exact, so fma(s, 0.125, -max) == (s * 0.125) - max
+            const float x0 = __fmaf_rn(__uint_as_float(v[8 * q + 2 * jj]), scale, neg_m), x1 = __fmaf_rn(__uint_as_float(v[8 * q + 2 * jj + 1]), scale, neg_m);
+            const float2 xr = __half22float2(__floats2half2_rn(x0, x1));               // the LUT index: f16(s - max)
+            float e0 = exp_fast(xr.x), e1 = exp_fast(xr.y);
+            if (MASKED) { const int key = key0 + 8 * q + 2 * jj; if (key >= vis) e0 = 0.f; if (key + 1 >= vis) e1 = 0.f; }
+            pk[jj] = pack_h2(e0, e1);                                                   // table_exp_f16 value: exact as fp16
+        }
+        const int ci = (c & 1) * 4 + q;
+        *reinterpret_cast<uint4 *>(prow + ((ci ^ (t & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
     }
 }
 
@@ -191,8 +219,8 @@ __global__ void __launch_bounds__(THREADS, 1) attention_ws_kernel(const __grid_c
             tc_commit(o_full);
         }
     } else {
-        // ================================================================ softmax warps: thread = (row t, column half hf)
-        const int q4 = warp & 3, hf = (warp - 2) >> 2, t = q4 * 32 + lane;  // a warp may only touch TMEM lanes 32 (warp % 4) ..
+        // ================================================================ softmax warps: thread = (row t, 32-column slice c)
+        const int q4 = warp & 3, c = (warp - 2) >> 2, t = q4 * 32 + lane;   // a warp may only touch TMEM lanes 32 (warp % 4) ..
         const int row = r0 + t;
         const bool row_ok = row < a.rows;
         const int tok = row / a.G, head = g * a.G + row % a.G;
@@ -200,7 +228,7 @@ __global__ void __launch_bounds__(THREADS, 1) attention_ws_kernel(const __grid_c
         const int vis_min = r0 + M <= a.rows ? a.n_past + r0 / a.G + 1 : 0; // keys visible to EVERY row of the tile (0 if it has padding rows)
         const float scale = 0.125f;                                         // 1 / sqrt(64), a power of two: s * scale is exact
         const uint32_t tm_lane = tmem_base + ((uint32_t) (q4 * 32) << 16);
-        store_half_row_f16(smem + SQ, t, a.qkv + (size_t) tok * a.qkv_stride + (size_t) head * D, row_ok, hf);
+        store_quarter_row_f16(smem + SQ, t, a.qkv + (size_t) tok * a.qkv_stride + (size_t) head * D, row_ok, c);
         fence_proxy_async();
         mbar_arrive(q_full);
 
@@ -210,81 +238,59 @@ __global__ void __launch_bounds__(THREADS, 1) attention_ws_kernel(const __grid_c
             const int b = kt & 1, k0 = kt * NK;
             mbar_wait(s_full + b, (uint32_t) ((kt >> 1) & 1));
             tc_fence_after();
-            const bool full = k0 + NK <= vis_min;
-#pragma unroll
-            for (int cc = 0; cc < 2; cc++) {
-                const int c = 2 * hf + cc;
-                uint32_t v[32];
-                tmem_ld32(tm_lane + TM_S + b * NK + c * 32, v);
-                if (full) {
-#pragma unroll
-                    for (int j = 0; j < 32; j++) mraw = fmaxf(mraw, __uint_as_float(v[j]));
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 32; j++) if (k0 + c * 32 + j < vis) mraw = fmaxf(mraw, __uint_as_float(v[j]));
-                }
-            }
+            uint32_t v[32];
+            tmem_ld32(tm_lane + TM_S + b * NK + c * 32, v);
             tc_fence_before();
-            mbar_arrive(s_free + b);
+            mbar_arrive(s_free + b);                                        // the scores are in registers: the tensor core may overwrite the buffer
+            if (k0 + NK <= vis_min) {
+#pragma unroll
+                for (int j = 0; j < 32; j++) mraw = fmaxf(mraw, __uint_as_float(v[j]));
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; j++) if (k0 + c * 32 + j < vis) mraw = fmaxf(mraw, __uint_as_float(v[j]));
+            }
         }
-        xch[hf * 128 + t] = mraw;
+        xch[c * 128 + t] = mraw;
         softmax_sync();
-        const float m = __fmul_rn(fmaxf(xch[t], xch[128 + t]), scale);
+        const float m = __fmul_rn(fmaxf(fmaxf(xch[t], xch[128 + t]), fmaxf(xch[256 + t], xch[384 + t])), scale);
         const float neg_m = -m;
 
         // ---- pass 2: e = table_exp_f16[f16(s - max)] (ggml.c:12427-12440), P = e as fp16 (exact), written into the A operand layout
         for (int i = 0; i < nt; i++) {
             const int j = nt + i, b = j & 1, pb = i & 1, k0 = i * NK;
             mbar_wait(s_full + b, (uint32_t) ((j >> 1) & 1));
-            if (i >= 2) mbar_wait(p_free + pb, (uint32_t) (((i >> 1) - 1) & 1));
             tc_fence_after();
-            const bool full = k0 + NK <= vis_min;
-#pragma unroll
-            for (int cc = 0; cc < 2; cc++) {
-                const int c = 2 * hf + cc;
-                uint32_t v[32];
-                tmem_ld32(tm_lane + TM_S + b * NK + c * 32, v);
-                uint8_t * prow = smem + SP + pb * 32768 + (c >> 1) * 16384 + t * 128;
-#pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    uint32_t pk[4];
-#pragma unroll
-                    for (int jj = 0; jj < 4; jj++) {
-                        // s - max with ONE rounding: the product with 0.125 is exact, so fma(s, 0.125, -max) == (s * 0.125) - max
-                        const float x0 = __fmaf_rn(__uint_as_float(v[8 * q + 2 * jj]), scale, neg_m), x1 = __fmaf_rn(__uint_as_float(v[8 * q + 2 * jj + 1]), scale, neg_m);
-                        const float2 xr = __half22float2(__floats2half2_rn(x0, x1));               // the LUT index: f16(s - max)
-                        // fast exponential: ex2.approx is within 2 ulp (fp32) of expf, so the fp16-rounded value differs from the table only when the
-                        // exact result sits within ~1e-6 (relative) of an fp16 rounding boundary -- inside this path's fp16-operand tolerance
-                        float e0 = __expf(xr.x), e1 = __expf(xr.y);
-                        if (!full) { const int key = k0 + c * 32 + 8 * q + 2 * jj; if (key >= vis) e0 = 0.f; if (key + 1 >= vis) e1 = 0.f; }
-                        pk[jj] = pack_h2(e0, e1);
-                    }
-                    const int ci = (c & 1) * 4 + q;
-                    *reinterpret_cast<uint4 *>(prow + ((ci ^ (t & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                }
-            }
+            uint32_t v[32];
+            tmem_ld32(tm_lane + TM_S + b * NK + c * 32, v);
             tc_fence_before();
             mbar_arrive(s_free + b);
+            if (i >= 2) mbar_wait(p_free + pb, (uint32_t) (((i >> 1) - 1) & 1));
+            uint8_t * prow = smem + SP + pb * 32768 + (c >> 1) * 16384 + t * 128;
+            if (k0 + NK <= vis_min) softmax_slice<false>(v, prow, c, t, scale, neg_m, 0, 0);
+            else softmax_slice<true>(v, prow, c, t, scale, neg_m, k0 + c * 32, vis);
             fence_proxy_async();                                            // P: generic-proxy stores -> visible to the tensor core
             mbar_arrive(p_full + pb);
         }
 
-        // ---- epilogue: O / sum -> out[tok][head * 64 + ...]
+        // ---- epilogue: O / sum -> out[tok][head * 64 + ...]: slice c of the row writes dims 16 c .. 16 c + 15
         mbar_wait(o_full, 0);
         tc_fence_after();
-        uint32_t ls[32];
-        tmem_ld32(tm_lane + TM_O + 64, ls);                                 // column 64 = sum of the row's P (ones row of V^T); warp-collective
         {
-            const float l = __uint_as_float(ls[0]);
-            const float inv = (float) (1.0 / (double) l);                   // ggml.c:12427-12449
-            float * dst = a.out + (size_t) tok * a.out_stride + (size_t) head * D + hf * 32;
             uint32_t v[32];
-            tmem_ld32(tm_lane + TM_O + hf * 32, v);
+            tmem_ld32(tm_lane + TM_O + 48, v);                              // columns 48..79: v[16] = column 64 = sum of the row's P (ones row of V^T)
+            const float l = __uint_as_float(v[16]);
+            const float inv = (float) (1.0 / (double) l);                   // ggml.c:12427-12449
+            uint32_t o[32];
+            tmem_ld32(tm_lane + TM_O + (c >> 1) * 32, o);                   // warp-collective: every lane loads, valid rows store
+            float * dst = a.out + (size_t) tok * a.out_stride + (size_t) head * D + c * 16;
             if (row_ok) {
 #pragma unroll
-                for (int j = 0; j < 32; j += 4)
-                    *reinterpret_cast<float4 *>(dst + j) = make_float4(__fmul_rn(__uint_as_float(v[j]), inv), __fmul_rn(__uint_as_float(v[j + 1]), inv),
-                                                                       __fmul_rn(__uint_as_float(v[j + 2]), inv), __fmul_rn(__uint_as_float(v[j + 3]), inv));
+                for (int jj = 0; jj < 16; jj += 4) {                        // (compile-time register indices: no local-memory array)
+                    const float4 lo = make_float4(__uint_as_float(o[jj]), __uint_as_float(o[jj + 1]), __uint_as_float(o[jj + 2]), __uint_as_float(o[jj + 3]));
+                    const float4 hi = make_float4(__uint_as_float(o[16 + jj]), __uint_as_float(o[17 + jj]), __uint_as_float(o[18 + jj]), __uint_as_float(o[19 + jj]));
+                    const float4 x = (c & 1) ? hi : lo;
+                    *reinterpret_cast<float4 *>(dst + jj) = make_float4(__fmul_rn(x.x, inv), __fmul_rn(x.y, inv), __fmul_rn(x.z, inv), __fmul_rn(x.w, inv));
+                }
             }
         }
     }

@@ -69,7 +69,7 @@ struct b200_falcon {
     // activation arena
     float * inp = nullptr, * qkv = nullptr, * att = nullptr, * ao = nullptr, * up = nullptr, * dn = nullptr, * logits = nullptr;
     void * actq_mem = nullptr; ActQ xa{}, xm{}, xatt{}, xup{}, xf{};
-    __half * xh_a = nullptr, * xh_b = nullptr;      // fp16 GEMM operands, one per branch
+    __half * xh_a = nullptr, * xh_b = nullptr, * xh_m = nullptr;      // fp16 GEMM operands (d * q), written by the kernels that quantise: attention branch, MLP branch, MLP input
     void * gemm_ws_a = nullptr, * gemm_ws_b = nullptr; size_t gemm_ws_bytes = 0;
     float * attn_scratch = nullptr;
     float * attn_dec_scratch = nullptr;            // split-KV decode attention: counters + scores + partials (attention.cu)
@@ -87,6 +87,7 @@ struct b200_falcon {
     ncclComm_t comm = nullptr;
     int launches = 0; float last_ms = 0.f;
     size_t weight_bytes = 0;
+    std::vector<const void *> borrowed;         // device planes adopted from another owner (ggml_cuda_transform_tensor): never freed here
 };
 
 static float * upload_f32(const void * data, int ggml_type, int64_t n, cudaStream_t s) {
@@ -220,10 +221,34 @@ static void ensure_actq(b200_falcon * f) {
     actq_bind(f->xup, at, f->FF, NB, p);
     if (NB > b200_mmv_max_n()) {
         B200_CUDA_CHECK(cudaMalloc(&f->xh_a, (size_t) NB * f->E * 2)); B200_CUDA_CHECK(cudaMalloc(&f->xh_b, (size_t) NB * f->FF * 2));
+        B200_CUDA_CHECK(cudaMalloc(&f->xh_m, (size_t) NB * f->E * 2));
         WPlanes big{}; big.type = T_Q4_K; big.K = f->FF; big.M = f->FF > f->V ? f->FF : f->V;
         f->gemm_ws_bytes = mmq_gemm_workspace_bytes(big, NB);
         B200_CUDA_CHECK(cudaMalloc(&f->gemm_ws_a, f->gemm_ws_bytes)); B200_CUDA_CHECK(cudaMalloc(&f->gemm_ws_b, f->gemm_ws_bytes));
     }
+}
+
+static void free_matrix(b200_falcon * f, WPlanes & W) {
+    for (const void * b : f->borrowed) if (b == (const void *) W.p[0]) { W = WPlanes{}; return; }      // adopted: its owner frees it
+    wplanes_free(W);
+}
+
+// A weight matrix that is already resident in this library's planar layout (uploaded by ggml_cuda_transform_tensor for the reference's
+// loader, ggml_surface.cu) becomes the engine's matrix `name` without another copy.  Returns false for an unknown name / wrong shape.
+extern "C++" bool falcon_adopt_matrix(b200_falcon * f, const char * name, const WPlanes & W) {
+    Slot s;
+    if (!parse_name(name, s) || (s.kind != 0 && s.kind != 3 && s.kind < 14)) return false;
+    if (s.layer >= 0 && (s.layer < f->hp.layer_first || s.layer >= f->hp.layer_last)) return false;
+    int64_t K, M; expected_shape(f, s, K, M);
+    if (W.K != K || W.M != M) return false;
+    invalidate_graphs(f);
+    Layer * L = s.layer >= 0 ? &f->layers[s.layer - f->hp.layer_first] : nullptr;
+    WPlanes & dst = s.kind == 0 ? f->tok_emb : s.kind == 3 ? f->lm_head : s.kind == 14 ? L->wqkv : s.kind == 15 ? L->wo : s.kind == 16 ? L->up : L->down;
+    if (dst.p[0]) { if (s.kind != 0) f->weight_bytes -= algorithmic_bytes(dst.type, dst.K, dst.M); free_matrix(f, dst); }
+    dst = W;
+    f->borrowed.push_back((const void *) W.p[0]);
+    if (s.kind != 0) { f->weight_bytes += algorithmic_bytes(W.type, K, M); note_act_type(f, W.type); }
+    return true;
 }
 
 static void place_tensor(b200_falcon * f, const Slot & s, int type, const void * host_data, bool random, uint64_t seed) {
@@ -235,7 +260,7 @@ static void place_tensor(b200_falcon * f, const Slot & s, int type, const void *
     cudaStream_t st = f->s_main;
     invalidate_graphs(f);
     auto matrix = [&](WPlanes & W) {
-        if (W.p[0]) { if (s.kind != 0) f->weight_bytes -= algorithmic_bytes(W.type, W.K, W.M); wplanes_free(W); }
+        if (W.p[0]) { if (s.kind != 0) f->weight_bytes -= algorithmic_bytes(W.type, W.K, W.M); free_matrix(f, W); }
         if (random) wplanes_alloc_random(W, type, (int) K, (int) M, seed, st);
         else wplanes_upload(W, type, (int) K, (int) M, host_data, st);
         if (s.kind != 0) { f->weight_bytes += algorithmic_bytes(type, K, M); note_act_type(f, type); }
@@ -337,12 +362,12 @@ void b200_falcon_init_pipeline(b200_falcon * f, const void * id128) {
 void b200_falcon_free(b200_falcon * f) {
     if (!f) return;
     cudaDeviceSynchronize();
-    for (auto & L : f->layers) { wplanes_free(L.wqkv); wplanes_free(L.wo); wplanes_free(L.up); wplanes_free(L.down);
+    for (auto & L : f->layers) { free_matrix(f, L.wqkv); free_matrix(f, L.wo); free_matrix(f, L.up); free_matrix(f, L.down);
         cudaFree(L.ln_attn_g); cudaFree(L.ln_attn_b); cudaFree(L.ln_mlp_g); cudaFree(L.ln_mlp_b); }
-    wplanes_free(f->tok_emb); wplanes_free(f->lm_head);
+    free_matrix(f, f->tok_emb); free_matrix(f, f->lm_head);
     cudaFree(f->lnf_g); cudaFree(f->lnf_b); cudaFree(f->k_cache); cudaFree(f->v_cache); cudaFree(f->k16); cudaFree(f->vt16);
     cudaFree(f->inp); cudaFree(f->qkv); cudaFree(f->att); cudaFree(f->ao); cudaFree(f->up); cudaFree(f->dn); cudaFree(f->logits);
-    cudaFree(f->attn_scratch); cudaFree(f->actq_mem); cudaFree(f->xh_a); cudaFree(f->xh_b); cudaFree(f->gemm_ws_a); cudaFree(f->gemm_ws_b);
+    cudaFree(f->attn_scratch); cudaFree(f->actq_mem); cudaFree(f->xh_a); cudaFree(f->xh_b); cudaFree(f->xh_m); cudaFree(f->gemm_ws_a); cudaFree(f->gemm_ws_b);
     cudaFree(f->tokens_dev); cudaFree(f->n_past_dev); cudaFree(f->q_ctr); cudaFree(f->attn_dec_scratch);
     cudaFreeHost(f->tokens_h); cudaFreeHost(f->n_past_h); cudaFreeHost(f->logits_h);
     for (int i = 0; i < 3; i++) if (f->graph[i]) cudaGraphExecDestroy(f->graph[i]);
@@ -365,9 +390,10 @@ static void mm(b200_falcon * f, const WPlanes & W, const ActQ & A, int N, float 
         launch_mmv(W, a, y, y_stride, e, st); f->launches++;
     } else {
         B200_ASSERT(epi != EPI_ADD2);
-        launch_actq_to_f16(a, xh, W.K, st);
+        if (a.h) xh = a.h;                                     // the producer of the codes already wrote the fp16 operand
+        else { launch_actq_to_f16(a, xh, W.K, st); f->launches++; }
         launch_mmq_gemm(W, xh, W.K, N, y, y_stride, epi == EPI_GELU, ws, f->gemm_ws_bytes, st);
-        f->launches += 2;
+        f->launches++;
     }
 }
 
@@ -461,6 +487,7 @@ static void enqueue_eval(b200_falcon * f, int N, int n_past, float theta_scale, 
     ensure_actq(f);
     ActQ xa = f->xa, xm = f->xm, xatt = f->xatt, xup = f->xup, xf = f->xf;
     xa.N = xm.N = xatt.N = xup.N = xf.N = N;
+    if (N > b200_mmv_max_n()) { xa.h = f->xh_a; xm.h = f->xh_m; xatt.h = f->xh_a; xup.h = f->xh_b; xf.h = f->xh_a; }     // GEMM path: fp16 operands come with the codes
 
     if (f->first) { ring_token_in(f); launch_dequant_rows(f->tok_emb, f->tokens_dev, N, f->inp, E, sa); f->launches++; }           // libfalcon.cpp:2120
     else B200_NCCL_CHECK(nccl().Recv(f->inp, (size_t) N * E, ncclFloat, f->hp.rank - 1, f->comm, sa));

@@ -58,9 +58,12 @@ struct WPlanes {
 //   d  f32  [N][K/blk]    scale  (Q8_0: the fp16-rounded value, widened)
 //   s  f32  [N][K/32]     Q8_1 only: d * sum(q)
 //   bs i16  [N][K/16]     Q8_K: sums of 16 codes (block_q8_K.bsums); Q8_0/Q8_1: [N][K/32] sum of the block's codes
+//   h  f16  [N][K]        optional: the dequantised value d * q rounded to fp16 -- the B operand of the tensor-core GEMM -- written by the
+//                         same kernel that produces the codes (prompt path), so no separate conversion pass runs
 struct ActQ {
     int type, K, N;
     int8_t * q; float * d; float * s; int16_t * bs;
+    __half * h;
 };
 static inline int act_block(int t) { return t == T_Q8_K ? 256 : 32; }
 static inline int act_type_for(int wtype) {

@@ -13,7 +13,10 @@
 #include "../../include/ggml_b200_cuda_surface.h"
 #include "../../include/ggml_b200.h"
 #include <cstring>
+#include <map>
 #include <mutex>
+#include <string>
+#include <vector>
 
 namespace {
 
@@ -126,9 +129,167 @@ void op_unary(int op, const abi::tensor * src0, const abi::tensor * src1, abi::t
     result_out(dst, y);
 }
 
+// ------------------------------------------------------------------------------------------------ whole-graph takeover
+// The per-node protocol above costs one H2D + D2H + stream synchronize per claimed node (241 MUL_MATs per Falcon-40B token).  The
+// reference's executor, however, shows this hook EVERY node of the eval graph in execution order (ggml.c:15779-15790, 17241-17300),
+// and libfalcon names its tensors (model tensors carry their GGCC names, libfalcon.cpp:1158; graph nodes "result_lm_head" etc.,
+// :2116-2443).  That is enough to run the whole Falcon eval on the device-resident engine (engine.cu, part B of ggml_b200.h) behind
+// the unmodified falcon_eval:
+//   eval 1 ("learning", e.g. falcon_main's BOS warm-up, falcon_main.cpp:662-673) runs through the per-node path while every model
+//     tensor the nodes reference is recorded by name.  At its last node the engine is built: the offloaded weight matrices are
+//     ADOPTED (they already are in this library's layout, ggml_cuda_transform_tensor), the CPU-resident embedding / lm_head /
+//     LayerNorm vectors are uploaded once, the KV capacity comes from "cache_k"; the engine then replays that eval to fill ITS cache.
+//   eval 2.. : GET_ROWS(tok_embeddings, embd) marks the start: the token ids are on the host there.  Every node is claimed without
+//     computing anything until the first ROPE node, whose src1 holds n_past and the rope context (ggml.c:6947-6952): the engine
+//     evaluates the whole graph there (one CUDA graph launch for N = 1); "result_lm_head" receives the logits.
+// Conditions: every layer's four matrices offloaded (n_gpu_layers >= n_layer), head_dim 64, first eval at n_past 0.  Otherwise the
+// per-node path stays in charge.  Under takeover the reference's HOST KV cache is not maintained (the cache lives in HBM; use
+// b200_falcon_kv_read for session files).  B200_NO_TAKEOVER=1 disables it.
+b200_falcon * b200_takeover_engine = nullptr;          // the engine behind the hook (tests read its counters)
+
+struct Takeover {
+    enum State { OFF, LEARNING, READY, DISABLED } state = OFF;
+    std::map<std::string, const abi::tensor *> named;   // GGCC name -> model tensor
+    const abi::tensor * emb = nullptr, * cache_k = nullptr;
+    std::vector<int32_t> tokens; int N = 0, n_past = -1, rope_ctx = 0;
+    bool active = false, launched = false;              // this eval is being evaluated by the engine
+    int valid_upto = 0, n_vocab = 0, n_batch = 0;
+    float * logits = nullptr; size_t logits_floats = 0; // pinned
+    long evals_taken = 0;
+} g_tk;
+
+bool is_model_name(const char * n) { return strncmp(n, "transformer.", 12) == 0 || strcmp(n, "lm_head.weight") == 0; }
+void tk_note(const abi::tensor * t) { if (t && t->name[0] && is_model_name(t->name)) g_tk.named[t->name] = t; }
+
+const float * tk_logits(size_t floats) {
+    if (floats > g_tk.logits_floats) {
+        if (g_tk.logits) B200_CUDA_CHECK(cudaFreeHost(g_tk.logits));
+        g_tk.logits_floats = floats; B200_CUDA_CHECK(cudaMallocHost(&g_tk.logits, floats * 4));
+    }
+    return g_tk.logits;
+}
+
+// end of the learning eval: build the engine from what the graph showed.  false -> stay on the per-node path for good
+bool tk_build() {
+    auto get = [&](const std::string & n) -> const abi::tensor * { auto it = g_tk.named.find(n); return it == g_tk.named.end() ? nullptr : it->second; };
+    const abi::tensor * qkv0 = get("transformer.h.0.self_attention.query_key_value.weight"), * head = get("lm_head.weight");
+    if (!qkv0 || !head || !g_tk.emb || !g_tk.cache_k) return false;
+    int n_layer = 0;
+    while (get("transformer.h." + std::to_string(n_layer) + ".self_attention.query_key_value.weight")) n_layer++;
+    b200_falcon_params hp{};
+    hp.n_embd = (int) qkv0->ne[0]; hp.n_head = hp.n_embd / 64; hp.n_head_kv = (int) ((qkv0->ne[1] / 64 - hp.n_head) / 2);
+    hp.n_vocab = (int) head->ne[1]; hp.n_layer = n_layer; hp.falcon_type = get("transformer.h.0.ln_attn.weight") ? 40 : 7;
+    if (hp.n_embd % 64 || hp.n_head_kv <= 0 || hp.n_head % hp.n_head_kv || (hp.n_head + 2 * hp.n_head_kv) * 64 != qkv0->ne[1]) return false;
+    hp.n_ctx = (int) (nelements(g_tk.cache_k) / ((int64_t) n_layer * hp.n_head_kv * 64));
+    hp.n_batch = g_tk.n_batch = 512;
+    if (hp.n_ctx <= 0 || (int64_t) hp.n_ctx * n_layer * hp.n_head_kv * 64 != nelements(g_tk.cache_k)) return false;
+    const char * mats[4] = { "self_attention.query_key_value.weight", "self_attention.dense.weight", "mlp.dense_h_to_4h.weight", "mlp.dense_4h_to_h.weight" };
+    for (int l = 0; l < n_layer; l++)
+        for (const char * m : mats) {
+            const abi::tensor * t = get("transformer.h." + std::to_string(l) + "." + m);
+            if (!t || !on_gpu(t) || !owned(t) || owned(t)->kind != 0) return false;                   // partial offload: keep the per-node path
+        }
+    b200_falcon * f = b200_falcon_create(&hp);
+    bool ok = true;
+    auto vec_or_mat = [&](const std::string & name) {
+        const abi::tensor * t = get(name);
+        if (!t) { ok = false; return; }
+        if (on_gpu(t) && owned(t) && owned(t)->kind == 0) { ok = ok && falcon_adopt_matrix(f, name.c_str(), owned(t)->W); return; }
+        const int64_t ne[2] = { t->ne[0], t->ne[1] };
+        if (on_gpu(t) && owned(t) && owned(t)->kind == 1) {                                              // 1-D f32 that the loader offloaded (7B's input_layernorm.weight)
+            std::vector<float> h((size_t) t->ne[0]);
+            B200_CUDA_CHECK(cudaMemcpy(h.data(), owned(t)->f32, h.size() * 4, cudaMemcpyDeviceToHost));
+            b200_falcon_set_tensor(f, name.c_str(), T_F32, 1, ne, h.data());
+        } else b200_falcon_set_tensor(f, name.c_str(), t->type, t->n_dims, ne, t->data);                 // CPU-resident: one upload (mmap'ed file bytes)
+    };
+    vec_or_mat("transformer.word_embeddings.weight"); vec_or_mat("lm_head.weight");
+    vec_or_mat("transformer.ln_f.weight"); vec_or_mat("transformer.ln_f.bias");
+    for (int l = 0; l < n_layer && ok; l++) {
+        const std::string p = "transformer.h." + std::to_string(l) + ".";
+        for (const char * m : mats) vec_or_mat(p + m);
+        if (hp.falcon_type == 40) { vec_or_mat(p + "ln_attn.weight"); vec_or_mat(p + "ln_attn.bias"); vec_or_mat(p + "ln_mlp.weight"); vec_or_mat(p + "ln_mlp.bias"); }
+        else { vec_or_mat(p + "input_layernorm.weight"); vec_or_mat(p + "input_layernorm.bias"); }
+    }
+    if (!ok) { b200_falcon_free(f); return false; }
+    b200_takeover_engine = f; g_tk.n_vocab = hp.n_vocab;
+    return true;
+}
+
+// returns true when the node is handled by the takeover machinery (the caller then returns true to ggml: skip the CPU)
+bool tk_node(const abi::compute_params * params, abi::tensor * t) {
+    if (g_tk.state == Takeover::DISABLED) return false;
+    const bool lead = params->ith == 0 && params->type == abi::TASK_COMPUTE;
+    const bool start = t->op == abi::OP_GET_ROWS && t->src0 && strcmp(t->src0->name, "transformer.word_embeddings.weight") == 0 && t->src1 && t->src1->type == 18 /* GGML_TYPE_I32 */;
+    if (start && lead && getenv("B200_NO_TAKEOVER")) {                       // read at the start of every eval: per-node path from here on
+        if (g_tk.evals_taken > 0) { fprintf(stderr, "b200: B200_NO_TAKEOVER set after the device took the KV cache over\n"); abort(); }
+        g_tk.state = Takeover::OFF; g_tk.active = false;
+        return false;
+    }
+    if (start && lead) {
+        g_tk.tokens.assign((const int32_t *) t->src1->data, (const int32_t *) t->src1->data + t->src1->ne[0]);
+        g_tk.N = (int) t->src1->ne[0]; g_tk.n_past = -1; g_tk.launched = false;
+        if (g_tk.state == Takeover::OFF) { g_tk.state = Takeover::LEARNING; g_tk.named.clear(); g_tk.emb = t->src0; }
+        else if (g_tk.state == Takeover::READY) {
+            if (t->src0 != g_tk.emb || g_tk.N > g_tk.n_batch) {              // another model / an oversized batch
+                if (g_tk.evals_taken > 0) { fprintf(stderr, "b200: n_batch %d > %d (or a second model) behind the operator hook after the device took the KV cache over\n", g_tk.N, g_tk.n_batch); abort(); }
+                g_tk.state = Takeover::DISABLED; return false;
+            }
+            g_tk.active = true;
+        }
+    }
+    if (g_tk.state == Takeover::LEARNING) {
+        if (lead) {
+            tk_note(t->src0); tk_note(t->src1);
+            if (t->op == abi::OP_ROPE && g_tk.n_past < 0) { g_tk.n_past = ((const int32_t *) t->src1->data)[0]; g_tk.rope_ctx = ((const int32_t *) t->src1->data)[3]; }
+            if (t->op == abi::OP_VIEW && t->src0 && strcmp(t->src0->name, "cache_k") == 0) g_tk.cache_k = t->src0;
+        }
+        return false;                                                          // the per-node path computes this eval
+    }
+    if (!g_tk.active) return false;
+    if (!lead) return true;
+    if (t->op == abi::OP_ROPE && !g_tk.launched) {
+        g_tk.n_past = ((const int32_t *) t->src1->data)[0]; g_tk.rope_ctx = ((const int32_t *) t->src1->data)[3];
+        if (g_tk.n_past > g_tk.valid_upto) {
+            fprintf(stderr, "b200: eval at n_past %d but the device KV cache holds %d positions (KV state restored on the host?); "
+                            "set B200_NO_TAKEOVER=1 to keep the per-node path\n", g_tk.n_past, g_tk.valid_upto);
+            abort();
+        }
+        float * lg = const_cast<float *>(tk_logits((size_t) g_tk.N * g_tk.n_vocab));
+        if (b200_falcon_eval(b200_takeover_engine, g_tk.tokens.data(), g_tk.N, g_tk.n_past, g_tk.rope_ctx, lg, 1) != 0) {
+            fprintf(stderr, "b200: engine eval failed behind ggml_cuda_compute_forward (N %d, n_past %d)\n", g_tk.N, g_tk.n_past); abort();
+        }
+        g_tk.valid_upto = g_tk.n_past + g_tk.N; g_tk.launched = true; g_tk.evals_taken++;
+    }
+    if (strcmp(t->name, "result_lm_head") == 0) {
+        B200_ASSERT(g_tk.launched && contiguous_f32(t) && nelements(t) == (int64_t) g_tk.N * g_tk.n_vocab);
+        memcpy(t->data, g_tk.logits, (size_t) g_tk.N * g_tk.n_vocab * 4);      // falcon_eval_internal reads the logits here (libfalcon.cpp:2538-2549)
+        t->meta.cuda_perf_mal_mul_type = g_tk.N <= b200_mmv_max_n() ? 1 : 16;
+        g_tk.active = false;
+    }
+    return true;
+}
+
+// called after the per-node path has finished the LAST node of the learning eval
+void tk_finish_learning() {
+    if (tk_build() && g_tk.n_past == 0) {
+        // replay the eval on the engine so that ITS cache holds these positions too (results discarded)
+        float * lg = const_cast<float *>(tk_logits((size_t) g_tk.N * g_tk.n_vocab));
+        if (g_tk.N <= g_tk.n_batch && b200_falcon_eval(b200_takeover_engine, g_tk.tokens.data(), g_tk.N, 0, g_tk.rope_ctx, lg, 1) == 0) {
+            g_tk.valid_upto = g_tk.N; g_tk.state = Takeover::READY;
+            if (getenv("B200_VERBOSE")) fprintf(stderr, "b200: Falcon eval graph recognised -- whole-graph evaluation on the device from the next eval on\n");
+            return;
+        }
+    }
+    if (b200_takeover_engine) { b200_falcon_free(b200_takeover_engine); b200_takeover_engine = nullptr; }
+    g_tk.state = Takeover::DISABLED;
+}
+
 } // namespace
 
 extern "C" {
+
+// test / bench hook: number of evals the engine has run behind ggml_cuda_compute_forward (0 = per-node path only)
+long b200_surface_takeover_evals(void) { return g_tk.evals_taken; }
 
 const GPUStatus * ggml_cuda_get_system_gpu_status(void) { return &g_status; }
 
@@ -213,6 +374,7 @@ void ggml_cuda_transform_tensor(void * data, struct ggml_tensor * t_) {
 void ggml_cuda_free_data(struct ggml_tensor * t_) {
     abi::tensor * t = (abi::tensor *) t_;
     if (!on_gpu(t) || !t->extra) return;
+    if (b200_takeover_engine) { b200_falcon_free(b200_takeover_engine); b200_takeover_engine = nullptr; g_tk = Takeover{}; }   // it borrows these planes
     DeviceTensor * d = owned(t);
     if (d) { if (d->kind == 0) wplanes_free(d->W); else cudaFree(d->f32); delete d; }
     delete (ggml_tensor_extra_gpu *) t->extra;
@@ -268,6 +430,9 @@ bool ggml_cuda_compute_forward(struct ggml_compute_params * p_, struct ggml_tens
     abi::tensor * t = (abi::tensor *) t_;
     if (t->op == abi::OP_NONE) return true;                                  // ggml-cuda.cu:3196
     if (g_status.num_devices == 0) return false;
+    if (tk_node(params, t)) return true;                                     // whole-graph takeover (see above)
+    const bool learning_last = g_tk.state == Takeover::LEARNING && params->ith == 0 && params->type == abi::TASK_COMPUTE && strcmp(t->name, "result_lm_head") == 0;
+    struct Finish { bool on; ~Finish() { if (on) tk_finish_learning(); } } finish_after_this_node{ learning_last };
     if (t->meta.cuda_op_directive == 0) return false;                        // ggml-cuda.cu:3202 (KQ / KQV, libfalcon.cpp:2309,2356)
     const bool any_on_device = t->backend == abi::BACKEND_GPU || (t->src0 && on_gpu(t->src0)) || (t->src1 && t->src1->backend == abi::BACKEND_GPU);
     if (!any_on_device) return false;

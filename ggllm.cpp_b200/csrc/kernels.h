@@ -95,3 +95,7 @@ void   launch_attention_prefill(const float * qkv, const float * k_cache, const 
 void   launch_mmq_gemm(const WPlanes & W, const __half * X, int64_t x_stride, int N, float * Y, int64_t y_stride,
                        int epi_gelu, void * workspace, size_t workspace_bytes, cudaStream_t stream);
 size_t mmq_gemm_workspace_bytes(const WPlanes & W, int N);
+
+// ---- engine.cu (internal, C++ linkage): adopt a matrix that is already resident in the planar layout (no copy, not freed by the engine)
+struct b200_falcon;
+bool   falcon_adopt_matrix(b200_falcon * f, const char * ggcc_name, const WPlanes & W);

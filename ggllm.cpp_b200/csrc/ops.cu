@@ -411,8 +411,61 @@ __global__ void rope_kv_append_kernel(float * __restrict__ qkv, float * __restri
     }
     trace_end(p.trace);
 }
+// The same work for a batch of tokens (prompt).  The single-token kernel above recomputes the 32 rotation angles of a position in every
+// one of its (n_head + 2 n_head_kv) x n_tok tiny CTAs and scatters V^T two bytes at a time (78 us per Falcon-40B layer at 512 tokens,
+// as long as the attention itself).  Here one CTA per token computes its cos / sin once and walks the row coalesced, and the V^T shadow
+// is written by extra CTAs that transpose 64 tokens x 64 dims through shared memory (128-byte rows).  Same arithmetic, same bits.
+__global__ void __launch_bounds__(256) rope_kv_append_batch_kernel(float * __restrict__ qkv, float * __restrict__ kc, float * __restrict__ vc, AttnParams p, float theta_scale) {
+    const int D = p.head_dim, half = D / 2, H = p.n_head, HKV = p.n_head_kv, N = p.n_tok;
+    const int n_past = p.n_past_dev ? *p.n_past_dev : p.n_past;
+    if ((int) blockIdx.x < N) {
+        __shared__ float cs[64], sn[64];
+        const int t = blockIdx.x, pos = n_past + t;
+        if ((int) threadIdx.x < half) {
+            float theta = (float) pos;
+            for (int k = 0; k < (int) threadIdx.x; k++) theta = __fmul_rn(theta, theta_scale);
+            cs[threadIdx.x] = cosf(theta); sn[threadIdx.x] = sinf(theta);
+        }
+        __syncthreads();
+        float * row = qkv + (size_t) t * p.qkv_stride;
+        for (int idx = threadIdx.x; idx < (H + HKV) * half; idx += 256) {
+            const int slot = idx / half, i = idx % half;
+            float * v = row + (size_t) slot * D;
+            const float x0 = v[i], x1 = v[i + half], c = cs[i], s = sn[i];
+            const float r0 = __fsub_rn(__fmul_rn(x0, c), __fmul_rn(x1, s)), r1 = __fadd_rn(__fmul_rn(x0, s), __fmul_rn(x1, c));
+            v[i] = r0; v[i + half] = r1;
+            if (slot >= H) {
+                const size_t o = ((size_t) pos * HKV + (slot - H)) * D;
+                kc[o + i] = r0; kc[o + i + half] = r1;
+                if (p.k16) { p.k16[o + i] = __float2half_rn(r0); p.k16[o + i + half] = __float2half_rn(r1); }
+            }
+        }
+        for (int idx = threadIdx.x; idx < HKV * D; idx += 256)
+            vc[(size_t) pos * HKV * D + idx] = row[(size_t) (H + HKV) * D + idx];
+    } else if (p.vt16) {
+        __shared__ __half sm[64][66];
+        const int tile = (int) blockIdx.x - N, tt = tile / HKV, kvh = tile % HKV;
+        const size_t cp = (size_t) ((p.n_ctx + 63) / 64 * 64);
+        for (int idx = threadIdx.x; idx < 64 * 64; idx += 256) {
+            const int tl = idx >> 6, d = idx & 63, t = tt * 64 + tl;
+            sm[tl][d] = t < N ? __float2half_rn(qkv[(size_t) t * p.qkv_stride + (size_t) (H + HKV + kvh) * 64 + d]) : __float2half_rn(0.f);
+        }
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < 64 * 64; idx += 256) {
+            const int d = idx >> 6, tl = idx & 63, t = tt * 64 + tl;
+            if (t < N) p.vt16[((size_t) kvh * 64 + d) * cp + n_past + t] = sm[tl][d];
+        }
+    }
+}
+
 void launch_rope_kv_append(float * qkv, float * k_cache, float * v_cache, const AttnParams & p, float theta_scale, cudaStream_t stream) {
     if (p.n_tok <= 0) return;
+    if (p.n_tok > 1 && p.head_dim <= 128 && (!p.vt16 || p.head_dim == 64)) {
+        const unsigned grid = (unsigned) (p.n_tok + (p.vt16 ? (p.n_tok + 63) / 64 * p.n_head_kv : 0));
+        rope_kv_append_batch_kernel<<<grid, 256, 0, stream>>>(qkv, k_cache, v_cache, p, theta_scale);
+        B200_CUDA_CHECK(cudaGetLastError());
+        return;
+    }
     dim3 grid((unsigned) (p.n_head + 2 * p.n_head_kv), (unsigned) p.n_tok);
     static bool set = false;
     if (!set) { B200_CUDA_CHECK(cudaFuncSetAttribute(rope_kv_append_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, B200_CARVEOUT)); set = true; }

@@ -13,8 +13,14 @@ HOOK = os.path.join(po.HERE, "_ref", "libfalcon_hook.so")
 
 
 @pytest.mark.skipif(not os.path.exists(HOOK), reason="oracle/_ref/libfalcon_hook.so not present (built where /root/reference exists)")
+@pytest.mark.parametrize("takeover", [True, False])
 @pytest.mark.parametrize("hp,wt,ftype", [(TINY_40B, po.Q4_K, 15), (TINY_7B, po.Q4_0, 2)])
-def test_reference_eval_runs_on_our_operator_surface(gpu, tmp_path, hp, wt, ftype):
+def test_reference_eval_runs_on_our_operator_surface(gpu, tmp_path, hp, wt, ftype, takeover, monkeypatch):
+    """takeover=True: from the second falcon_eval on, the hook recognises the Falcon graph and evaluates it whole on the device-resident
+    engine (ggml_surface.cu "whole-graph takeover"); False (B200_NO_TAKEOVER=1): every claimed node goes through the per-node protocol."""
+    if not takeover:
+        monkeypatch.setenv("B200_NO_TAKEOVER", "1")
+    taken0 = gpu.lib().b200_surface_takeover_evals()
     tensors = synth_model(hp, wt, seed=1234)
     path = str(tmp_path / "m.ggcc")
     ggcc.write_ggcc(path, hp, tensors, ftype=ftype)
@@ -43,4 +49,6 @@ def test_reference_eval_runs_on_our_operator_surface(gpu, tmp_path, hp, wt, ftyp
         tok = np.array([300 + i], np.int32)
         g, w = ref.eval(tok, 12 + i, n_threads=2), o.eval(tok, 12 + i, all_logits=True)
         assert np.abs(g - w).max() <= 3e-2 * S and np.median(np.abs(g - w)) <= 5e-3 * S
+    taken = gpu.lib().b200_surface_takeover_evals() - taken0
+    assert taken == (8 if takeover else 0), taken          # every eval after the first ("learning") one ran on the engine
     ref.close()
