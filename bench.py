@@ -17,6 +17,8 @@ Top level = the headline config (or the one --config selects):
             inside the timed region; N > 1: the last rank's host arg-max is broadcast before the next step may start)
   roofline: the dominant kernel (decode mat-vec) timed alone with CUDA events over the model's own matrices; step_frac = the whole
             step's algorithmic bytes / time against the measured HBM peak (the number the north-star target is about)
+  e2e_dropin: the same metric through the UNMODIFIED reference's own falcon_eval (libfalcon.cpp + ggml.c built with -DGGML_USE_CUBLAS)
+            running on top of this library's ggml_cuda_* operator surface -- the drop-in number
   cpu_baseline / --impl reference: the UNMODIFIED reference's CPU path (oracle/_ref falcon_eval) on the box's host cores over the
             REAL full-size model file (written to /dev/shm; identical layer tensors repeated, CPU time does not depend on values)
   prompt  : BASELINE config 3 (2048-token prompt, n_batch 512) with its own tensor roofline
@@ -160,43 +162,65 @@ def write_full_model(path, hp, wtype, rng):
     return sum(ggcc.tensor_nbytes(t, ne) for n, (t, ne, _) in tensors.items() if len(ne) == 2 and "word_embeddings" not in n)
 
 
-def reference_cpu_decode(model, wtype, steps, warmup, n_ctx_rope=129):
+class FullModelFile:
+    """the FULL-size random model as a GGCC file in /dev/shm for the reference-side arms (CPU baseline, drop-in run); falls back to a
+    6-layer slice ("extrapolated": true, tok/s scaled by the weight-byte ratio) only when /dev/shm cannot hold it or is too slow"""
+
+    def __init__(self, model, wtype):
+        self.model, self.wtype = model, wtype
+        hp_full = dict(MODELS[model])
+        self.full_bytes = weight_elems(hp_full) * BYTES_PER_WEIGHT[wtype]
+        need = self.full_bytes * 1.05 + hp_full["n_vocab"] * hp_full["n_embd"] * BYTES_PER_WEIGHT[wtype]
+        shm = "/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir()
+        st = os.statvfs(shm)
+        self.extrapolated = st.f_bavail * st.f_frsize < need * 1.1
+        if not self.extrapolated:                        # writing the file must stay a small part of a run that has to end within minutes
+            probe_path = os.path.join(shm, "b200_bench_probe_%d" % os.getpid())
+            t0 = time.time()
+            np.zeros(1 << 28, np.uint8).tofile(probe_path)
+            rate = (1 << 28) / max(time.time() - t0, 1e-3)
+            os.unlink(probe_path)
+            self.extrapolated = need / rate > float(os.environ.get("BENCH_REF_MAX_WRITE_S", "100"))
+        self.hp = dict(hp_full, n_layer=6) if self.extrapolated else hp_full
+        self.path = os.path.join(shm if not self.extrapolated else tempfile.gettempdir(), "b200_bench_ref_%d.ggcc" % os.getpid())
+        t0 = time.time()
+        self.sample_bytes = write_full_model(self.path, self.hp, wtype, np.random.default_rng(1))
+        self.write_s = time.time() - t0
+        self.scale = self.sample_bytes / self.full_bytes
+
+    def what(self):
+        return ("the %s random-init %s %s GGCC model (%.2f GB of weights, %s)"
+                % ("FULL %d-layer" % self.hp["n_layer"] if not self.extrapolated else "%d-layer slice of the" % self.hp["n_layer"], self.model,
+                   TYPE_NAME[self.wtype], self.sample_bytes / 1e9,
+                   "no extrapolation" if not self.extrapolated else "tok/s scaled by the weight-byte ratio %.4f" % self.scale))
+
+    def close(self):
+        if os.path.exists(self.path):
+            os.unlink(self.path)
+
+
+def reference_cpu_decode(model, wtype, steps, warmup, n_ctx_rope=129, mf=None):
     """The UNMODIFIED reference's CPU path (falcon_eval from oracle/_ref/libfalcon_ref.so; the oracle port if that library is absent)
-    decoding with n_batch = 1 over the full-size random model.  Falls back to a layer slice scaled by bytes ("extrapolated": true)
-    only when /dev/shm cannot hold the file."""
+    decoding with n_batch = 1 over the full-size random model file."""
     po = _oracle()
     kind = "reference" if po.have_ref_falcon() else "port"
-    hp_full = dict(MODELS[model])
-    full_bytes = weight_elems(hp_full) * BYTES_PER_WEIGHT[wtype]
-    need = full_bytes * 1.05 + hp_full["n_vocab"] * hp_full["n_embd"] * BYTES_PER_WEIGHT[wtype]
-    shm = "/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir()
-    st = os.statvfs(shm)
-    extrapolated = st.f_bavail * st.f_frsize < need * 1.1
-    if not extrapolated:                             # writing the file must stay a small part of a run that has to end within minutes
-        probe_path = os.path.join(shm, "b200_bench_probe_%d" % os.getpid())
-        t0 = time.time()
-        np.zeros(1 << 28, np.uint8).tofile(probe_path)
-        rate = (1 << 28) / max(time.time() - t0, 1e-3)
-        os.unlink(probe_path)
-        extrapolated = need / rate > float(os.environ.get("BENCH_REF_MAX_WRITE_S", "100"))
-    hp = dict(hp_full, n_layer=6) if extrapolated else hp_full
+    own = mf is None
+    if own:
+        mf = FullModelFile(model, wtype)
     cores = _host_threads()
-    rng = np.random.default_rng(1)
     t0 = time.time()
-    path = os.path.join(shm if not extrapolated else tempfile.gettempdir(), "b200_bench_ref_%d.ggcc" % os.getpid())
     try:
-        sample_bytes = write_full_model(path, hp, wtype, rng)
         if kind == "reference":
-            eng = po.RefFalcon(path, n_ctx=256, n_batch=1)
+            eng = po.RefFalcon(mf.path, n_ctx=256, n_batch=1)
             run = lambda tok, pos, t: eng.eval(np.array([tok], np.int32), pos, n_threads=t, n_max_real_ctx=n_ctx_rope)
         else:
             import ggllm_cpp_b200.ggcc as ggcc
-            _, tensors = ggcc.read_ggcc(path)
-            eng = po.OrcFalcon(hp, tensors, n_ctx=256)
+            _, tensors = ggcc.read_ggcc(mf.path)
+            eng = po.OrcFalcon(mf.hp, tensors, n_ctx=256)
             run = lambda tok, pos, t: eng.eval(np.array([tok], np.int32), pos, n_ctx_rope=n_ctx_rope, nthreads=min(t, 64))
         run(11, 0, min(cores, 32))                      # the reference's own warm-up eval (falcon_main.cpp:662-673): also faults the file in
         # thread count: ggml's spin-barrier pool does not scale monotonically with threads (README.md:137) -- probe, keep the fastest
-        pos, best_t, probe = 1, min(cores, 32), {}
+        pos, probe = 1, {}
         for t in sorted(set(min(cores, c) for c in (8, 16, 32, 64, 128))):
             t1 = time.time()
             run(50 + t, pos, t); pos += 1
@@ -213,17 +237,45 @@ def reference_cpu_decode(model, wtype, steps, warmup, n_ctx_rope=129):
         if kind == "reference":
             eng.close()
     finally:
-        if os.path.exists(path):
-            os.unlink(path)
-    scale = sample_bytes / full_bytes
-    tps = steps / dt * scale
-    return dict(value=tps, unit="tok/s", cores=best_t, kind=kind, ms_per_step=1e3 / tps, steps=steps, extrapolated=bool(extrapolated),
-                sample=("%d decode tokens (after BOS + %d probe + %d warm-up evals) of the %s random-init %s %s GGCC model (%.2f GB of weights, %s) "
-                        "through %s falcon_eval, -t %d (fastest of %s on %d host cores); setup %.0f s")
-                       % (steps, len(probe), warmup, "FULL %d-layer" % hp["n_layer"] if not extrapolated else "%d-layer slice of the" % hp["n_layer"],
-                          model, TYPE_NAME[wtype], sample_bytes / 1e9, "no extrapolation" if not extrapolated else "tok/s scaled by the weight-byte ratio %.4f" % scale,
-                          "the unmodified reference's (oracle/_ref)" if kind == "reference" else "the oracle port's", best_t,
-                          {k: round(v, 3) for k, v in probe.items()}, cores, t1 - t0))
+        if own:
+            mf.close()
+    tps = steps / dt * mf.scale
+    return dict(value=tps, unit="tok/s", cores=best_t, kind=kind, ms_per_step=1e3 / tps, steps=steps, extrapolated=bool(mf.extrapolated),
+                sample=("%d decode tokens (after BOS + %d probe + %d warm-up evals) of %s through %s falcon_eval, -t %d (fastest of %s on %d host cores); "
+                        "file written in %.0f s, load + evals %.0f s")
+                       % (steps, len(probe), warmup, mf.what(), "the unmodified reference's (oracle/_ref)" if kind == "reference" else "the oracle port's", best_t,
+                          {k: round(v, 3) for k, v in probe.items()}, cores, mf.write_s, time.time() - t0))
+
+
+def dropin_decode(cx, mf, steps, warmup, n_ctx_rope=129):
+    """The drop-in number: the UNMODIFIED reference (ggml.c + libfalcon.cpp built with -DGGML_USE_CUBLAS, oracle/_ref/libfalcon_hook.so) loads the
+    same GGCC file with every layer offloaded and decodes through ITS OWN falcon_eval; the ggml_cuda_* symbols it calls are this
+    library's.  After the first eval the operator hook recognises the Falcon graph and evaluates it whole on the device (ggml_surface.cu)."""
+    po = _oracle()
+    hook = os.path.join(po.HERE, "_ref", "libfalcon_hook.so")
+    if not os.path.exists(hook):
+        return {"unavailable": "oracle/_ref/libfalcon_hook.so not built (needs /root/reference at build time)"}
+    L = cx.b.lib()                                      # libggml_b200.so in the global symbol scope: resolves the hook library's ggml_cuda_*
+    t0 = time.time()
+    eng = po.RefFalcon(mf.path, n_ctx=2048, n_batch=1, hook=True, n_gpu_layers=mf.hp["n_layer"] + 2)
+    load_s = time.time() - t0
+    taken0 = L.b200_surface_takeover_evals()
+    eng.eval(np.array([11], np.int32), 0, n_threads=1, n_max_real_ctx=n_ctx_rope)      # falcon_main's BOS warm-up eval = the hook's learning eval (per-node path)
+    pos = 1
+    for i in range(warmup):
+        eng.eval(np.array([100 + i], np.int32), pos, n_threads=1, n_max_real_ctx=n_ctx_rope); pos += 1
+    t1 = time.perf_counter()
+    for i in range(steps):
+        eng.eval(np.array([200 + i], np.int32), pos, n_threads=1, n_max_real_ctx=n_ctx_rope); pos += 1
+    dt = time.perf_counter() - t1
+    taken = L.b200_surface_takeover_evals() - taken0
+    eng.close()
+    tps = steps / dt * mf.scale
+    return {"value": tps, "unit": "tok/s", "ms_per_step": 1e3 / tps, "steps": steps, "engine_evals": int(taken), "extrapolated": bool(mf.extrapolated),
+            "load_seconds": load_s, "h2d_bytes_per_step": 8, "d2h_bytes_per_step": mf.hp["n_vocab"] * 4,
+            "api": "falcon_eval of the unmodified reference (-t 1, every layer offloaded) on top of libggml_b200.so's ggml_cuda_* surface",
+            "what": "%d decode tokens of %s; %d of %d evals after the first ran as whole-graph device evaluations behind ggml_cuda_compute_forward"
+                    % (steps, mf.what(), taken, steps + warmup)}
 
 
 def reference_cpu_matvec(K=4096, M=4096, n_mats=32, iters=8):
@@ -635,11 +687,20 @@ def main():
     if out_extra:
         out["configs"] = out_extra
     if world == 1 and extras and not args.no_cpu_baseline and sel in DECODE_CONFIGS:
+        mf = None
         try:
-            r = reference_cpu_decode(model, wtype, steps=8, warmup=2, n_ctx_rope=rope)
+            mf = FullModelFile(model, wtype)
+            try:
+                out["e2e_dropin"] = dropin_decode(cx, mf, steps=max(8, min(args.steps, 64)), warmup=3, n_ctx_rope=rope)
+            except Exception as ex:
+                out["e2e_dropin"] = {"error": repr(ex)}
+            r = reference_cpu_decode(model, wtype, steps=8, warmup=2, n_ctx_rope=rope, mf=mf)
             out["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample", "extrapolated")}
         except Exception as ex:       # the baseline is reporting only; never let it take the GPU number down
             out["cpu_baseline"] = {"value": None, "unit": "tok/s", "cores": 0, "kind": "reference", "sample": "failed: %r" % (ex,)}
+        finally:
+            if mf is not None:
+                mf.close()
     print(json.dumps(out))
 
 

@@ -155,8 +155,17 @@ struct Takeover {
     bool active = false, launched = false;              // this eval is being evaluated by the engine
     int valid_upto = 0, n_vocab = 0, n_batch = 0;
     float * logits = nullptr; size_t logits_floats = 0; // pinned
-    long evals_taken = 0;
+    long evals_taken = 0;                               // by this engine (the cumulative count for tests / bench is g_tk_total)
 } g_tk;
+long g_tk_total = 0;
+
+// a model is being (un)loaded: whatever engine exists borrows planes of the old one
+void tk_reset() {
+    if (b200_takeover_engine) { b200_falcon_free(b200_takeover_engine); b200_takeover_engine = nullptr; }
+    float * lg = g_tk.logits; const size_t lf = g_tk.logits_floats;
+    g_tk = Takeover{};
+    g_tk.logits = lg; g_tk.logits_floats = lf;
+}
 
 bool is_model_name(const char * n) { return strncmp(n, "transformer.", 12) == 0 || strcmp(n, "lm_head.weight") == 0; }
 void tk_note(const abi::tensor * t) { if (t && t->name[0] && is_model_name(t->name)) g_tk.named[t->name] = t; }
@@ -258,7 +267,7 @@ bool tk_node(const abi::compute_params * params, abi::tensor * t) {
         if (b200_falcon_eval(b200_takeover_engine, g_tk.tokens.data(), g_tk.N, g_tk.n_past, g_tk.rope_ctx, lg, 1) != 0) {
             fprintf(stderr, "b200: engine eval failed behind ggml_cuda_compute_forward (N %d, n_past %d)\n", g_tk.N, g_tk.n_past); abort();
         }
-        g_tk.valid_upto = g_tk.n_past + g_tk.N; g_tk.launched = true; g_tk.evals_taken++;
+        g_tk.valid_upto = g_tk.n_past + g_tk.N; g_tk.launched = true; g_tk.evals_taken++; g_tk_total++;
     }
     if (strcmp(t->name, "result_lm_head") == 0) {
         B200_ASSERT(g_tk.launched && contiguous_f32(t) && nelements(t) == (int64_t) g_tk.N * g_tk.n_vocab);
@@ -281,7 +290,7 @@ void tk_finish_learning() {
         }
     }
     if (b200_takeover_engine) { b200_falcon_free(b200_takeover_engine); b200_takeover_engine = nullptr; }
-    g_tk.state = Takeover::DISABLED;
+    g_tk.state = Takeover::DISABLED;                                         // until the next model load (tk_reset)
 }
 
 } // namespace
@@ -289,7 +298,7 @@ void tk_finish_learning() {
 extern "C" {
 
 // test / bench hook: number of evals the engine has run behind ggml_cuda_compute_forward (0 = per-node path only)
-long b200_surface_takeover_evals(void) { return g_tk.evals_taken; }
+long b200_surface_takeover_evals(void) { return g_tk_total; }
 
 const GPUStatus * ggml_cuda_get_system_gpu_status(void) { return &g_status; }
 
@@ -353,6 +362,7 @@ int ggml_cuda_pool_purge_buffers_with_access_count(int, int) { return 0; }
 void ggml_cuda_transform_tensor(void * data, struct ggml_tensor * t_) {
     abi::tensor * t = (abi::tensor *) t_;
     ensure_init();
+    if (b200_takeover_engine || g_tk.state != Takeover::OFF) tk_reset();     // a (new) model is loading
     B200_ASSERT(t->backend == abi::BACKEND_GPU || t->backend == abi::BACKEND_GPU_SPLIT);
     B200_ASSERT(t->ne[2] == 1 && t->ne[3] == 1);
     DeviceTensor * d = new DeviceTensor();
@@ -374,7 +384,7 @@ void ggml_cuda_transform_tensor(void * data, struct ggml_tensor * t_) {
 void ggml_cuda_free_data(struct ggml_tensor * t_) {
     abi::tensor * t = (abi::tensor *) t_;
     if (!on_gpu(t) || !t->extra) return;
-    if (b200_takeover_engine) { b200_falcon_free(b200_takeover_engine); b200_takeover_engine = nullptr; g_tk = Takeover{}; }   // it borrows these planes
+    if (b200_takeover_engine || g_tk.state != Takeover::OFF) tk_reset();     // the engine borrows these planes
     DeviceTensor * d = owned(t);
     if (d) { if (d->kind == 0) wplanes_free(d->W); else cudaFree(d->f32); delete d; }
     delete (ggml_tensor_extra_gpu *) t->extra;

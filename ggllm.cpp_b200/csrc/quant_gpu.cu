@@ -9,6 +9,7 @@
 #include "kernels.h"
 
 cudaStream_t b200_current_stream();
+bool launch_quantize_kquant(int ggml_type, const float * x_dev, void * blocks_dev, int64_t n_elems, cudaStream_t s);
 
 __device__ __forceinline__ int rne_int_dev(float v) {                 // nearest_int: the 1.5 * 2^23 magic constant
     const float t = __fadd_rn(v, 12582912.f);
@@ -112,7 +113,7 @@ extern "C" int b200_quantize_weights(int ggml_type, const float * x_dev, void * 
     } else if (ggml_type == T_Q4_K && n_elems % 256 == 0) {
         const int64_t nb = n_elems / 256;
         quantize_q4_K_kernel<<<(unsigned) ((nb + 63) / 64), 64, 0, s>>>(x_dev, (uint8_t *) blocks_dev, nb);
-    } else return 0;
+    } else return launch_quantize_kquant(ggml_type, x_dev, blocks_dev, n_elems, s) ? 1 : 0;      // Q2_K / Q3_K / Q5_K / Q6_K: quant_gpu_k.cu
     B200_CUDA_CHECK(cudaGetLastError());
     return 1;
 }

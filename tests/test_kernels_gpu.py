@@ -374,9 +374,10 @@ def test_full_size_gemm_tensor_core_vs_cuda_core(gpu, K, M, N):
     assert np.median(np.abs(a - b)) <= 5e-6 * grow * scale, (float(np.median(np.abs(a - b))), scale)
 
 
-@pytest.mark.parametrize("t", [po.Q4_0, po.Q4_K])
+@pytest.mark.parametrize("t", [po.Q4_0, po.Q4_K, po.Q2_K, po.Q3_K, po.Q5_K, po.Q6_K])
 def test_device_weight_quantiser_bit_exact(gpu, orc, t):
-    """b200_quantize_weights writes the reference quantiser's blocks bit for bit (ggml.c:927-962, k_quants.c:542-605):
+    """b200_quantize_weights writes the reference quantiser's blocks bit for bit (ggml.c:927-962, k_quants.c:275-342, 396-470, 542-605,
+    652-732, 781-843):
     normal, tiny, huge, zero, constant, one-sided and the reference test's 0.1 + 2 cos(i) data (tests/test-quantize-fns.cpp:26-32)"""
     K, rng = 4096, np.random.default_rng(t)
     rows = [rng.standard_normal(K), 1e-8 * rng.standard_normal(K), 1e8 * rng.standard_normal(K), np.zeros(K), np.full(K, 0.37),
@@ -388,4 +389,4 @@ def test_device_weight_quantiser_bit_exact(gpu, orc, t):
     assert gpu.lib().b200_quantize_weights(t, xd.ptr, out.ptr, w.size) == 1
     got = out.download(np.uint8, want.shape)
     assert np.array_equal(got, want), int((got != want).sum())
-    assert gpu.lib().b200_quantize_weights(po.Q6_K, xd.ptr, out.ptr, w.size) == 0       # no device quantiser for this type yet
+    assert gpu.lib().b200_quantize_weights(po.Q8_0, xd.ptr, out.ptr, w.size) == 0       # no device quantiser for this type: the caller quantises on the host
