@@ -18,12 +18,13 @@ PART_A = ["b200_event_create", "b200_event_destroy", "b200_event_record", "b200_
           "b200_memcpy_d2h", "b200_memset", "b200_host_malloc", "b200_host_free", "b200_weight_upload", "b200_weight_random",
           "b200_weight_free", "b200_weight_device_bytes", "b200_dequantize_rows", "b200_actq_alloc", "b200_actq_free",
           "b200_quantize_act", "b200_actq_download", "b200_mul_mat", "b200_mul_mat_f16", "b200_mul_mat_vec_fused", "b200_mul_mat_vec_q", "b200_mul_mat_vec_q_chain", "b200_quantize_weights", "b200_mmv_max_n", "b200_layernorm",
-          "b200_gelu", "b200_add", "b200_rope_neox", "b200_attention", "b200_layernorm_q", "b200_attention_decode"]
+          "b200_gelu", "b200_add", "b200_rope_neox", "b200_attention", "b200_layernorm_q", "b200_attention_decode",
+          "b200_sampler_create", "b200_sampler_sample", "b200_sampler_free"]
 PART_B = ["b200_falcon_create", "b200_falcon_set_tensor", "b200_falcon_set_tensor_random", "b200_falcon_load_ggcc",
           "b200_ggcc_read_hparams", "b200_falcon_free", "b200_falcon_weight_bytes", "b200_nccl_unique_id",
           "b200_falcon_init_pipeline", "b200_falcon_eval", "b200_falcon_decode_dev", "b200_falcon_logits_dev", "b200_falcon_generate_greedy",
           "b200_falcon_last_launches", "b200_falcon_last_ms", "b200_falcon_stream", "b200_falcon_profile_matvec",
-          "b200_falcon_kv_read", "b200_falcon_kv_write", "b200_falcon_kv_fill_random"]
+          "b200_falcon_kv_read", "b200_falcon_kv_write", "b200_falcon_kv_fill_random", "b200_falcon_generate", "b200_falcon_load_seconds", "b200_falcon_save_kv", "b200_falcon_load_kv"]
 
 
 def build(verbose=False):
@@ -62,6 +63,10 @@ def lib():
             "b200_attention_decode": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]),
             "b200_falcon_kv_read": (i32, [vp, i32, i32, i32, vp, vp]), "b200_falcon_kv_write": (i32, [vp, i32, i32, i32, vp, vp]),
             "b200_falcon_kv_fill_random": (i32, [vp, i32, i32, C.c_uint64]),
+            "b200_sampler_create": (vp, [vp, vp, i32]), "b200_sampler_sample": (i32, [vp, vp, i32]), "b200_sampler_free": (None, [vp]),
+            "b200_falcon_generate": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, vp]),
+            "b200_falcon_load_seconds": (C.c_double, [vp, vp]),
+            "b200_falcon_save_kv": (i32, [vp, C.c_char_p, i32]), "b200_falcon_load_kv": (i32, [vp, C.c_char_p]),
             "b200_falcon_create": (vp, [vp]), "b200_falcon_set_tensor": (None, [vp, C.c_char_p, i32, i32, vp, vp]),
             "b200_falcon_set_tensor_random": (None, [vp, C.c_char_p, i32, C.c_uint64]),
             "b200_falcon_load_ggcc": (i32, [vp, C.c_char_p]), "b200_ggcc_read_hparams": (i32, [C.c_char_p, vp]),
@@ -201,6 +206,39 @@ class ActQ:
             pass
 
 
+class SamplingParams(C.Structure):
+    """b200_sampling_params: falcon_main's defaults (examples/falcon_common.h: top_k 40, top_p 0.95, temp 0.8, repeat_penalty 1.1, repeat_last_n 64)"""
+    _fields_ = [("top_k", C.c_int32), ("top_p", C.c_float), ("temp", C.c_float), ("repeat_penalty", C.c_float), ("repeat_last_n", C.c_int32), ("seed", C.c_uint32)]
+
+    def __init__(self, top_k=40, top_p=0.95, temp=0.8, repeat_penalty=1.1, repeat_last_n=64, seed=1):
+        super().__init__(top_k, top_p, temp, repeat_penalty, repeat_last_n, seed)
+
+
+class Sampler:
+    """stand-alone device sampler over logits rows in HBM (b200_sampler_*)"""
+
+    def __init__(self, params, last_tokens=()):
+        self.L = lib()
+        lt = np.ascontiguousarray(last_tokens, dtype=np.int32)
+        self.h = self.L.b200_sampler_create(C.byref(params), _np_ptr(lt) if lt.size else None, lt.size)
+        if not self.h:
+            raise ValueError("b200_sampler_create: bad sampling parameters")
+
+    def sample(self, logits_dev_ptr, n_vocab):
+        return int(self.L.b200_sampler_sample(self.h, logits_dev_ptr, n_vocab))
+
+    def free(self):
+        if self.h:
+            self.L.b200_sampler_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
 class FalconParams(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("n_vocab", "n_embd", "n_head", "n_head_kv", "n_layer", "falcon_type", "n_ctx", "n_batch",
                                           "layer_first", "layer_last", "rank", "world")]
@@ -237,6 +275,11 @@ class Falcon:
         if self.L.b200_falcon_load_ggcc(self.h, path.encode()) != 0:
             raise RuntimeError("failed to load " + path)
 
+    def load_stats(self):
+        """-> (seconds, quantised-matrix bytes) of the last load_ggcc"""
+        by = C.c_size_t(0)
+        return float(self.L.b200_falcon_load_seconds(self.h, C.byref(by))), by.value
+
     def set_tensor(self, name, ggml_type, ne, data):
         data = np.ascontiguousarray(data)
         ne_a = (C.c_int64 * 2)(ne[0], ne[1] if len(ne) > 1 else 1)
@@ -266,6 +309,15 @@ class Falcon:
             raise RuntimeError("b200_falcon_generate_greedy failed (rc=%d)" % rc)
         return out
 
+    def generate(self, params, last_tokens, first_token, n_past, n_steps, n_ctx_rope=0):
+        """generation with the sampling chain on the device (b200_falcon_generate); last_tokens seed the repetition-penalty window"""
+        out = np.zeros(n_steps, dtype=np.int32)
+        lt = np.ascontiguousarray(last_tokens, dtype=np.int32)
+        rc = self.L.b200_falcon_generate(self.h, C.byref(params), _np_ptr(lt) if lt.size else None, lt.size, int(first_token), n_past, n_steps, n_ctx_rope, _np_ptr(out))
+        if rc != 0:
+            raise RuntimeError("b200_falcon_generate failed (rc=%d)" % rc)
+        return out
+
     def decode_dev(self, token_dev_ptr, n_past, n_ctx_rope=0):
         if self.L.b200_falcon_decode_dev(self.h, token_dev_ptr, n_past, n_ctx_rope) != 0:
             raise RuntimeError("b200_falcon_decode_dev: n_past %d outside [0, n_ctx)" % n_past)
@@ -282,6 +334,16 @@ class Falcon:
         k, v = np.ascontiguousarray(k, np.float32), np.ascontiguousarray(v, np.float32)
         if self.L.b200_falcon_kv_write(self.h, layer, pos, k.shape[0], _np_ptr(k), _np_ptr(v)) != 0:
             raise RuntimeError("b200_falcon_kv_write: bad layer / range")
+
+    def save_kv(self, path, n_tokens):
+        if self.L.b200_falcon_save_kv(self.h, path.encode(), n_tokens) != 0:
+            raise RuntimeError("b200_falcon_save_kv failed")
+
+    def load_kv(self, path):
+        n = self.L.b200_falcon_load_kv(self.h, path.encode())
+        if n < 0:
+            raise RuntimeError("b200_falcon_load_kv: missing / truncated / mismatching session file")
+        return n
 
     def kv_fill_random(self, pos, n, seed=1):
         if self.L.b200_falcon_kv_fill_random(self.h, pos, n, seed) != 0:

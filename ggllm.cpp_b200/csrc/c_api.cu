@@ -227,6 +227,31 @@ void b200_attention(float * qkv, float * kc, float * vc, float * out, int n_head
     }
 }
 
+// ---- stand-alone sampler over a logits row on the device (the engine's generation loop runs the same kernel inside its step graph)
+struct b200_sampler { SamplerState * st; SamplerParams p; float * work; size_t work_floats; int32_t * out; };
+b200_sampler * b200_sampler_create(const b200_sampling_params * sp, const int32_t * last_tokens, int n_last) {
+    if (!sp || sp->top_k < 1 || sp->top_k > 1024 || sp->repeat_last_n < 0 || sp->repeat_last_n > B200_SAMPLER_MAX_WINDOW || n_last < 0) return nullptr;
+    b200_sampler * s = new b200_sampler();
+    s->st = sampler_state_alloc(); s->p = { sp->top_k, sp->top_p, sp->temp, sp->repeat_penalty }; s->work = nullptr; s->work_floats = 0;
+    B200_CUDA_CHECK(cudaMalloc(&s->out, 4));
+    int32_t * w = nullptr;
+    if (n_last > 0) { B200_CUDA_CHECK(cudaMalloc(&w, (size_t) n_last * 4)); B200_CUDA_CHECK(cudaMemcpyAsync(w, last_tokens, (size_t) n_last * 4, cudaMemcpyHostToDevice, g_stream)); }
+    launch_sampler_init(s->st, sp->seed, w, n_last, sp->repeat_last_n, g_stream);
+    B200_CUDA_CHECK(cudaStreamSynchronize(g_stream));
+    if (w) B200_CUDA_CHECK(cudaFree(w));
+    return s;
+}
+int32_t b200_sampler_sample(b200_sampler * s, const float * logits_dev, int n_vocab) {
+    if ((size_t) n_vocab > s->work_floats) { if (s->work) B200_CUDA_CHECK(cudaFree(s->work)); s->work_floats = (size_t) n_vocab; B200_CUDA_CHECK(cudaMalloc(&s->work, s->work_floats * 4)); }
+    if (s->p.top_k > n_vocab) s->p.top_k = n_vocab;
+    launch_sample(logits_dev, n_vocab, s->p, s->st, s->work, s->out, nullptr, nullptr, g_stream);
+    int32_t id = -1;
+    B200_CUDA_CHECK(cudaMemcpyAsync(&id, s->out, 4, cudaMemcpyDeviceToHost, g_stream));
+    B200_CUDA_CHECK(cudaStreamSynchronize(g_stream));
+    return id;
+}
+void b200_sampler_free(b200_sampler * s) { if (!s) return; sampler_state_free(s->st); cudaFree(s->work); cudaFree(s->out); delete s; }
+
 // the decode step's LayerNorm node exactly as the engine launches it (cluster kernel for one row of <= 8192 values, register
 // kernel otherwise): [x = (ra + rb) + x] ; a1 = Q(norm(x) * g1 + b1) ; a2 = Q(norm(x) * g2 + b2) (a2 optional)
 void b200_layernorm_q(float * x, int64_t x_stride, const float * ra, const float * rb, const float * g1, const float * b1, b200_actq * a1,

@@ -21,8 +21,11 @@
 #include <sys/mman.h>
 #include <sys/stat.h>
 #include <unistd.h>
+#include <atomic>
+#include <chrono>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 cudaStream_t b200_current_stream();
@@ -82,11 +85,14 @@ struct b200_falcon {
     cudaGraphExec_t graph[3] = { nullptr, nullptr, nullptr }; float graph_theta[3] = { -1.f, -1.f, -1.f }; int graph_launches = 0;
     bool ring_mode = false;                     // set while the generation-step graph is being captured
     int32_t * tok_next = nullptr, * gen_hist = nullptr; int * gen_step = nullptr;   // sampled id, ids so far, step counter (device)
+    SamplerState * sampler = nullptr; SamplerParams sampler_p{}; bool use_sampler = false; float * sampler_work = nullptr;   // generation with the sampling chain (sampling.cu)
     int act_type = -1;
     unsigned * q_ctr = nullptr;                 // chunk counters of the quantise-on-completion epilogue (ffn_up -> ffn_down)
     ncclComm_t comm = nullptr;
     int launches = 0; float last_ms = 0.f;
     size_t weight_bytes = 0;
+    double load_seconds = 0.0; size_t load_bytes = 0;   // b200_falcon_load_ggcc
+    size_t pending_floats = 0;                  // logits of the eval in flight (falcon_eval_begin / finish)
     std::vector<const void *> borrowed;         // device planes adopted from another owner (ggml_cuda_transform_tensor): never freed here
 };
 
@@ -251,6 +257,22 @@ extern "C++" bool falcon_adopt_matrix(b200_falcon * f, const char * name, const 
     return true;
 }
 
+static double wall_seconds() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+// the engine's matrix slot for `s` with freshly allocated (unfilled) planes of `type`; nullptr when the tensor belongs to another rank
+static WPlanes * place_matrix_alloc(b200_falcon * f, const Slot & s, int type) {
+    if (s.layer >= 0 && (s.layer < f->hp.layer_first || s.layer >= f->hp.layer_last)) return nullptr;
+    if ((s.kind == 0 && !f->first) || (s.kind == 3 && !f->last)) return nullptr;
+    int64_t K, M; expected_shape(f, s, K, M);
+    invalidate_graphs(f);
+    Layer * L = s.layer >= 0 ? &f->layers[s.layer - f->hp.layer_first] : nullptr;
+    WPlanes & W = s.kind == 0 ? f->tok_emb : s.kind == 3 ? f->lm_head : s.kind == 14 ? L->wqkv : s.kind == 15 ? L->wo : s.kind == 16 ? L->up : L->down;
+    if (W.p[0]) { if (s.kind != 0) f->weight_bytes -= algorithmic_bytes(W.type, W.K, W.M); free_matrix(f, W); }
+    wplanes_upload(W, type, (int) K, (int) M, nullptr, f->s_main);              // allocation + layout only
+    if (s.kind != 0) { f->weight_bytes += algorithmic_bytes(type, K, M); note_act_type(f, type); }
+    return &W;
+}
+
 static void place_tensor(b200_falcon * f, const Slot & s, int type, const void * host_data, bool random, uint64_t seed) {
     const bool is_layer = s.layer >= 0;
     if (is_layer && (s.layer < f->hp.layer_first || s.layer >= f->hp.layer_last)) return;
@@ -301,54 +323,124 @@ void b200_falcon_set_tensor_random(b200_falcon * f, const char * name, int type,
     place_tensor(f, s, type, nullptr, true, seed);
 }
 
-// ---- GGCC v10 reader (libfalcon.cpp:770-973): header, vocab, merges, then {n_dims, name_len, type, ne[], name, pad32, data}
-struct Cursor { const uint8_t * p; size_t off, size;
-    uint32_t u32() { B200_ASSERT(off + 4 <= size); uint32_t v; memcpy(&v, p + off, 4); off += 4; return v; } };
+// ---- GGCC v10 reader (libfalcon.cpp:770-973): header, vocab, merges, then {n_dims, name_len, type, ne[], name, pad32, data}.
+// The file is untrusted input: every read is bounds-checked and a malformed file makes the loaders return -1 (no assert, no leak).
+struct Cursor { const uint8_t * p; size_t off, size; bool bad;
+    uint32_t u32() { if (off + 4 > size) { bad = true; return 0; } uint32_t v; memcpy(&v, p + off, 4); off += 4; return v; }
+    void skip(size_t n) { if (n > size - off) bad = true; else off += n; } };
 static int ggcc_header(Cursor & c, b200_falcon_params * out) {
-    if (c.u32() != 0x67676363u || c.u32() != 10u) return -1;
+    if (c.u32() != 0x67676363u || c.u32() != 10u || c.bad) return -1;
     out->n_vocab = (int32_t) c.u32(); out->n_embd = (int32_t) c.u32(); out->n_head = (int32_t) c.u32(); out->n_head_kv = (int32_t) c.u32();
     out->n_layer = (int32_t) c.u32(); out->falcon_type = (int32_t) c.u32();
     c.u32(); /* ftype */ c.u32(); /* n_bpe_merges */
-    return 0;
+    return c.bad ? -1 : 0;
 }
 int b200_ggcc_read_hparams(const char * path, b200_falcon_params * out) {
     FILE * fp = fopen(path, "rb");
     if (!fp) return -1;
     uint8_t buf[40]; const size_t n = fread(buf, 1, sizeof(buf), fp); fclose(fp);
     if (n < 40) return -1;
-    Cursor c = { buf, 0, n };
+    Cursor c = { buf, 0, n, false };
     return ggcc_header(c, out);
 }
+
+// GPU-direct weight path (replaces the loader's per-tensor blocking cudaMemcpy, libfalcon.cpp:1196-1270 +
+// ggml-cuda.cu:3030-3073): the file is mapped, every matrix's planes are allocated up front, then LOAD_THREADS host threads stream row
+// chunks  page cache -> pinned ring buffer -> cudaMemcpyAsync -> repack kernel (AoS blocks -> planar layout, formats.cuh)  each on its
+// own stream with two buffers in flight, so the host copy of chunk i+1 overlaps the DMA and repack of chunk i; one synchronize at the end.
+struct LoadItem { WPlanes * W; const uint8_t * src; int64_t row0, nrows; size_t bytes; };
+static constexpr size_t LOAD_BUF = 32u << 20;
+static constexpr int LOAD_THREADS = 6, LOAD_SLOTS = 2;
+
+static void load_worker(int dev, const std::vector<LoadItem> * items, std::atomic<size_t> * next) {
+    B200_CUDA_CHECK(cudaSetDevice(dev));
+    cudaStream_t st; B200_CUDA_CHECK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    uint8_t * pin[LOAD_SLOTS], * stage[LOAD_SLOTS]; cudaEvent_t done[LOAD_SLOTS]; bool used[LOAD_SLOTS] = {};
+    for (int k = 0; k < LOAD_SLOTS; k++) {
+        B200_CUDA_CHECK(cudaMallocHost(&pin[k], LOAD_BUF)); B200_CUDA_CHECK(cudaMalloc(&stage[k], LOAD_BUF));
+        B200_CUDA_CHECK(cudaEventCreateWithFlags(&done[k], cudaEventDisableTiming));
+    }
+    for (int n = 0;; n++) {
+        const size_t i = next->fetch_add(1);
+        if (i >= items->size()) break;
+        const LoadItem & it = (*items)[i];
+        const int k = n % LOAD_SLOTS;
+        if (used[k]) B200_CUDA_CHECK(cudaEventSynchronize(done[k]));          // the DMA that read this pinned buffer (and the repack behind it) is finished
+        memcpy(pin[k], it.src, it.bytes);                                      // page cache / mmap -> pinned
+        B200_CUDA_CHECK(cudaMemcpyAsync(stage[k], pin[k], it.bytes, cudaMemcpyHostToDevice, st));
+        launch_repack_rows(*it.W, stage[k], it.row0, it.nrows, st);
+        B200_CUDA_CHECK(cudaEventRecord(done[k], st)); used[k] = true;
+    }
+    B200_CUDA_CHECK(cudaStreamSynchronize(st));
+    for (int k = 0; k < LOAD_SLOTS; k++) { cudaFreeHost(pin[k]); cudaFree(stage[k]); cudaEventDestroy(done[k]); }
+    cudaStreamDestroy(st);
+}
+
 int b200_falcon_load_ggcc(b200_falcon * f, const char * path) {
     const int fd = open(path, O_RDONLY);
     if (fd < 0) { fprintf(stderr, "b200: cannot open %s\n", path); return -1; }
-    struct stat sb; fstat(fd, &sb);
+    struct stat sb;
+    if (fstat(fd, &sb) != 0 || sb.st_size < 40) { close(fd); return -1; }
     void * map = mmap(nullptr, (size_t) sb.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
     close(fd);
     if (map == MAP_FAILED) return -1;
-    Cursor c = { (const uint8_t *) map, 0, (size_t) sb.st_size };
+    auto fail = [&](const char * why) { fprintf(stderr, "b200: %s: %s\n", path, why); munmap(map, (size_t) sb.st_size); return -1; };
+    Cursor c = { (const uint8_t *) map, 0, (size_t) sb.st_size, false };
     b200_falcon_params hp{};
-    if (ggcc_header(c, &hp) != 0) { munmap(map, sb.st_size); fprintf(stderr, "b200: %s is not a GGCC v10 file\n", path); return -1; }
-    B200_ASSERT(hp.n_vocab == f->hp.n_vocab && hp.n_embd == f->hp.n_embd && hp.n_head == f->hp.n_head && hp.n_head_kv == f->hp.n_head_kv && hp.n_layer == f->hp.n_layer);
-    for (int i = 0; i < hp.n_vocab; i++) { const uint32_t len = c.u32(); c.off += len + 4; }
+    if (ggcc_header(c, &hp) != 0) return fail("not a GGCC v10 file");
+    if (hp.n_vocab != f->hp.n_vocab || hp.n_embd != f->hp.n_embd || hp.n_head != f->hp.n_head || hp.n_head_kv != f->hp.n_head_kv || hp.n_layer != f->hp.n_layer)
+        return fail("hyper-parameters differ from the engine's");
+    for (int i = 0; i < hp.n_vocab && !c.bad; i++) { const uint32_t len = c.u32(); c.skip((size_t) len + 4); }
     const uint32_t n_merges = c.u32();
-    for (uint32_t i = 0; i < 2 * n_merges; i++) { const uint32_t len = c.u32(); c.off += len; }
+    for (uint32_t i = 0; i < 2 * n_merges && !c.bad; i++) { const uint32_t len = c.u32(); c.skip(len); }
+    if (c.bad) return fail("truncated vocabulary");
+    const double t0 = wall_seconds();
+    std::vector<LoadItem> items;
+    size_t total = 0;
     while (c.off < c.size) {
         const uint32_t n_dims = c.u32(), name_len = c.u32(), type = c.u32();
+        if (c.bad || n_dims < 1 || n_dims > 2 || name_len > 256) return fail("malformed tensor header");
         int64_t ne[2] = { 1, 1 };
         for (uint32_t d = 0; d < n_dims; d++) ne[d] = c.u32();
-        std::string name((const char *) c.p + c.off, name_len); c.off += name_len;
-        c.off += (size_t) (-(int64_t) c.off & 31);
+        if (c.bad || name_len > c.size - c.off) return fail("truncated tensor header");
+        const std::string name((const char *) c.p + c.off, name_len); c.off += name_len;
+        c.skip((size_t) (-(int64_t) c.off & 31));
         const TypeSpec ts = type_spec((int) type);
-        B200_ASSERT(ts.blk_elems > 0 && n_dims >= 1 && n_dims <= 2);
-        const size_t nbytes = (size_t) (ne[0] / ts.blk_elems) * ts.blk_bytes * (size_t) ne[1];
-        B200_ASSERT(c.off + nbytes <= c.size);
-        b200_falcon_set_tensor(f, name.c_str(), (int) type, (int) n_dims, ne, c.p + c.off);
+        if (c.bad || ts.blk_elems <= 0 || ne[0] <= 0 || ne[1] <= 0 || ne[0] % ts.blk_elems != 0) return fail("bad tensor type / shape");
+        const size_t row_bytes = (size_t) (ne[0] / ts.blk_elems) * ts.blk_bytes, nbytes = row_bytes * (size_t) ne[1];
+        if (nbytes > c.size - c.off) return fail("tensor data runs past the end of the file");
+        Slot s;
+        if (!parse_name(name, s)) return fail("unknown tensor name");
+        int64_t K, M; expected_shape(f, s, K, M);
+        if (ne[0] != K || (n_dims == 1 ? M != 1 : ne[1] != M)) return fail("tensor shape does not match the hyper-parameters");
+        const uint8_t * data = c.p + c.off;
         c.off += nbytes;
+        if (n_dims == 1 || ts.n_planes == 1) {                                  // LayerNorm vectors, f16 / f32 matrices: the plain path
+            if (n_dims == 1 && type != T_F32) return fail("1-D tensors must be f32");
+            place_tensor(f, s, (int) type, data, false, 0);
+            continue;
+        }
+        WPlanes * W = place_matrix_alloc(f, s, (int) type);                     // planes allocated, not filled; nullptr: not this rank's tensor
+        if (!W) continue;
+        const int64_t chunk = (int64_t) (LOAD_BUF / row_bytes);
+        if (chunk < 1) return fail("a row does not fit the staging buffer");
+        for (int64_t r0 = 0; r0 < M; r0 += chunk) {
+            const int64_t nr = r0 + chunk <= M ? chunk : M - r0;
+            items.push_back({ W, data + (size_t) r0 * row_bytes, r0, nr, (size_t) nr * row_bytes });
+        }
+        total += nbytes;
     }
-    munmap(map, sb.st_size);
+    int dev; B200_CUDA_CHECK(cudaGetDevice(&dev));
+    std::atomic<size_t> next(0);
+    std::vector<std::thread> th;
+    for (int t = 0; t < LOAD_THREADS; t++) th.emplace_back(load_worker, dev, &items, &next);
+    for (auto & t : th) t.join();
+    munmap(map, (size_t) sb.st_size);
+    f->load_seconds = wall_seconds() - t0; f->load_bytes = total;
+    if (getenv("B200_VERBOSE")) fprintf(stderr, "b200: %s: %.2f GB of quantised matrices in %.2f s (%.1f GB/s)\n", path, total / 1e9, f->load_seconds, total / 1e9 / f->load_seconds);
     return 0;
 }
+double b200_falcon_load_seconds(const b200_falcon * f, size_t * bytes) { if (bytes) *bytes = f->load_bytes; return f->load_seconds; }
 
 size_t b200_falcon_weight_bytes(const b200_falcon * f) { return f->weight_bytes; }
 
@@ -371,7 +463,7 @@ void b200_falcon_free(b200_falcon * f) {
     cudaFree(f->tokens_dev); cudaFree(f->n_past_dev); cudaFree(f->q_ctr); cudaFree(f->attn_dec_scratch);
     cudaFreeHost(f->tokens_h); cudaFreeHost(f->n_past_h); cudaFreeHost(f->logits_h);
     for (int i = 0; i < 3; i++) if (f->graph[i]) cudaGraphExecDestroy(f->graph[i]);
-    cudaFree(f->tok_next); cudaFree(f->gen_hist); cudaFree(f->gen_step);
+    cudaFree(f->tok_next); cudaFree(f->gen_hist); cudaFree(f->gen_step); cudaFree(f->sampler_work); sampler_state_free(f->sampler);
     if (f->comm) nccl().CommDestroy(f->comm);
     cudaEventDestroy(f->e_fork); cudaEventDestroy(f->e_join); cudaEventDestroy(f->e_t0); cudaEventDestroy(f->e_t1);
     cudaStreamDestroy(f->s_main); cudaStreamDestroy(f->s_mlp);
@@ -411,7 +503,9 @@ static void ring_token_in(b200_falcon * f) {
 static void ring_token_out(b200_falcon * f) {
     if (!f->ring_mode) return;
     int32_t * dst = f->hp.world > 1 ? f->tok_next : f->tokens_dev;
-    launch_argmax_hist(f->logits, f->V, dst, f->gen_hist, f->gen_step, f->s_main); f->launches++;
+    if (f->use_sampler) launch_sample(f->logits, f->V, f->sampler_p, f->sampler, f->sampler_work, dst, f->gen_hist, f->gen_step, f->s_main);
+    else launch_argmax_hist(f->logits, f->V, dst, f->gen_hist, f->gen_step, f->s_main);
+    f->launches++;
     if (f->hp.world > 1) B200_NCCL_CHECK(nccl().Send(f->tok_next, 1, ncclInt32, 0, f->comm, f->s_main));
 }
 
@@ -569,7 +663,10 @@ static void build_decode_graph(b200_falcon * f, int which, float theta_scale) {
 
 extern "C" {
 
-int b200_falcon_eval(b200_falcon * f, const int32_t * tokens, int n_tokens, int n_past, int n_ctx_rope, float * logits, int all_logits) {
+// The eval in two halves: enqueue everything (returns at once: the GPU works while the caller does something else) / wait and hand the
+// logits over.  b200_falcon_eval is begin + finish; the operator hook (ggml_surface.cu) calls begin at the graph's first ROPE node and
+// finish at "result_lm_head", so the reference's walk over its remaining ~2000 graph nodes overlaps the device work.
+extern "C++" int falcon_eval_begin(b200_falcon * f, const int32_t * tokens, int n_tokens, int n_past, int n_ctx_rope, int all_logits) {
     if (n_tokens <= 0 || n_past < 0 || n_past + n_tokens > f->hp.n_ctx || n_tokens > (f->hp.n_batch > 0 ? f->hp.n_batch : 1)) return 1;
     if (f->first) {                                  // token ids index the embedding matrix: reject anything outside it (ggml_get_rows asserts, ggml.c:11990)
         if (!tokens) return 1;
@@ -582,9 +679,8 @@ int b200_falcon_eval(b200_falcon * f, const int32_t * tokens, int n_tokens, int 
         B200_CUDA_CHECK(cudaEventRecord(f->e_t0, f->s_main));
         B200_CUDA_CHECK(cudaGraphLaunch(f->graph[1], f->s_main));
         B200_CUDA_CHECK(cudaEventRecord(f->e_t1, f->s_main));
-        B200_CUDA_CHECK(cudaStreamSynchronize(f->s_main));
         f->launches = f->graph_launches;
-        if (f->last && logits) memcpy(logits, f->logits_h, (size_t) f->V * 4);
+        f->pending_floats = f->last ? (size_t) f->V : 0;
     } else {
         const int r0 = all_logits ? 0 : n_tokens - 1;
         f->launches = 0;
@@ -593,18 +689,28 @@ int b200_falcon_eval(b200_falcon * f, const int32_t * tokens, int n_tokens, int 
         B200_CUDA_CHECK(cudaEventRecord(f->e_t0, f->s_main));
         enqueue_eval(f, n_tokens, n_past, theta, false, r0);
         B200_CUDA_CHECK(cudaEventRecord(f->e_t1, f->s_main));
-        if (f->last && logits) {
+        f->pending_floats = 0;
+        if (f->last) {
             const size_t nfl = (size_t) (n_tokens - r0) * f->V;
             if (nfl > f->logits_h_floats) {          // graph[1] copies its logits row into this buffer: rebuild it around the new one
                 invalidate_graphs(f);
                 B200_CUDA_CHECK(cudaFreeHost(f->logits_h)); f->logits_h_floats = nfl; B200_CUDA_CHECK(cudaMallocHost(&f->logits_h, nfl * 4));
             }
             B200_CUDA_CHECK(cudaMemcpyAsync(f->logits_h, f->logits, nfl * 4, cudaMemcpyDeviceToHost, f->s_main));
-            B200_CUDA_CHECK(cudaStreamSynchronize(f->s_main));
-            memcpy(logits, f->logits_h, nfl * 4);
-        } else B200_CUDA_CHECK(cudaStreamSynchronize(f->s_main));
+            f->pending_floats = nfl;
+        }
     }
+    return 0;
+}
+extern "C++" void falcon_eval_finish(b200_falcon * f, float * logits) {
+    B200_CUDA_CHECK(cudaStreamSynchronize(f->s_main));
+    if (logits && f->pending_floats) memcpy(logits, f->logits_h, f->pending_floats * 4);
     B200_CUDA_CHECK(cudaEventElapsedTime(&f->last_ms, f->e_t0, f->e_t1));
+}
+int b200_falcon_eval(b200_falcon * f, const int32_t * tokens, int n_tokens, int n_past, int n_ctx_rope, float * logits, int all_logits) {
+    const int rc = falcon_eval_begin(f, tokens, n_tokens, n_past, n_ctx_rope, all_logits);
+    if (rc != 0) return rc;
+    falcon_eval_finish(f, logits);
     return 0;
 }
 
@@ -633,7 +739,31 @@ const float * b200_falcon_logits_dev(const b200_falcon * f) { return f->logits; 
 // PCIe between steps: this is the strict autoregressive single-stream rate.  First slice of SURVEY 8f-2 (the reference samples on
 // the host from a 260 KB logits row per token, falcon_main.cpp:897-980 with top_k = 1 / temp <= 0 -> llama_sample_token_greedy,
 // libfalcon.cpp:3464-3473).  Every rank of a pipeline calls it with the same arguments; tokens_out is written on the last rank.
+static int generate_impl(b200_falcon * f, int32_t first_token, int n_past, int n_steps, int n_ctx_rope, int32_t * tokens_out);
 int b200_falcon_generate_greedy(b200_falcon * f, int32_t first_token, int n_past, int n_steps, int n_ctx_rope, int32_t * tokens_out) {
+    if (f->use_sampler) { f->use_sampler = false; invalidate_graphs(f); }       // the generation-step graph bakes the sampler kernel in
+    return generate_impl(f, first_token, n_past, n_steps, n_ctx_rope, tokens_out);
+}
+// Generation with the reference's default sampling chain on the device (sampling.cu): repetition penalty over the last repeat_last_n ids
+// (seeded with last_tokens[0..n_last), oldest first), top-k, top-p, temperature and the MT19937-driven draw of llama_sample_token
+// (falcon_main.cpp:945-975, libfalcon.cpp:3281-3307, 3094-3150, 3269-3279, 3449-3468).  temp <= 0 = greedy after the penalty.
+// Returns 0 on success, 1 on a bad argument (top_k outside 1..1024, repeat_last_n > 256, positions outside the context).
+int b200_falcon_generate(b200_falcon * f, const b200_sampling_params * sp, const int32_t * last_tokens, int n_last,
+                         int32_t first_token, int n_past, int n_steps, int n_ctx_rope, int32_t * tokens_out) {
+    if (!sp || sp->top_k < 1 || sp->top_k > 1024 || sp->repeat_last_n < 0 || sp->repeat_last_n > B200_SAMPLER_MAX_WINDOW || n_last < 0) return 1;
+    const SamplerParams np = { sp->top_k < f->V ? sp->top_k : f->V, sp->top_p, sp->temp, sp->repeat_penalty };
+    if (!f->use_sampler || memcmp(&np, &f->sampler_p, sizeof(np)) != 0) { invalidate_graphs(f); f->sampler_p = np; f->use_sampler = true; }
+    if (f->last) {
+        if (!f->sampler) { f->sampler = sampler_state_alloc(); B200_CUDA_CHECK(cudaMalloc(&f->sampler_work, (size_t) f->V * 4)); }
+        int32_t * w = nullptr;
+        if (n_last > 0) { B200_CUDA_CHECK(cudaMalloc(&w, (size_t) n_last * 4)); B200_CUDA_CHECK(cudaMemcpyAsync(w, last_tokens, (size_t) n_last * 4, cudaMemcpyHostToDevice, f->s_main)); }
+        launch_sampler_init(f->sampler, sp->seed, w, n_last, sp->repeat_last_n, f->s_main);
+        B200_CUDA_CHECK(cudaStreamSynchronize(f->s_main));
+        if (w) B200_CUDA_CHECK(cudaFree(w));
+    }
+    return generate_impl(f, first_token, n_past, n_steps, n_ctx_rope, tokens_out);
+}
+static int generate_impl(b200_falcon * f, int32_t first_token, int n_past, int n_steps, int n_ctx_rope, int32_t * tokens_out) {
     if (n_steps <= 0 || n_past < 0 || n_past + n_steps > f->hp.n_ctx || first_token < 0 || first_token >= f->V) return 1;
     const float theta = rope_theta_scale_host(f->D, n_ctx_rope ? n_ctx_rope : f->hp.n_ctx, 1, 2.0f, 0);
     cudaStream_t st = f->s_main;
@@ -698,6 +828,44 @@ int b200_falcon_kv_fill_random(b200_falcon * f, int pos, int n, uint64_t seed) {
     B200_CUDA_CHECK(cudaGetLastError());
     B200_CUDA_CHECK(cudaStreamSynchronize(f->s_main));
     return 0;
+}
+// Session file over the device KV cache: what falcon_save_session_file / falcon_load_session_file (libfalcon.cpp:4490-4563) keep of
+// the KV state, written straight from / read straight into HBM through a bounded pinned buffer.  Own container (the reference's
+// serialises its transposed, ping-ponged host V buffers, which do not exist here):
+//   u32 magic 'b2kv', u32 version 1, i32 layer_first, layer_last, n_head_kv, head_dim, n_tokens; then per local layer: K rows, V rows (f32)
+// save: returns 0 / -1.  load: returns the number of positions restored (the caller continues at that n_past), -1 on any mismatch.
+int b200_falcon_save_kv(b200_falcon * f, const char * path, int n_tokens) {
+    if (n_tokens < 0 || n_tokens > f->hp.n_ctx) return -1;
+    FILE * fp = fopen(path, "wb");
+    if (!fp) return -1;
+    const int32_t hdr[7] = { 0x766b3262, 1, f->hp.layer_first, f->hp.layer_last, f->HKV, f->D, n_tokens };
+    bool ok = fwrite(hdr, sizeof(hdr), 1, fp) == 1;
+    const size_t row = (size_t) f->HKV * f->D, bytes = (size_t) n_tokens * row * 4;
+    std::vector<float> buf(bytes / 4 + 1);
+    B200_CUDA_CHECK(cudaStreamSynchronize(f->s_main));
+    for (int l = 0; l < f->NL && ok; l++)
+        for (float * base : { f->k_cache, f->v_cache }) {
+            B200_CUDA_CHECK(cudaMemcpy(buf.data(), base + (size_t) l * f->hp.n_ctx * row, bytes, cudaMemcpyDeviceToHost));
+            ok = ok && (bytes == 0 || fwrite(buf.data(), bytes, 1, fp) == 1);
+        }
+    ok = (fclose(fp) == 0) && ok;
+    return ok ? 0 : -1;
+}
+int b200_falcon_load_kv(b200_falcon * f, const char * path) {
+    FILE * fp = fopen(path, "rb");
+    if (!fp) return -1;
+    int32_t hdr[7];
+    if (fread(hdr, sizeof(hdr), 1, fp) != 1 || hdr[0] != 0x766b3262 || hdr[1] != 1 || hdr[2] != f->hp.layer_first || hdr[3] != f->hp.layer_last ||
+        hdr[4] != f->HKV || hdr[5] != f->D || hdr[6] < 0 || hdr[6] > f->hp.n_ctx) { fclose(fp); return -1; }
+    const int n = hdr[6];
+    const size_t row = (size_t) f->HKV * f->D, bytes = (size_t) n * row * 4;
+    std::vector<float> k(bytes / 4 + 1), v(bytes / 4 + 1);
+    for (int l = 0; l < f->NL; l++) {
+        if (bytes && (fread(k.data(), bytes, 1, fp) != 1 || fread(v.data(), bytes, 1, fp) != 1)) { fclose(fp); return -1; }
+        if (b200_falcon_kv_write(f, f->hp.layer_first + l, 0, n, k.data(), v.data()) != 0) { fclose(fp); return -1; }     // also refreshes the fp16 shadow
+    }
+    fclose(fp);
+    return n;
 }
 int b200_falcon_last_launches(const b200_falcon * f) { return f->launches; }
 float b200_falcon_last_ms(const b200_falcon * f) { return f->last_ms; }

@@ -263,15 +263,15 @@ bool tk_node(const abi::compute_params * params, abi::tensor * t) {
                             "set B200_NO_TAKEOVER=1 to keep the per-node path\n", g_tk.n_past, g_tk.valid_upto);
             abort();
         }
-        float * lg = const_cast<float *>(tk_logits((size_t) g_tk.N * g_tk.n_vocab));
-        if (b200_falcon_eval(b200_takeover_engine, g_tk.tokens.data(), g_tk.N, g_tk.n_past, g_tk.rope_ctx, lg, 1) != 0) {
+        // enqueue only: the device evaluates the graph while ggml walks (and this hook claims) the remaining nodes
+        if (falcon_eval_begin(b200_takeover_engine, g_tk.tokens.data(), g_tk.N, g_tk.n_past, g_tk.rope_ctx, 1) != 0) {
             fprintf(stderr, "b200: engine eval failed behind ggml_cuda_compute_forward (N %d, n_past %d)\n", g_tk.N, g_tk.n_past); abort();
         }
         g_tk.valid_upto = g_tk.n_past + g_tk.N; g_tk.launched = true; g_tk.evals_taken++; g_tk_total++;
     }
     if (strcmp(t->name, "result_lm_head") == 0) {
         B200_ASSERT(g_tk.launched && contiguous_f32(t) && nelements(t) == (int64_t) g_tk.N * g_tk.n_vocab);
-        memcpy(t->data, g_tk.logits, (size_t) g_tk.N * g_tk.n_vocab * 4);      // falcon_eval_internal reads the logits here (libfalcon.cpp:2538-2549)
+        falcon_eval_finish(b200_takeover_engine, (float *) t->data);            // falcon_eval_internal reads the logits here (libfalcon.cpp:2538-2549)
         t->meta.cuda_perf_mal_mul_type = g_tk.N <= b200_mmv_max_n() ? 1 : 16;
         g_tk.active = false;
     }

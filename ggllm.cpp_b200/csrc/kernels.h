@@ -7,6 +7,7 @@ size_t wplanes_layout(WPlanes & W, int type, int K, int M);
 void   wplanes_upload(WPlanes & W, int type, int K, int M, const void * host_raw, cudaStream_t stream);
 void   wplanes_from_device_raw(WPlanes & W, int type, int K, int M, const void * dev_raw, cudaStream_t stream);
 void   wplanes_alloc_random(WPlanes & W, int type, int K, int M, uint64_t seed, cudaStream_t stream);
+void   launch_repack_rows(const WPlanes & W, const void * stage_dev, int64_t row0, int64_t nrows, cudaStream_t stream);   // raw blocks of rows [row0, row0 + nrows) -> planes
 void   wplanes_free(WPlanes & W);
 void   launch_dequant_rows(const WPlanes & W, const int32_t * rows_dev, int nrows, float * dst, int64_t dst_stride, cudaStream_t stream);
 
@@ -96,6 +97,17 @@ void   launch_mmq_gemm(const WPlanes & W, const __half * X, int64_t x_stride, in
                        int epi_gelu, void * workspace, size_t workspace_bytes, cudaStream_t stream);
 size_t mmq_gemm_workspace_bytes(const WPlanes & W, int N);
 
+// ---- sampling.cu: the reference's default sampling chain on the device (repetition penalty, top-k, top-p, temperature, MT19937 draw)
+#define B200_SAMPLER_MAX_WINDOW 256
+struct SamplerParams { int top_k; float top_p; float temp; float repeat_penalty; };
+struct SamplerState;
+SamplerState * sampler_state_alloc();
+void   sampler_state_free(SamplerState * s);
+void   launch_sampler_init(SamplerState * s, uint32_t seed, const int32_t * window_dev, int n, int cap, cudaStream_t stream);
+void   launch_sample(const float * logits, int n_vocab, const SamplerParams & p, SamplerState * st, float * work, int32_t * out, int32_t * hist, int * step, cudaStream_t stream);
+
 // ---- engine.cu (internal, C++ linkage): adopt a matrix that is already resident in the planar layout (no copy, not freed by the engine)
 struct b200_falcon;
 bool   falcon_adopt_matrix(b200_falcon * f, const char * ggcc_name, const WPlanes & W);
+int    falcon_eval_begin(b200_falcon * f, const int32_t * tokens, int n_tokens, int n_past, int n_ctx_rope, int all_logits);   // enqueue only (b200_falcon_eval's checks and return codes)
+void   falcon_eval_finish(b200_falcon * f, float * logits);                                                                   // wait; logits (optional) receive what begin asked for

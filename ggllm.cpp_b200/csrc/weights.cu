@@ -72,6 +72,14 @@ void wplanes_upload(WPlanes & W, int type, int K, int M, const void * host_raw, 
     B200_CUDA_CHECK(cudaFree(stage));
 }
 
+// rows [row0, row0 + nrows) of an allocated matrix from their raw blocks staged on the device (the streaming loader, engine.cu)
+void launch_repack_rows(const WPlanes & W, const void * stage_dev, int64_t row0, int64_t nrows, cudaStream_t stream) {
+    const int64_t n = nrows * W.nb;
+    if (n <= 0) return;
+    repack_kernel<<<(unsigned) ((n + 255) / 256), 256, 0, stream>>>((const uint8_t *) stage_dev, W, type_spec(W.type), row0, nrows);
+    B200_CUDA_CHECK(cudaGetLastError());
+}
+
 // repack from a raw AoS copy that is already on the device (synthetic models generated on the GPU)
 void wplanes_from_device_raw(WPlanes & W, int type, int K, int M, const void * dev_raw, cudaStream_t stream) {
     const TypeSpec ts = type_spec(type);

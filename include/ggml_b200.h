@@ -135,6 +135,19 @@ void   b200_layernorm_q(float * x_dev, int64_t x_stride, const float * ra_dev, c
 int    b200_attention_decode(float * qkv_dev, float * k_cache_dev, float * v_cache_dev, float * out_dev,
                              int n_head, int n_head_kv, int head_dim, int n_past, int n_ctx, int n_ctx_rope, b200_actq * qout);
 
+/* ---- sampling on the device: falcon_main's default chain (examples/falcon/falcon_main.cpp:945-975) over a logits row in HBM:
+ * llama_sample_repetition_penalty over the last repeat_last_n ids, then temp <= 0 ? llama_sample_token_greedy :
+ * llama_sample_top_k -> llama_sample_top_p -> llama_sample_temperature -> llama_sample_token (libfalcon.cpp:3281-3307, 3433-3447,
+ * 3094-3150, 3269-3279, 3449-3468).  The draw reproduces std::discrete_distribution over std::mt19937(seed), so the same seed samples
+ * the same ids as the reference.  top_k must be 1..1024 (the reference's "<= 0 means the whole vocabulary" is not supported),
+ * repeat_last_n <= 256; tail-free / typical / mirostat / frequency and presence penalties (all off by default) are not implemented. */
+typedef struct { int32_t top_k; float top_p; float temp; float repeat_penalty; int32_t repeat_last_n; uint32_t seed; } b200_sampling_params;
+typedef struct b200_sampler b200_sampler;
+/* last_tokens[0..n_last): the ids already generated / in the prompt, oldest first; the last repeat_last_n of them seed the window.  NULL on bad parameters. */
+b200_sampler * b200_sampler_create(const b200_sampling_params * p, const int32_t * last_tokens, int n_last);
+int32_t        b200_sampler_sample(b200_sampler * s, const float * logits_dev, int n_vocab);   /* samples, appends the id to the window, returns it */
+void           b200_sampler_free(b200_sampler * s);
+
 /* ========================================= part B: Falcon eval path ====================================== */
 
 typedef struct b200_falcon b200_falcon;
@@ -158,8 +171,13 @@ void          b200_falcon_set_tensor(b200_falcon * f, const char * name, int ggm
                                      const int64_t * ne, const void * data);
 /* random-init tensor of the named shape generated on the device (synthetic throughput models) */
 void          b200_falcon_set_tensor_random(b200_falcon * f, const char * name, int ggml_type, uint64_t seed);
-/* load every tensor of a GGCC v10 file (format: libfalcon.cpp:770-973).  Returns 0 on success. */
+/* load every tensor of a GGCC v10 file (format: libfalcon.cpp:770-973) through the GPU-direct path: mmap -> pinned ring buffers ->
+ * cudaMemcpyAsync -> on-the-fly planar repack, several host threads, two buffers in flight each, one synchronize at the end
+ * (replaces libfalcon.cpp:1196-1270 + the blocking per-tensor copy of ggml-cuda.cu:3030-3073).  The file is validated while it is
+ * read (bounds, types, shapes, names); returns 0 on success, -1 on an unreadable / malformed / mismatching file. */
 int           b200_falcon_load_ggcc(b200_falcon * f, const char * path);
+/* seconds the last b200_falcon_load_ggcc took (header parse to the final synchronize) and the quantised-matrix bytes it streamed */
+double        b200_falcon_load_seconds(const b200_falcon * f, size_t * bytes);
 /* hparams of a GGCC file without loading it (fills n_vocab..falcon_type); returns 0 on success */
 int           b200_ggcc_read_hparams(const char * path, b200_falcon_params * out);
 void          b200_falcon_free(b200_falcon * f);
@@ -190,8 +208,17 @@ int           b200_falcon_generate_greedy(b200_falcon * f, int32_t first_token, 
  * device-resident cache.  Return 0 on success, 1 if the layer is not on this rank or the range leaves [0, n_ctx). */
 int           b200_falcon_kv_read(b200_falcon * f, int layer, int pos, int n, float * k_out, float * v_out);
 int           b200_falcon_kv_write(b200_falcon * f, int layer, int pos, int n, const float * k_in, const float * v_in);
+/* session file over the device KV cache (what falcon_save_session_file / falcon_load_session_file keep of the KV state,
+ * libfalcon.cpp:4490-4563), in this library's own container: positions [0, n_tokens) of every local layer.  save: 0 / -1.
+ * load: the number of positions restored (continue evaluating at that n_past), -1 on a missing / truncated / mismatching file. */
+int           b200_falcon_save_kv(b200_falcon * f, const char * path, int n_tokens);
+int           b200_falcon_load_kv(b200_falcon * f, const char * path);
 /* pseudo-random K / V rows for positions [pos, pos + n) of every local layer, generated on the device (long-context throughput runs) */
 int           b200_falcon_kv_fill_random(b200_falcon * f, int pos, int n, uint64_t seed);
+/* b200_falcon_generate_greedy with the sampling chain above run on the device after every step (every rank of a pipeline calls it with
+ * the same arguments; the last rank samples).  Returns 0 on success, 1 on bad arguments. */
+int           b200_falcon_generate(b200_falcon * f, const b200_sampling_params * p, const int32_t * last_tokens, int n_last,
+                                   int32_t first_token, int n_past, int n_steps, int n_ctx_rope, int32_t * tokens_out);
 /* the cudaStream_t the eval path runs on (for event timing) */
 void *        b200_falcon_stream(b200_falcon * f);
 /* roofline probe: every resident quantised mat-vec of this rank (4 per layer + lm_head) launched back to back,

@@ -337,6 +337,18 @@ class RefFalcon:
         assert rc == 0
         return out
 
+    def set_seed(self, seed):
+        self.L.refh_set_seed.argtypes = [C.c_void_p, C.c_int]
+        self.L.refh_set_seed(self.h, seed)
+
+    def sample(self, logits, last_tokens, top_k=40, top_p=0.95, temp=0.8, repeat_penalty=1.1):
+        """falcon_main's default sampling chain (the reference's own llama_sample_* functions) on one logits row"""
+        self.L.refh_sample.restype = C.c_int
+        self.L.refh_sample.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float]
+        lg = np.ascontiguousarray(logits, dtype=np.float32)
+        lt = np.ascontiguousarray(last_tokens, dtype=np.int32)
+        return int(self.L.refh_sample(self.h, _fp(lg), lg.size, _fp(lt), lt.size, top_k, top_p, temp, repeat_penalty))
+
     def close(self):
         if self.h:
             self.L.refh_free(self.h)

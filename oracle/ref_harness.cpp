@@ -92,6 +92,24 @@ double refh_matvec_bench(int K, int M, int n_mats, int iters, int n_threads, con
     return total / ((double) iters * n_mats);
 }
 
+// falcon_main's default sampling chain over a caller-provided logits row (examples/falcon/falcon_main.cpp:945-975): repetition penalty
+// over last_tokens, then greedy (temp <= 0) or top-k -> top-p -> temperature -> llama_sample_token, which draws from the context's
+// std::mt19937 (reseed with refh_set_seed).  Only calls the reference's public llama_sample_* functions, in falcon_main's order.
+void refh_set_seed(void * h, int seed) { llama_set_rng_seed((falcon_context *) h, seed); }
+int refh_sample(void * h, const float * logits, int n_vocab, const int * last_tokens, int n_last, int top_k, float top_p, float temp, float repeat_penalty) {
+    falcon_context * ctx = (falcon_context *) h;
+    std::vector<falcon_token_data> candidates;
+    candidates.reserve(n_vocab);
+    for (falcon_token id = 0; id < n_vocab; id++) candidates.emplace_back(falcon_token_data{ id, logits[id], 0.0f });
+    falcon_token_data_array cp = { candidates.data(), candidates.size(), false };
+    llama_sample_repetition_penalty(ctx, &cp, last_tokens, (size_t) n_last, repeat_penalty);
+    if (temp <= 0) return llama_sample_token_greedy(ctx, &cp);
+    llama_sample_top_k(ctx, &cp, top_k <= 0 ? n_vocab : top_k, 1);
+    llama_sample_top_p(ctx, &cp, top_p, 1);
+    llama_sample_temperature(ctx, &cp, temp);
+    return llama_sample_token(ctx, &cp);
+}
+
 // the reference's own timing table (libfalcon.cpp:4700-4714)
 void refh_print_timings(void * h) { falcon_print_timings((falcon_context *) h); }
 

@@ -270,3 +270,57 @@ def test_session_state_roundtrip_over_device_kv(gpu):
     with pytest.raises(RuntimeError):
         a.kv_read(0, 40, 9)
     a.free(); b.free()
+
+
+def test_session_file_over_device_kv(gpu, tmp_path):
+    """b200_falcon_save_kv / load_kv: a prompt evaluated in one engine, saved, restored into a fresh engine (both the f32 cache and the
+    fp16 shadow the prompt kernel reads), continues with the same bits -- decode steps AND a further prompt chunk; bad files are refused"""
+    hp = dict(TINY_40B)
+    tensors = synth_model(hp, po.Q4_K, seed=51)
+    a, b = gpu.Falcon(hp, n_ctx=64, n_batch=16), gpu.Falcon(hp, n_ctx=64, n_batch=16)
+    a.set_tensors(tensors); b.set_tensors(tensors)
+    prompt = np.arange(20, 32, dtype=np.int32)                      # 12 tokens: the tensor-core prompt path
+    a.eval(prompt, 0)
+    path = str(tmp_path / "s.kv")
+    a.save_kv(path, 12)
+    assert b.load_kv(path) == 12
+    assert np.array_equal(a.eval(np.array([40], np.int32), 12), b.eval(np.array([40], np.int32), 12))
+    chunk = np.arange(50, 62, dtype=np.int32)
+    assert np.array_equal(a.eval(chunk, 13, all_logits=True), b.eval(chunk, 13, all_logits=True))      # attention over the restored shadow
+    open(str(tmp_path / "t.kv"), "wb").write(open(path, "rb").read()[:1000])
+    with pytest.raises(RuntimeError):
+        b.load_kv(str(tmp_path / "t.kv"))
+    with pytest.raises(RuntimeError):
+        b.load_kv(str(tmp_path / "missing.kv"))
+    c = gpu.Falcon(dict(TINY_7B), n_ctx=64, n_batch=16)
+    with pytest.raises(RuntimeError):
+        c.load_kv(path)                                              # another model's geometry
+    a.free(); b.free(); c.free()
+
+
+def test_ggcc_loader_rejects_malformed_files(gpu, tmp_path):
+    """the streaming loader validates while it reads: truncated data, a corrupt header, a wrong shape and a foreign tensor name all
+    return an error (no abort, no out-of-bounds read), and the engine still loads the intact file afterwards"""
+    hp = dict(TINY_7B)
+    tensors = synth_model(hp, po.Q4_0, seed=9)
+    good = str(tmp_path / "good.ggcc")
+    ggcc.write_ggcc(good, hp, tensors, ftype=2)
+    raw = open(good, "rb").read()
+    cases = {"trunc_data": raw[:len(raw) - 1000], "trunc_vocab": raw[:60], "bad_magic": b"xxxx" + raw[4:], "tiny": raw[:20]}
+    wrong = dict(tensors); name = "transformer.h.0.mlp.dense_h_to_4h.weight"
+    t, ne, arr = wrong[name]; wrong[name] = (t, (ne[0], ne[1] - 32), arr[:-32])
+    ggcc.write_ggcc(str(tmp_path / "wrong_shape.ggcc"), hp, wrong, ftype=2)
+    alien = dict(tensors); alien["transformer.h.0.some_other.weight"] = alien.pop(name)
+    ggcc.write_ggcc(str(tmp_path / "alien.ggcc"), hp, alien, ftype=2)
+    f = gpu.Falcon(hp, n_ctx=32, n_batch=4)
+    for key, blob in cases.items():
+        open(str(tmp_path / (key + ".ggcc")), "wb").write(blob)
+    for key in list(cases) + ["wrong_shape", "alien", "does_not_exist"]:
+        with pytest.raises(RuntimeError):
+            f.load_ggcc(str(tmp_path / (key + ".ggcc")))
+    f.load_ggcc(good)
+    g = gpu.Falcon(hp, n_ctx=32, n_batch=4)
+    g.set_tensors(tensors)
+    toks = np.array([11, 20, 21], np.int32)
+    assert np.array_equal(f.eval(toks, 0, all_logits=True), g.eval(toks, 0, all_logits=True))
+    f.free(); g.free()

@@ -232,6 +232,24 @@ def test_full_k_gemm_against_oracle_columns(gpu, orc, t, K, M, N):
     assert np.median(np.abs(got - want) / mag) < 1e-4
 
 
+def test_streaming_loader_at_real_widths(gpu, tmp_path):
+    """b200_falcon_load_ggcc (mmap -> pinned ring -> cudaMemcpyAsync -> planar repack, six host threads) on a 0.8 GB file whose matrices
+    span many 32 MB chunks: the loaded engine is bit-identical to one filled tensor by tensor"""
+    hp = GEOM["40b"]
+    tensors = random_model(hp, po.Q4_K, seed=MODEL_SEED["40b"] + po.Q4_K)
+    path = str(tmp_path / "m40.ggcc")
+    ggcc.write_ggcc(path, hp, tensors, ftype=15)
+    a, b = gpu.Falcon(hp, n_ctx=64, n_batch=4), gpu.Falcon(hp, n_ctx=64, n_batch=4)
+    a.load_ggcc(path)
+    secs, nbytes = a.load_stats()
+    assert nbytes == sum(ggcc.tensor_nbytes(t, ne) for n, (t, ne, _) in tensors.items() if len(ne) == 2) and secs > 0
+    b.set_tensors(tensors)
+    toks = np.array([11, 200, 300], np.int32)
+    assert np.array_equal(a.eval(toks, 0, all_logits=True), b.eval(toks, 0, all_logits=True))
+    assert np.array_equal(a.eval(toks[:1], 3), b.eval(toks[:1], 3))
+    a.free(); b.free()
+
+
 def test_release_cached_models():
     for k in list(_models):
         f, o = _models.pop(k)
