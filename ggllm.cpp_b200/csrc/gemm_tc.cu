@@ -197,14 +197,15 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
         const int t = threadIdx.x - 64, r = t >> 2, h = t & 3;
         const size_t row = (size_t) min(m0 + r, a.W.M - 1);                // rows past M are computed from row M-1 and never stored
         uint8_t * my_row = nullptr;
-        RawQ4K raw;
-        if (TYPE == T_Q4_K) raw = load_q4k(a.W, row, kb0, h);
+        RawQ4K raw, raw1;                                                  // the bytes of K blocks kb and kb + 1: two loads in flight per thread
+        if (TYPE == T_Q4_K) { raw = load_q4k(a.W, row, kb0, h); raw1 = load_q4k(a.W, row, kb0 + (KB > 1 ? 1 : 0), h); }
         for (int kb = 0; kb < KB; kb++) {
             const int s = kb % SA;
             Chunks ch;
             if (TYPE == T_Q4_K) {
                 ch = dequant_q4k(raw);
-                if (kb + 1 < KB) raw = load_q4k(a.W, row, kb0 + kb + 1, h);      // next block's bytes are in flight while this one is stored
+                raw = raw1;
+                if (kb + 2 < KB) raw1 = load_q4k(a.W, row, kb0 + kb + 2, h);     // two blocks ahead: an L2 / HBM round trip is longer than one block's MMA time
             } else ch = dequant_generic(a.W, row, (kb0 + kb) * BK, h);
             if (kb >= SA) mbar_wait(a_empty + s, (uint32_t) ((kb / SA - 1) & 1));
             my_row = sA + (size_t) s * A_STAGE + r * 128;

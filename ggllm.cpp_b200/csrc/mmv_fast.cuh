@@ -205,17 +205,20 @@ template <> struct FX<T_Q3_K> {
         r.d = ldg_u16(p.b3 + (uint64_t) row * p.s3);
         return r;
     }
-    // hsh = 4 n: the per-thread shift into its half of the high-bit plane (piece_aux)
+    // hsh = 4 n: the per-thread shift into its half of the high-bit plane (piece_aux).
+    // The 2-bit field of quad j and the high bit are dotted IN PLACE (as the high nibbles of Q4_K are): a masked byte holds
+    // 4^j * q2 (<= 192) resp. 2^(hsh+j) * hbit, dp4a is linear, so one exact shift per quad undoes the factor after the 16-value sum --
+    // 2 LOP3 + 2 dp4a per word instead of 2 shifts + 2 masks + or + dp4a (this kernel is issue-bound, not HBM-bound).
     __device__ static float dot(const WR & w, const XR & x, int hsh) {
         const uint32_t q[4] = { w.q.x, w.q.y, w.q.z, w.q.w }, hm[4] = { w.hm.x, w.hm.y, w.hm.z, w.hm.w };
+        const uint32_t hbase = 0x01010101u << hsh;
         int i[4];
 #pragma unroll
         for (int quad = 0; quad < 4; quad++) {
-            uint32_t cw[4];
-#pragma unroll
-            for (int k = 0; k < 4; k++)                                      // unsigned code 0..7: low two bits | high bit moved to bit 2
-                cw[k] = ((q[k] >> (2 * quad)) & 0x03030303u) | (((hm[k] >> (hsh + quad)) << 2) & 0x04040404u);
-            i[quad] = dot16(cw[0], cw[1], cw[2], cw[3], x.x[quad]);         // <= 16 * 7 * 127 < 2^15
+            const uint32_t qm = 0x03030303u << (2 * quad), hmk = hbase << quad;
+            const int dq = dot16(q[0] & qm, q[1] & qm, q[2] & qm, q[3] & qm, x.x[quad]);          // 4^quad * sum q2 x   (< 2^19)
+            const int dh = dot16(hm[0] & hmk, hm[1] & hmk, hm[2] & hmk, hm[3] & hmk, x.x[quad]);   // 2^(hsh+quad) * sum hbit x   (< 2^19)
+            i[quad] = (dq >> (2 * quad)) + ((dh >> (hsh + quad)) << 2);                            // exact: both are multiples; <= 16 * 7 * 127 < 2^15
         }
         int isum = dp2a_lo_ss((i[0] & 0xffff) | (i[1] << 16), w.sc, 0);
         isum = dp2a_hi_ss((i[2] & 0xffff) | (i[3] << 16), w.sc, isum);
