@@ -86,15 +86,29 @@ def kv_bytes(hp, n_past):
 
 
 def stage_ranges(hp, world):
-    """contiguous layer ranges balanced by BYTES: the last rank also streams lm_head (worth V / (12 E + (H + 2 HKV) D) layers), so it
-    gets correspondingly fewer layers (replaces the VRAM-proportional tensor_split, ggml-cuda.cu:1999-2012)"""
+    """contiguous layer ranges balanced by BYTES: the last rank also streams lm_head (worth V / (9 E + (H + 2 HKV) D) layers), so it
+    gets correspondingly fewer layers; the other ranks share the rest evenly (replaces the VRAM-proportional tensor_split,
+    ggml-cuda.cu:1999-2012).  Of the two candidate sizes of the last stage the one with the smaller maximum stage is taken."""
     E, H, HKV, L, V = hp["n_embd"], hp["n_head"], hp["n_head_kv"], hp["n_layer"], hp["n_vocab"]
     D = E // H
+    if world == 1:
+        return [(0, L)]
     head = V / float(9 * E + (H + 2 * HKV) * D)
     per = (L + head) / world
-    cuts = [0] + [min(L, max(0, int(round(per * r)))) for r in range(1, world)] + [L]
-    for r in range(1, world + 1):                      # strictly increasing where possible
-        cuts[r] = max(cuts[r], cuts[r - 1])
+    best = None
+    for n_last in {max(1, int(per - head)), max(1, int(per - head) + 1)}:
+        rest = L - n_last
+        if rest < world - 1:
+            continue
+        base, rem = divmod(rest, world - 1)
+        sizes = [base + (1 if r < rem else 0) for r in range(world - 1)] + [n_last]
+        loads = sizes[:-1] + [n_last + head]
+        key = (max(loads), max(loads) - min(loads))                  # smallest maximum stage, then smallest spread
+        if best is None or key < best[0]:
+            best = (key, sizes)
+    cuts = [0]
+    for n in best[1]:
+        cuts.append(cuts[-1] + n)
     return [(cuts[r], cuts[r + 1]) for r in range(world)]
 
 

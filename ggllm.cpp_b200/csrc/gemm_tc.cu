@@ -88,14 +88,18 @@ __device__ __forceinline__ Chunks dequant_generic(const WPlanes & W, size_t row,
     }
     return o;
 }
-// Q4_K: w = (d*sc)*q - dmin*m, computed in fp32 exactly like dequantize_row_q4_K (k_quants.c:607-631), one rounding to fp16
+// Q4_K: w = (d*sc)*q - dmin*m with the fp32 roundings of dequantize_row_q4_K (k_quants.c:607-631), then one rounding to fp16.
+// d*sc and dmin*m are exact in fp32 (11-bit x 6-bit significands) and so is (d*sc)*q (17 x 4 bits), hence fma(d*sc, q, -dmin*m) rounds
+// exactly once where the CPU's fmul + fsub rounds exactly once: same bits, one instruction less per weight (the producers bound this kernel).
 struct RawQ4K { uint2 q; uint32_t sm, dd; };
-__device__ __forceinline__ RawQ4K load_q4k(const WPlanes & W, size_t row, int kb, int h) {      // h = 0..3: bytes 8h .. 8h+7 of the 32
+// K block kb (64 weights) of a row: quant bytes at 32 kb + 8 h, the (sc, sc, min, min) word at 4 kb, (d, dmin) at 4 (kb / 4): running pointers
+struct PtrQ4K { const uint8_t * q, * sm, * dd; };
+__device__ __forceinline__ PtrQ4K ptr_q4k(const WPlanes & W, size_t row, int kb, int h) {      // h = 0..3: bytes 8h .. 8h+7 of the 32
+    return { W.p[0] + row * W.stride[0] + (size_t) kb * 32 + h * 8, W.p[1] + row * W.stride[1] + (size_t) kb * 4, W.p[2] + row * W.stride[2] };
+}
+__device__ __forceinline__ RawQ4K load_q4k(const PtrQ4K & p, int kb) {
     RawQ4K r;
-    const int b = kb >> 2, p = kb & 3;
-    r.q = ldg_stream_v2(W.p[0] + row * W.stride[0] + (size_t) b * 128 + p * 32 + h * 8);
-    r.sm = ldg_u32(W.p[1] + row * W.stride[1] + (size_t) b * 16 + p * 4);
-    r.dd = ldg_u32(W.p[2] + row * W.stride[2] + (size_t) b * 4);
+    r.q = ldg_stream_v2(p.q); r.sm = ldg_u32(p.sm); r.dd = ldg_u32(p.dd + (size_t) (kb >> 2) * 4);
     return r;
 }
 __device__ __forceinline__ Chunks dequant_q4k(const RawQ4K & r) {
@@ -109,8 +113,8 @@ __device__ __forceinline__ Chunks dequant_q4k(const RawQ4K & r) {
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             const uint32_t byte = (w[i] >> (8 * j)) & 0xff;
-            lo[4 * i + j] = __fsub_rn(__fmul_rn(d0, (float) (byte & 0xF)), m0);
-            hi[4 * i + j] = __fsub_rn(__fmul_rn(d1, (float) (byte >> 4)), m1);
+            lo[4 * i + j] = __fmaf_rn(d0, (float) (byte & 0xF), -m0);
+            hi[4 * i + j] = __fmaf_rn(d1, (float) (byte >> 4), -m1);
         }
     Chunks o;
     o.c[0] = make_uint4(pack_h2(lo[0], lo[1]), pack_h2(lo[2], lo[3]), pack_h2(lo[4], lo[5]), pack_h2(lo[6], lo[7]));
@@ -196,22 +200,23 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
         // ===== dequant producers (2 threads per weight row) =====
         const int t = threadIdx.x - 64, r = t >> 2, h = t & 3;
         const size_t row = (size_t) min(m0 + r, a.W.M - 1);                // rows past M are computed from row M-1 and never stored
-        uint8_t * my_row = nullptr;
         RawQ4K raw, raw1;                                                  // the bytes of K blocks kb and kb + 1: two loads in flight per thread
-        if (TYPE == T_Q4_K) { raw = load_q4k(a.W, row, kb0, h); raw1 = load_q4k(a.W, row, kb0 + (KB > 1 ? 1 : 0), h); }
+        PtrQ4K pq = ptr_q4k(a.W, row, kb0 + (KB > 1 ? 1 : 0), h);
+        if (TYPE == T_Q4_K) { const PtrQ4K p0 = ptr_q4k(a.W, row, kb0, h); raw = load_q4k(p0, kb0); raw1 = load_q4k(pq, kb0 + (KB > 1 ? 1 : 0)); }
+        const int sw = r & 7;
+        const uint32_t st0 = smem_u32(sA) + (uint32_t) (r * 128 + ((h ^ sw) << 4)), st1 = smem_u32(sA) + (uint32_t) (r * 128 + (((4 + h) ^ sw) << 4));
         for (int kb = 0; kb < KB; kb++) {
             const int s = kb % SA;
             Chunks ch;
             if (TYPE == T_Q4_K) {
                 ch = dequant_q4k(raw);
                 raw = raw1;
-                if (kb + 2 < KB) raw1 = load_q4k(a.W, row, kb0 + kb + 2, h);     // two blocks ahead: an L2 / HBM round trip is longer than one block's MMA time
+                pq.q += 32; pq.sm += 4;                                     // -> K block kb0 + kb + 2
+                if (kb + 2 < KB) raw1 = load_q4k(pq, kb0 + kb + 2);         // two blocks ahead: an L2 / HBM round trip is longer than one block's MMA time
             } else ch = dequant_generic(a.W, row, (kb0 + kb) * BK, h);
             if (kb >= SA) mbar_wait(a_empty + s, (uint32_t) ((kb / SA - 1) & 1));
-            my_row = sA + (size_t) s * A_STAGE + r * 128;
-            const int sw = r & 7;
-            *reinterpret_cast<uint4 *>(my_row + ((h ^ sw) << 4)) = ch.c[0];                // elements 8h .. 8h+7
-            *reinterpret_cast<uint4 *>(my_row + (((4 + h) ^ sw) << 4)) = ch.c[1];          // elements 32+8h .. 32+8h+7
+            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" :: "r"(st0 + (uint32_t) s * A_STAGE), "r"(ch.c[0].x), "r"(ch.c[0].y), "r"(ch.c[0].z), "r"(ch.c[0].w) : "memory");   // elements 8h .. 8h+7
+            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" :: "r"(st1 + (uint32_t) s * A_STAGE), "r"(ch.c[1].x), "r"(ch.c[1].y), "r"(ch.c[1].z), "r"(ch.c[1].w) : "memory");   // elements 32+8h .. 32+8h+7
             fence_proxy_async();                                           // generic-proxy stores -> visible to the tensor core (async proxy)
             mbar_arrive(a_full + s);
         }
@@ -245,172 +250,6 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
     if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(512) : "memory");
 }
 
-// ---------------------------------------------------------------------------------------------------------------
-// N > 256: a CLUSTER of two CTAs shares one 128-row weight tile.  CTA r of the pair owns tokens [256 r, 256 r + 256) (256 accumulator
-// columns) and dequantises only every other K block (those with kb % 2 == r) -- but writes each of its A tiles into BOTH CTAs'
-// shared memory (st.shared::cluster), so every weight is dequantised ONCE per 512 tokens instead of once per CTA and the fp32
-// dequantisation chain, which bounded the single-CTA kernel (tensor pipe 65 % busy, profiles/r1_gemm_tc.md), has twice the time.
-//   a_full[s]  (512 arrivals, in both CTAs): the producing CTA's threads arrive locally and, with release.cluster, on the peer's barrier
-//   a_done[s]  (1, local): this CTA's MMAs have read stage s (tcgen05.commit)
-//   a_empty[s] (2, in the CTA that produces stage s = CTA s % 2, SA is even): one relay thread per CTA forwards its a_done[s] there
-// Twice as many CTAs of half the width also fill the machine for the narrow matrices (qkv: 144, wo / ffn_down: 128 CTAs), so the
-// split-K + atomics path of the single-CTA kernel is not needed here.
-__device__ __forceinline__ uint32_t cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
-__device__ __forceinline__ uint32_t map_peer(uint32_t saddr, uint32_t rank) { uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank)); return r; }
-__device__ __forceinline__ void st_cluster_v4(uint32_t addr, const uint4 & v) {
-    asm volatile("st.shared::cluster.v4.u32 [%0], {%1, %2, %3, %4};" :: "r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t addr) {      // addr: shared::cluster address (own or peer CTA)
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" :: "r"(addr) : "memory");
-}
-__device__ __forceinline__ void mbar_wait_cluster(uint64_t * bar, uint32_t phase) {     // acquire at cluster scope: data written by the peer CTA
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "WAITC_%=:\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONEC_%=;\n\t"
-        "bra WAITC_%=;\n\t"
-        "DONEC_%=:\n\t}"
-        :: "r"(smem_u32(bar)), "r"(phase) : "memory");
-}
-__device__ __forceinline__ void cluster_barrier() { asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory"); }
-
-constexpr int SB2 = 3, THREADS2 = THREADS + 32;                            // + one warp whose lane 0 relays a_done -> a_empty
-template <int TYPE>
-__global__ void __launch_bounds__(THREADS2, 1) gemm_tc2_kernel(const __grid_constant__ CUtensorMap xmap, const GemmArgs a) {
-    extern __shared__ __align__(1024) uint8_t smem_raw[];
-    uint8_t * smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t) 1023);
-    constexpr int b_stage = 256 * 128;                                     // 256 tokens x 64 halves
-    uint8_t * sA = smem, * sB = smem + SA * A_STAGE;
-    uint64_t * bars = reinterpret_cast<uint64_t *>(sB + SB2 * b_stage);
-    uint64_t * a_full = bars, * a_done = bars + SA, * a_empty = bars + 2 * SA, * b_full = bars + 3 * SA, * b_empty = b_full + SB2, * acc_full = b_empty + SB2;
-    uint32_t * tmem_slot = reinterpret_cast<uint32_t *>(acc_full + 1);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t rank = cluster_rank(), peer = rank ^ 1;
-    const int m0 = (int) (blockIdx.x >> 1) * BM;
-    const int n_base = (int) rank * 256;                                   // this CTA's first token
-    const int ncols = min(256, a.NT - n_base);                             // its accumulator columns (multiple of 16, >= 16)
-    const int KB = a.W.K / BK;
-
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < SA; s++) { mbar_init(a_full + s, PRODUCER_THREADS); mbar_init(a_done + s, 1); mbar_init(a_empty + s, 2); }
-        for (int s = 0; s < SB2; s++) { mbar_init(b_full + s, 1); mbar_init(b_empty + s, 1); }
-        mbar_init(acc_full, 1);
-        mbar_fence_init();
-    }
-    if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"(256) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    tc_fence_before();
-    __syncthreads();
-    cluster_barrier();                                                     // both CTAs' barriers exist before anybody arrives remotely
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-
-    if (warp == 0) {
-        // ===== TMA producer: this CTA's activation tile [256 tokens x 64] of K block kb =====
-        if (lane == 0) {
-            for (int kb = 0; kb < KB; kb++) {
-                const int s = kb % SB2;
-                if (kb >= SB2) mbar_wait(b_empty + s, (uint32_t) ((kb / SB2 - 1) & 1));
-                mbar_expect_tx(b_full + s, (uint32_t) b_stage);
-                tma_load_2d(sB + (size_t) s * b_stage, &xmap, kb * BK, n_base, b_full + s);
-            }
-        }
-    } else if (warp == 1) {
-        // ===== MMA issuer =====
-        if (lane == 0) {
-            const uint32_t id = instr_desc_f16(ncols);
-            for (int kb = 0; kb < KB; kb++) {
-                const int sa = kb % SA, sb = kb % SB2;
-                mbar_wait_cluster(a_full + sa, (uint32_t) ((kb / SA) & 1));
-                mbar_wait(b_full + sb, (uint32_t) ((kb / SB2) & 1));
-                tc_fence_after();
-                const uint32_t a_addr = smem_u32(sA + (size_t) sa * A_STAGE), b_addr = smem_u32(sB + (size_t) sb * b_stage);
-#pragma unroll
-                for (int k = 0; k < BK / 16; k++) tc_mma_f16(tmem_base, umma_desc(a_addr + k * 32), umma_desc(b_addr + k * 32), id, (kb | k) != 0);
-                tc_commit(a_done + sa);
-                tc_commit(b_empty + sb);
-            }
-            tc_commit(acc_full);
-        }
-    } else if (warp == THREADS / 32) {
-        // ===== relay: "this CTA has consumed stage s" -> the CTA that refills stage s (CTA s % 2) =====
-        if (lane == 0) {
-            for (int kb = 0; kb + SA < KB; kb++) {                         // only uses that are followed by a refill
-                const int s = kb % SA;
-                mbar_wait(a_done + s, (uint32_t) ((kb / SA) & 1));
-                mbar_arrive_cluster(map_peer(smem_u32(a_empty + s), (uint32_t) (s & 1)));
-            }
-        }
-    } else {
-        // ===== dequant producers: 4 threads per weight row, K blocks kb = rank, rank + 2, ... ; every tile goes to both CTAs =====
-        const int t = threadIdx.x - 64, r = t >> 2, h = t & 3;
-        const size_t row = (size_t) min(m0 + r, a.W.M - 1);
-        RawQ4K raw, raw1;
-        if (TYPE == T_Q4_K) { raw = load_q4k(a.W, row, min((int) rank, KB - 1), h); raw1 = load_q4k(a.W, row, min((int) rank + 2, KB - 1), h); }
-        const int sw = r & 7;
-        for (int kb = (int) rank; kb < KB; kb += 2) {
-            const int s = kb % SA;                                         // s % 2 == rank: this CTA owns stage s for the whole kernel
-            Chunks ch;
-            if (TYPE == T_Q4_K) {
-                ch = dequant_q4k(raw);
-                raw = raw1;
-                if (kb + 4 < KB) raw1 = load_q4k(a.W, row, kb + 4, h);
-            } else ch = dequant_generic(a.W, row, kb * BK, h);
-            if (kb >= SA) mbar_wait_cluster(a_empty + s, (uint32_t) ((kb / SA - 1) & 1));     // both CTAs' MMAs are done with the previous tenant
-            const uint32_t l0 = smem_u32(sA + (size_t) s * A_STAGE + r * 128 + ((h ^ sw) << 4)), l1 = smem_u32(sA + (size_t) s * A_STAGE + r * 128 + (((4 + h) ^ sw) << 4));
-            *reinterpret_cast<uint4 *>(sA + (size_t) s * A_STAGE + r * 128 + ((h ^ sw) << 4)) = ch.c[0];
-            *reinterpret_cast<uint4 *>(sA + (size_t) s * A_STAGE + r * 128 + (((4 + h) ^ sw) << 4)) = ch.c[1];
-            st_cluster_v4(map_peer(l0, peer), ch.c[0]);
-            st_cluster_v4(map_peer(l1, peer), ch.c[1]);
-            asm volatile("fence.proxy.async;" ::: "memory");               // generic-proxy stores (local and remote) -> visible to the tensor cores (async proxy)
-            mbar_arrive_cluster(map_peer(smem_u32(a_full + s), rank));
-            mbar_arrive_cluster(map_peer(smem_u32(a_full + s), peer));
-        }
-        // ===== epilogue: TMEM -> registers -> global =====
-        mbar_wait(acc_full, 0);
-        tc_fence_after();
-        const int q = warp & 3, half_id = (warp - 2) >> 2;
-        const int m = m0 + q * 32 + lane;
-        const int nchunks = (ncols + 31) / 32;
-        for (int c = half_id; c < nchunks; c += PRODUCER_THREADS / 128) {
-            uint32_t v[32];
-            tmem_ld32(tmem_base + ((uint32_t) (q * 32) << 16) + (uint32_t) (c * 32), v);
-            if (m < a.W.M) {
-#pragma unroll
-                for (int j = 0; j < 32; j++) {
-                    const int n = n_base + c * 32 + j;
-                    if (n < a.N) {
-                        float y = __uint_as_float(v[j]);
-                        if (a.epi_gelu) { const float f = __half2float(__float2half_rn(y));
-                            y = __half2float(__float2half_rn(0.5f * f * (1.0f + tanhf(0.79788456080286535587989211986876f * f * (1.0f + 0.044715f * f * f))))); }
-                        a.Y[(size_t) n * a.y_stride + m] = y;
-                    }
-                }
-            }
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    cluster_barrier();                                                     // nobody leaves while the peer may still write into its shared memory / barriers
-    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(256) : "memory");
-}
-
-template <int TYPE>
-void launch_typed2(const CUtensorMap & map, const GemmArgs & a, cudaStream_t stream) {
-    const size_t smem = 1024 + (size_t) SA * A_STAGE + (size_t) SB2 * 256 * 128 + 256;
-    static bool set = false;
-    if (!set) { B200_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc2_kernel<TYPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); set = true; }
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3((unsigned) (2 * ((a.W.M + BM - 1) / BM))); cfg.blockDim = dim3(THREADS2); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension; attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
-    B200_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_tc2_kernel<TYPE>, map, a));
-}
-
 PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
     static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
     if (!fn) {
@@ -442,6 +281,7 @@ bool launch_gemm_tc(const WPlanes & W, const __half * X, int64_t x_stride, int N
     // fewer than ~100 row tiles cannot fill 148 SMs: split K in two (deterministic, see GemmArgs::ksplit)
     const int tiles = (W.M + BM - 1) / BM;
     a.ksplit = (tiles < 100 && !epi_gelu && W.K / BK >= 8 && !getenv("B200_GEMM_NOSPLIT")) ? 2 : 1;
+    if (a.ksplit > 1) B200_CUDA_CHECK(cudaMemsetAsync(Y, 0, ((size_t) (N - 1) * y_stride + W.M) * sizeof(float), stream));
     CUtensorMap map;
     const cuuint64_t gdim[2] = { (cuuint64_t) W.K, (cuuint64_t) N };
     const cuuint64_t gstr[1] = { (cuuint64_t) x_stride * 2 };
@@ -450,14 +290,6 @@ bool launch_gemm_tc(const WPlanes & W, const __half * X, int64_t x_stride, int N
     const CUresult rc = get_encode()(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void *) X, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (rc != CUDA_SUCCESS) { fprintf(stderr, "b200: cuTensorMapEncodeTiled failed (%d)\n", (int) rc); exit(1); }
-    if (a.NT > 256 && !getenv("B200_GEMM_V1")) {                           // two-CTA cluster sharing the dequantised weight tile (no split-K needed)
-        switch (W.type) {
-            case T_Q4_K: launch_typed2<T_Q4_K>(map, a, stream); break;
-            default:     launch_typed2<-1>(map, a, stream); break;
-        }
-        return true;
-    }
-    if (a.ksplit > 1) B200_CUDA_CHECK(cudaMemsetAsync(Y, 0, ((size_t) (N - 1) * y_stride + W.M) * sizeof(float), stream));
     const size_t b_stage = (size_t) a.box_rows * (a.NT > 256 ? 2 : 1) * 128;
     const size_t smem = 1024 + (size_t) SA * A_STAGE + SB * b_stage + 256;
     switch (W.type) {

@@ -90,20 +90,61 @@ def test_two_rank_pipeline_gloo():
     assert np.array_equal(got[1], whole.eval(np.array([42], np.int32), 3, all_logits=True))
 
 
-def test_committed_bench_line_has_every_contract_key():
-    """profiles/r1_bench_final.json is the line `python bench.py` printed on a B200 at the end of the round: the keys the
-    driver and the judge read must all be there (guards bench.py's JSON contract against accidental edits)"""
-    import json, os
-    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "r1_bench_final.json")
-    d = json.load(open(path))
+def test_bench_stage_ranges_and_byte_counts():
+    """bench.py's host logic (no GPU): layer ranges balanced by bytes cover the model contiguously with the last rank relieved by the
+    lm_head it also streams; the byte counts are BASELINE.md's"""
+    import bench
+    assert bench.weight_elems(bench.MODELS["falcon40b"]) * bench.BYTES_PER_WEIGHT[bench.Q4_K] == 23231987712
+    assert bench.weight_elems(bench.MODELS["falcon7b"]) * bench.BYTES_PER_WEIGHT[bench.Q4_0] == 3893299200
+    assert bench.weight_elems(bench.MODELS["falcon40b"]) * bench.BYTES_PER_WEIGHT[bench.Q3_K] == 17746657280
+    assert abs(bench.weight_elems(bench.MODELS["falcon180b"]) * bench.BYTES_PER_WEIGHT[bench.Q4_K] - 100.44e9) < 0.01e9
+    assert bench.kv_bytes(bench.MODELS["falcon180b"], 8192) == 80 * 2 * 8192 * 8 * 64 * 4
+    for name, hp in bench.MODELS.items():
+        per_layer = hp["n_embd"] * ((hp["n_head"] + 2 * hp["n_head_kv"]) * 64 + 9 * hp["n_embd"])
+        head = hp["n_embd"] * hp["n_vocab"]
+        for world in (1, 2, 4, 8):
+            r = bench.stage_ranges(hp, world)
+            assert r[0][0] == 0 and r[-1][1] == hp["n_layer"] and all(r[i][1] == r[i + 1][0] for i in range(world - 1))
+            loads = [(b - a) * per_layer + (head if i == world - 1 else 0) for i, (a, b) in enumerate(r)]
+            assert max(loads) - min(loads) <= per_layer + 1, (name, world, r)       # balanced to within one layer's bytes
+            assert all(b > a for a, b in r)
+
+
+def test_bench_line_contract(monkeypatch, capsys):
+    """the JSON line bench.py prints carries every key the driver reads: bench.main() run with the GPU legs replaced by canned
+    measurements (the contract lives in main's assembly code, which is what this exercises)"""
+    import json
+    import bench
+
+    class FakeCx:
+        rank, world, local_rank, dist = 0, 1, 0, None
+        def make_model(self, *a, **k):
+            class M:
+                def free(self): pass
+            return M()
+    canned = {"tok_s": 208.0, "ms_per_step": 4.8, "e2e_tok_s": 205.0, "e2e_ms_per_step": 4.88, "wall_ms_per_step": 4.81, "gpu_launches": 10880,
+              "weight_bytes": 23231987712.0, "step_bytes": 23239000000.0, "n_past": [9, 29], "step_achieved_GBs": 4833.0, "step_frac": 0.734,
+              "roofline_tok_s": 283.4, "_probe": (12.7, 723, 69696000000)}
+    monkeypatch.setattr(bench, "Ctx", FakeCx)
+    monkeypatch.setattr(bench, "decode_leg", lambda *a, **k: dict(canned))
+    monkeypatch.setattr(bench, "prompt_leg", lambda *a, **k: {"tok_s": 11000.0, "seconds": 0.186, "roofline": {"bound": "tensor", "frac": 0.64}})
+    monkeypatch.setattr(bench, "matvec_leg", lambda *a, **k: {"gpu": {"us_per_call": 4.2}})
+    monkeypatch.setattr(bench, "FullModelFile", lambda *a, **k: type("F", (), {"close": lambda self: None})())
+    monkeypatch.setattr(bench, "dropin_decode", lambda *a, **k: {"value": 93.0, "unit": "tok/s"})
+    monkeypatch.setattr(bench, "reference_cpu_decode", lambda *a, **k: {"value": 2.7, "unit": "tok/s", "cores": 16, "kind": "reference", "sample": "canned", "extrapolated": False})
+    monkeypatch.setattr(bench.ClockSampler, "__init__", lambda self, dev: None)
+    monkeypatch.setattr(bench.ClockSampler, "stop", lambda self: {"sm_mhz": 1965.0, "sm_max_mhz": 1965.0, "reasons": []})
+    monkeypatch.setattr(sys, "argv", ["bench.py", "--gpus", "1", "--steps", "20", "--warmup", "5"])
+    bench.main()
+    d = json.loads(capsys.readouterr().out.strip().splitlines()[-1])
     for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
-              "dtype", "data", "config", "e2e", "gpu_launches", "clocks", "roofline", "cpu_baseline"):
+              "dtype", "data", "config", "e2e", "gpu_launches", "clocks", "roofline", "cpu_baseline", "prompt", "configs", "e2e_dropin"):
         assert k in d, k
+    assert d["metric"] == "falcon40b_q4_k_decode_tokens_per_s" and d["steps"] == 20 and d["warmup"] == 5 and d["n_gpus"] == 1
     assert d["config"]["workload"] and "model" not in d["config"]
     assert set(("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step")) <= set(d["e2e"])
     assert set(("bound", "achieved", "peak", "unit", "frac", "traffic")) <= set(d["roofline"])
     assert abs(d["roofline"]["frac"] - d["roofline"]["achieved"] / d["roofline"]["peak"]) < 1e-9
     assert set(("value", "unit", "cores", "kind", "sample")) <= set(d["cpu_baseline"])
-    assert set(("sm_mhz", "sm_max_mhz", "reasons")) <= set(d["clocks"])
-    assert d["gpu_launches"] > 0 and d["higher_is_better"] is True and d["vs_baseline"] is None
-    assert d["e2e"]["value"] <= d["value"] * 1.02          # the host round trip cannot be faster than the device-resident step
+    assert d["higher_is_better"] is True and d["vs_baseline"] is None and d["value"] == 208.0 and d["e2e"]["value"] == 205.0
+    assert set(d["configs"]) == {"cfg1", "cfg2", "cfg4", "cfg5"}
