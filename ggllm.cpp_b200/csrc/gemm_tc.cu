@@ -250,6 +250,182 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
     if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(512) : "memory");
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// 256 < N <= 512: CTA PAIR (cta_group::2).  ncu on the single-CTA kernel (profiles/r2_gemm_tc.md): the dequantisation producers wait for
+// free stages, yet the tensor pipe is only 66 % busy -- every CTA pulls its own copy of the 64 KB activation tile per K block, 64 B/clk
+// per SM against a chip-wide L2 throughput of ~6300 B/clk = 42.6 B/clk per SM: 42.6 / 64 = 0.665.  In a pair the B operand of one
+// tcgen05.mma.cta_group::2 (M = 256: the two CTAs' 128 weight rows, N = 256 tokens) is split between the two CTAs' shared memories and
+// read by both tensor cores, so each CTA loads only HALF of every activation tile (32 KB per K block, 32 B/clk).
+//   CTA r of the pair: weight rows [m0 + 128 r, +128) dequantised by its own producers (as before); tokens [128 r, 128 r + 128) of
+//   token tile 0 and [256 + h r, ...) of token tile 1 (h = half of that tile) loaded by its own TMA thread;
+//   the LEADER (rank 0) issues every MMA; a_full / b_full live in the leader (producers of the peer arrive remotely, the peer's TMA
+//   signals the leader's barrier through the cta_group::2 form), a_empty / b_empty / acc_full are multicast commits to both CTAs.
+__device__ __forceinline__ uint32_t cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t map_to_rank(uint32_t saddr, uint32_t rank) { uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank)); return r; }
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" :: "r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t * bar, uint32_t phase) {     // acquire at cluster scope: data produced by the peer CTA
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAITC_%=:\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONEC_%=;\n\t"
+        "bra WAITC_%=;\n\t"
+        "DONEC_%=:\n\t}"
+        :: "r"(smem_u32(bar)), "r"(phase) : "memory");
+}
+__device__ __forceinline__ void cluster_barrier() { asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit_pair(uint64_t * bar) {          // arrives on `bar` in BOTH CTAs once the pair's MMAs issued so far are done
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" :: "r"(smem_u32(bar)), "h"((uint16_t) 3) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16_pair(uint32_t tmem_c, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t}"
+                 :: "r"(tmem_c), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(0) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(void * smem_dst, const CUtensorMap * map, int c0, int c1, uint64_t * leader_bar) {
+    // executed by both CTAs; the peer bit of the barrier address is cleared so that the bytes are counted by the leader's barrier
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 :: "r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(leader_bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ uint32_t instr_desc_f16_m256(int n) { return (1u << 4) | ((uint32_t) (n >> 3) << 17) | ((uint32_t) (256 >> 4) << 24); }
+
+constexpr int SB2 = 4, B2_STAGE = 2 * 128 * 128;                           // per CTA and K block: two 128-token x 64-half boxes = 32 KB
+template <int TYPE>
+__global__ void __launch_bounds__(THREADS, 1) gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap xmap, const GemmArgs a) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t * smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t) 1023);
+    uint8_t * sA = smem, * sB = smem + SA * A_STAGE;
+    uint64_t * bars = reinterpret_cast<uint64_t *>(sB + SB2 * B2_STAGE);
+    uint64_t * a_full = bars, * a_empty = bars + SA, * b_full = bars + 2 * SA, * b_empty = b_full + SB2, * acc_full = b_empty + SB2;
+    uint32_t * tmem_slot = reinterpret_cast<uint32_t *>(acc_full + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_rank();
+    const int m0 = (int) blockIdx.x * BM;                                  // blockIdx.x = 2 * pair + rank: consecutive row tiles
+    const int KBT = a.W.K / BK;
+    const int kb0 = (int) ((int64_t) KBT * blockIdx.y / a.ksplit), KB = (int) ((int64_t) KBT * (blockIdx.y + 1) / a.ksplit) - kb0;
+    const int n1 = a.NT - 256, h1 = n1 / 2;                                // token tile 1 and its per-CTA half (n1 % 32 == 0)
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < SA; s++) { mbar_init(a_full + s, 2 * (PRODUCER_THREADS / 32)); mbar_init(a_empty + s, 1); }    // one arrival per producer warp of each CTA
+        for (int s = 0; s < SB2; s++) { mbar_init(b_full + s, 1); mbar_init(b_empty + s, 1); }
+        mbar_init(acc_full, 1);
+        mbar_fence_init();
+    }
+    cluster_barrier();                                                     // (both CTAs) before the paired TMEM allocation and any remote arrive
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_barrier();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA: this CTA's halves of the two token tiles of K block kb =====
+        if (lane == 0) {
+            for (int kb = 0; kb < KB; kb++) {
+                const int s = kb % SB2;
+                if (kb >= SB2) mbar_wait(b_empty + s, (uint32_t) ((kb / SB2 - 1) & 1));
+                if (rank == 0) mbar_expect_tx(b_full + s, (uint32_t) (2 * B2_STAGE));      // both CTAs' bytes land on the leader's barrier
+                tma_load_2d_pair(sB + (size_t) s * B2_STAGE, &xmap, (kb0 + kb) * BK, (int) rank * 128, b_full + s);
+                tma_load_2d_pair(sB + (size_t) s * B2_STAGE + 128 * 128, &xmap, (kb0 + kb) * BK, 256 + (int) rank * h1, b_full + s);
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer: the leader CTA only =====
+        if (lane == 0 && rank == 0) {
+            const uint32_t id0 = instr_desc_f16_m256(256), id1 = instr_desc_f16_m256(n1);
+            for (int kb = 0; kb < KB; kb++) {
+                const int sa = kb % SA, sb = kb % SB2;
+                mbar_wait_cluster(a_full + sa, (uint32_t) ((kb / SA) & 1));
+                mbar_wait_cluster(b_full + sb, (uint32_t) ((kb / SB2) & 1));
+                tc_fence_after();
+                const uint32_t a_addr = smem_u32(sA + (size_t) sa * A_STAGE), b_addr = smem_u32(sB + (size_t) sb * B2_STAGE);
+#pragma unroll
+                for (int k = 0; k < BK / 16; k++) {
+                    const uint64_t da = umma_desc(a_addr + k * 32);
+                    tc_mma_f16_pair(tmem_base, da, umma_desc(b_addr + k * 32), id0, (kb | k) != 0);
+                    tc_mma_f16_pair(tmem_base + 256, da, umma_desc(b_addr + 128 * 128 + k * 32), id1, (kb | k) != 0);
+                }
+                tc_commit_pair(a_empty + sa);
+                tc_commit_pair(b_empty + sb);
+            }
+            tc_commit_pair(acc_full);
+        }
+    } else {
+        // ===== dequant producers (4 threads per weight row), then the epilogue: exactly the single-CTA kernel's, except for the arrival =====
+        const int t = threadIdx.x - 64, r = t >> 2, h = t & 3;
+        const size_t row = (size_t) min(m0 + r, a.W.M - 1);
+        RawQ4K raw, raw1;
+        PtrQ4K pq = ptr_q4k(a.W, row, kb0 + (KB > 1 ? 1 : 0), h);
+        if (TYPE == T_Q4_K) { const PtrQ4K p0 = ptr_q4k(a.W, row, kb0, h); raw = load_q4k(p0, kb0); raw1 = load_q4k(pq, kb0 + (KB > 1 ? 1 : 0)); }
+        const int sw = r & 7;
+        const uint32_t st0 = smem_u32(sA) + (uint32_t) (r * 128 + ((h ^ sw) << 4)), st1 = smem_u32(sA) + (uint32_t) (r * 128 + (((4 + h) ^ sw) << 4));
+        const uint32_t full0 = map_to_rank(smem_u32(a_full), 0);          // the leader's a_full[0] as a shared::cluster address
+        for (int kb = 0; kb < KB; kb++) {
+            const int s = kb % SA;
+            Chunks ch;
+            if (TYPE == T_Q4_K) {
+                ch = dequant_q4k(raw);
+                raw = raw1;
+                pq.q += 32; pq.sm += 4;
+                if (kb + 2 < KB) raw1 = load_q4k(pq, kb0 + kb + 2);
+            } else ch = dequant_generic(a.W, row, (kb0 + kb) * BK, h);
+            if (kb >= SA) mbar_wait(a_empty + s, (uint32_t) ((kb / SA - 1) & 1));
+            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" :: "r"(st0 + (uint32_t) s * A_STAGE), "r"(ch.c[0].x), "r"(ch.c[0].y), "r"(ch.c[0].z), "r"(ch.c[0].w) : "memory");
+            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" :: "r"(st1 + (uint32_t) s * A_STAGE), "r"(ch.c[1].x), "r"(ch.c[1].y), "r"(ch.c[1].z), "r"(ch.c[1].w) : "memory");
+            fence_proxy_async();                                           // generic-proxy stores -> visible to the tensor cores (async proxy)
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(full0 + (uint32_t) s * 8);  // one arrival per warp on the LEADER's barrier
+        }
+        mbar_wait(acc_full, 0);
+        tc_fence_after();
+        const int q = warp & 3, half_id = (warp - 2) >> 2;
+        const int m = m0 + q * 32 + lane;
+        const int nchunks = (a.NT + 31) / 32;
+        for (int c = half_id; c < nchunks; c += PRODUCER_THREADS / 128) {
+            uint32_t v[32];
+            tmem_ld32(tmem_base + ((uint32_t) (q * 32) << 16) + (uint32_t) (c * 32), v);
+            if (m < a.W.M) {
+#pragma unroll
+                for (int j = 0; j < 32; j++) {
+                    // accumulator column -> token: tile 0 = columns [0, 256), tile 1 = columns [256, 256 + n1)
+                    const int n = c * 32 + j;
+                    if (n < a.N) {
+                        float y = __uint_as_float(v[j]);
+                        if (a.epi_gelu) { const float f = __half2float(__float2half_rn(y));
+                            y = __half2float(__float2half_rn(0.5f * f * (1.0f + tanhf(0.79788456080286535587989211986876f * f * (1.0f + 0.044715f * f * f))))); }
+                        if (a.ksplit > 1) atomicAdd(a.Y + (size_t) n * a.y_stride + m, y);
+                        else a.Y[(size_t) n * a.y_stride + m] = y;
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_barrier();                                                     // the peer may still read this CTA's shared memory (B halves) / arrive on its barriers
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(512) : "memory");
+}
+
+template <int TYPE>
+void launch_typed_pair(const CUtensorMap & map, const GemmArgs & a, cudaStream_t stream) {
+    const size_t smem = 1024 + (size_t) SA * A_STAGE + (size_t) SB2 * B2_STAGE + 256;
+    static bool set = false;
+    if (!set) { B200_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_pair_kernel<TYPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); set = true; }
+    const int tiles = (a.W.M + BM - 1) / BM;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned) ((tiles + 1) / 2 * 2), (unsigned) a.ksplit); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension; attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    B200_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_tc_pair_kernel<TYPE>, map, a));
+}
+
 PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
     static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
     if (!fn) {
@@ -282,14 +458,22 @@ bool launch_gemm_tc(const WPlanes & W, const __half * X, int64_t x_stride, int N
     const int tiles = (W.M + BM - 1) / BM;
     a.ksplit = (tiles < 100 && !epi_gelu && W.K / BK >= 8 && !getenv("B200_GEMM_NOSPLIT")) ? 2 : 1;
     if (a.ksplit > 1) B200_CUDA_CHECK(cudaMemsetAsync(Y, 0, ((size_t) (N - 1) * y_stride + W.M) * sizeof(float), stream));
+    const bool pair = a.NT > 256 && (a.NT - 256) % 32 == 0 && !getenv("B200_GEMM_V1");      // CTA pair sharing the activation tile
     CUtensorMap map;
     const cuuint64_t gdim[2] = { (cuuint64_t) W.K, (cuuint64_t) N };
     const cuuint64_t gstr[1] = { (cuuint64_t) x_stride * 2 };
-    const cuuint32_t box[2] = { (cuuint32_t) BK, (cuuint32_t) a.box_rows };
+    const cuuint32_t box[2] = { (cuuint32_t) BK, (cuuint32_t) (pair ? 128 : a.box_rows) };
     const cuuint32_t estr[2] = { 1, 1 };
     const CUresult rc = get_encode()(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void *) X, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (rc != CUDA_SUCCESS) { fprintf(stderr, "b200: cuTensorMapEncodeTiled failed (%d)\n", (int) rc); exit(1); }
+    if (pair) {
+        switch (W.type) {
+            case T_Q4_K: launch_typed_pair<T_Q4_K>(map, a, stream); break;
+            default:     launch_typed_pair<-1>(map, a, stream); break;
+        }
+        return true;
+    }
     const size_t b_stage = (size_t) a.box_rows * (a.NT > 256 ? 2 : 1) * 128;
     const size_t smem = 1024 + (size_t) SA * A_STAGE + SB * b_stage + 256;
     switch (W.type) {
