@@ -532,7 +532,7 @@ static void enqueue_decode_fused(b200_falcon * f, int n_past, float theta_scale,
     auto skip = [&](const char * what) { return dbg && strstr(dbg, what) != nullptr; };
     // All four mat-vecs of a layer go back to back on ONE stream (each is launched with programmatic dependent launch,
     // so its weight prefetch overlaps the previous one's tail); the small attention kernels run beside ffn_up on the
-    // second stream:   s_main: LN -> qkv -> ffn_up(+GELU) -> ffn_down -> wo        s_mlp: rope+kv append -> attention
+    // second stream:   s_main: LN -> qkv -> ffn_up(+GELU) -> wo -> ffn_down        s_mlp: rope+kv append -> attention
     for (int l = 0; l < f->NL; l++) {
         const Layer & L = f->layers[l];
         const float * ra = l > 0 ? f->dn : nullptr, * rb = l > 0 ? f->ao : nullptr;
@@ -556,9 +556,12 @@ static void enqueue_decode_fused(b200_falcon * f, int n_past, float theta_scale,
         }
         B200_CUDA_CHECK(cudaEventRecord(f->e_join, sb));
         if (!skip("up")) launch_mmv(L.up, xm, f->up, f->FF, gelu, sa);                                           // :2389-2392
-        if (!skip("down")) launch_mmv(L.down, xup, f->dn, E, none, sa);                                         // :2394
+        // wo before ffn_down: the attention kernels of the side stream run BESIDE ffn_up (its 256-thread CTAs leave them registers);
+        // ffn_down's CTAs own the whole register file, so attention work still pending when ffn_up ends would otherwise be shut out
+        // until ffn_down has drained and wo would start after that (Falcon-7B: the attention chain is longer than ffn_up)
         B200_CUDA_CHECK(cudaStreamWaitEvent(sa, f->e_join, 0));
         if (!skip("wo")) launch_mmv(L.wo, xatt, f->ao, E, none, sa);                                          // :2370
+        if (!skip("down")) launch_mmv(L.down, xup, f->dn, E, none, sa);                                         // :2394
         f->launches += 8;
     }
     if (f->last) {

@@ -262,18 +262,12 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
 //   signals the leader's barrier through the cta_group::2 form), a_empty / b_empty / acc_full are multicast commits to both CTAs.
 __device__ __forceinline__ uint32_t cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ uint32_t map_to_rank(uint32_t saddr, uint32_t rank) { uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank)); return r; }
+// Arrival on a barrier of the peer CTA.  Default semantics (release at CTA scope), as CUTLASS signals the leader of a pair
+// (cutlass/arch/barrier.h: umma_arrive_2x1SM_sm0): what the arrival orders is this CTA's shared-memory tile -- made visible to the
+// async proxy by fence.proxy.async -- against the MMA the leader issues afterwards, and that MMA reads the tile through THIS CTA's
+// tensor core.  The .release.cluster / .acquire.cluster forms compile to MEMBAR.ALL.GPU + CCTL.IVALL per call (measured: 40 % slower).
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" :: "r"(cluster_addr) : "memory");
-}
-__device__ __forceinline__ void mbar_wait_cluster(uint64_t * bar, uint32_t phase) {     // acquire at cluster scope: data produced by the peer CTA
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "WAITC_%=:\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONEC_%=;\n\t"
-        "bra WAITC_%=;\n\t"
-        "DONEC_%=:\n\t}"
-        :: "r"(smem_u32(bar)), "r"(phase) : "memory");
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" :: "r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ void cluster_barrier() { asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit_pair(uint64_t * bar) {          // arrives on `bar` in BOTH CTAs once the pair's MMAs issued so far are done
@@ -341,8 +335,8 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_pair_kernel(const __grid_c
             const uint32_t id0 = instr_desc_f16_m256(256), id1 = instr_desc_f16_m256(n1);
             for (int kb = 0; kb < KB; kb++) {
                 const int sa = kb % SA, sb = kb % SB2;
-                mbar_wait_cluster(a_full + sa, (uint32_t) ((kb / SA) & 1));
-                mbar_wait_cluster(b_full + sb, (uint32_t) ((kb / SB2) & 1));
+                mbar_wait(a_full + sa, (uint32_t) ((kb / SA) & 1));
+                mbar_wait(b_full + sb, (uint32_t) ((kb / SB2) & 1));
                 tc_fence_after();
                 const uint32_t a_addr = smem_u32(sA + (size_t) sa * A_STAGE), b_addr = smem_u32(sB + (size_t) sb * B2_STAGE);
 #pragma unroll
@@ -380,7 +374,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_pair_kernel(const __grid_c
             asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" :: "r"(st1 + (uint32_t) s * A_STAGE), "r"(ch.c[1].x), "r"(ch.c[1].y), "r"(ch.c[1].z), "r"(ch.c[1].w) : "memory");
             fence_proxy_async();                                           // generic-proxy stores -> visible to the tensor cores (async proxy)
             __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(full0 + (uint32_t) s * 8);  // one arrival per warp on the LEADER's barrier
+            if (lane == 0) { if (rank == 0) mbar_arrive(a_full + s); else mbar_arrive_cluster(full0 + (uint32_t) s * 8); }   // one arrival per warp on the LEADER's barrier
         }
         mbar_wait(acc_full, 0);
         tc_fence_after();

@@ -195,7 +195,7 @@ static void launch_mode(const WPlanes & W, const FastX & X, float * y, int64_t y
     if (!set) { B200_CUDA_CHECK(cudaFuncSetAttribute(mmv_fast_kernel<TYPE, NT, J, D, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         // same L1/shared split as the small kernels of the other stream: an SM cannot host kernels with different carve-outs at once
         B200_CUDA_CHECK(cudaFuncSetAttribute(mmv_fast_kernel<TYPE, NT, J, D, MODE>, cudaFuncAttributePreferredSharedMemoryCarveout, B200_CARVEOUT)); set = true; }
-    int ctas = fast_num_sms() * (NT == 128 ? 4 : NT == 160 ? 3 : NT == 256 ? 2 : 1);
+    int ctas = fast_num_sms() * (NT == 128 ? 4 : NT == 160 || NT == 192 ? 3 : NT == 256 ? 2 : 1);
     if (ctas > (W.M + 3) / 4) ctas = (W.M + 3) / 4;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned) ctas, (unsigned) X.N); cfg.blockDim = dim3(NT); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
@@ -225,6 +225,9 @@ static bool launch_type(const WPlanes & W, const FastX & X, float * y, int64_t y
     else if (P > 128 && P <= 160 && D1 == 8 && !getenv("B200_NO_NT160")) launch_cfg<TYPE, 160, 1, D1>(W, X, y, y_stride, epi, stream);   // Falcon-7B: K = 4544 is 142 pieces
     else if (P <= 256) launch_cfg<TYPE, 256, 1, D1>(W, X, y, y_stride, epi, stream);
     else if (P <= 512) launch_cfg<TYPE, 512, 1, D1>(W, X, y, y_stride, epi, stream);
+    // Falcon-7B's ffn_down (K = 18176: 568 pieces): 3 pieces per thread of a 192-thread CTA use 568 of 576 slots; the 512 x 2 shape
+    // below would leave 45 % of its lanes without a piece (and its 128-register CTAs own the whole register file)
+    else if (P > 512 && P <= 576 && D1 == 8 && X.mode == 0 && !getenv("B200_NO_NT192")) launch_cfg<TYPE, 192, 3, 2>(W, X, y, y_stride, epi, stream);
     else if (P <= 1024) launch_cfg<TYPE, 512, 2, D1 / 2>(W, X, y, y_stride, epi, stream);
     else if (P <= 2048 && D1 == 8) launch_cfg<TYPE, 512, 4, 2>(W, X, y, y_stride, epi, stream);
     else return false;
