@@ -112,6 +112,7 @@ struct AttnDecArgs {
     int n_head, n_head_kv, G, n_past; const int * n_past_dev; int n_ctx; int64_t qkv_stride;
     unsigned long long * trace;
     ActQ qA; int has_q;          // optional quantised copy of the output row (see AttnParams::qout)
+    int fuse_rope; float theta_scale; float * kc_w; float * vc_w; __half * k16; __half * vt16; int ctx_pad;     // see AttnParams::fuse_rope
 };
 
 // 16 per-lane values -> lane l ends up with the warp total of value (l >> 1)
@@ -129,8 +130,13 @@ __device__ __forceinline__ float butterfly16(float (&v)[16], int lane) {
     r += __shfl_xor_sync(0xffffffffu, r, 1);
     return r;
 }
+// keys per split: at least AD_MIN_KEYS, so that a short context occupies few CTAs and the combine step reads few partials (at
+// n_past < 64 one CTA per KV-head group does everything; the other CTAs of the fixed grid only check in at the counter)
+#define AD_MIN_KEYS 64
+__device__ __forceinline__ int split_keys(int T) { return max(AD_MIN_KEYS, (T + AD_SPLITS - 1) / AD_SPLITS); }
+__device__ __forceinline__ int splits_used(int T) { const int per = split_keys(T); return (T + per - 1) / per; }
 __device__ __forceinline__ void split_range(int T, int split, int & k_lo, int & k_hi) {
-    const int per = (T + AD_SPLITS - 1) / AD_SPLITS;
+    const int per = split_keys(T);
     k_lo = min(T, split * per); k_hi = min(T, k_lo + per);
 }
 
@@ -141,22 +147,54 @@ __global__ void __launch_bounds__(AD_THREADS, 6) attn_dec_scores_kernel(const At
     const int h0 = kvh * a.G + blockIdx.z * AD_G, G = min(AD_G, a.G - (int) blockIdx.z * AD_G);      // this CTA's query heads: h0 .. h0 + G - 1
     const int n_past = a.n_past_dev ? *a.n_past_dev : a.n_past, T = n_past + 1;
     int k_lo, k_hi; split_range(T, split, k_lo, k_hi);
+    if (k_lo >= k_hi) { trace_end(a.trace); return; }            // a split without keys (short context): nothing to score, nobody reads its pmax
     const float scale = 1.0f / sqrtf(64.0f);
     const size_t kv_row = (size_t) a.n_head_kv * 64;
     float2 q[AD_G];
 #pragma unroll
     for (int h = 0; h < AD_G; h++)
         q[h] = h < G ? *reinterpret_cast<const float2 *>(a.qkv + (size_t) (h0 + h) * 64 + 2 * lane) : make_float2(0.f, 0.f);
+    // Fused RoPE + KV append (libfalcon.cpp:2229-2281).  A lane holds elements (2l, 2l+1) of a head; NeoX pairs element i < 32 with i + 32,
+    // i.e. with the same component of lane l ^ 16.  Angles as rope_pair (ops.cu): theta = n_past * theta_scale^i by repeated fp32 products.
+    float2 knew = make_float2(0.f, 0.f);
+    if (a.fuse_rope) {
+        const int i0 = (2 * lane) & 31;
+        float th0 = (float) n_past;
+        for (int k = 0; k < i0; k++) th0 = __fmul_rn(th0, a.theta_scale);
+        const float th1 = __fmul_rn(th0, a.theta_scale);
+        const float c0 = cosf(th0), s0 = sinf(th0), c1 = cosf(th1), s1 = sinf(th1);
+        auto rot = [&](float2 v) {
+            const float ox = __shfl_xor_sync(0xffffffffu, v.x, 16), oy = __shfl_xor_sync(0xffffffffu, v.y, 16);
+            return lane < 16 ? make_float2(__fsub_rn(__fmul_rn(v.x, c0), __fmul_rn(ox, s0)), __fsub_rn(__fmul_rn(v.y, c1), __fmul_rn(oy, s1)))     // x0 c - x1 s
+                             : make_float2(__fadd_rn(__fmul_rn(ox, s0), __fmul_rn(v.x, c0)), __fadd_rn(__fmul_rn(oy, s1), __fmul_rn(v.y, c1)));    // x0 s + x1 c
+        };
+#pragma unroll
+        for (int h = 0; h < AD_G; h++) q[h] = rot(q[h]);
+        knew = rot(*reinterpret_cast<const float2 *>(a.qkv + (size_t) (a.n_head + kvh) * 64 + 2 * lane));        // this position's key row, rotated
+        if (blockIdx.z == 0 && warp == 0 && n_past >= k_lo && n_past < k_hi) {                                     // one warp appends K and V to the cache
+            const size_t o = ((size_t) n_past * a.n_head_kv + kvh) * 64 + 2 * lane;
+            const float2 vnew = *reinterpret_cast<const float2 *>(a.qkv + (size_t) (a.n_head + a.n_head_kv + kvh) * 64 + 2 * lane);
+            *reinterpret_cast<float2 *>(a.kc_w + o) = knew;
+            *reinterpret_cast<float2 *>(a.vc_w + o) = vnew;
+            if (a.k16) {
+                *reinterpret_cast<__half2 *>(a.k16 + o) = __floats2half2_rn(knew.x, knew.y);
+                __half * vt = a.vt16 + ((size_t) kvh * 64 + 2 * lane) * a.ctx_pad + n_past;
+                vt[0] = __float2half_rn(vnew.x); vt[a.ctx_pad] = __float2half_rn(vnew.y);
+            }
+        }
+    }
     const int hh = lane >> 1;                                     // the head whose total this lane receives
     float lmax = -INFINITY;
     const float * kp = a.kc + (size_t) kvh * 64 + 2 * lane;
     // AD_B keys per warp and step, the next batch's rows already in flight (memory-level parallelism without more warps)
     float2 cur[AD_B], nxt[AD_B];
+    const int k_new = a.fuse_rope ? n_past : -1;                 // this key is not in the cache yet (another CTA may be writing it right now): use the registers
+    auto ld_key = [&](int kk) { return kk >= k_hi ? make_float2(0.f, 0.f) : kk == k_new ? knew : __ldg(reinterpret_cast<const float2 *>(kp + (size_t) kk * kv_row)); };
 #pragma unroll
-    for (int b = 0; b < AD_B; b++) { const int kk = k_lo + warp + b * AD_WARPS; cur[b] = kk < k_hi ? __ldg(reinterpret_cast<const float2 *>(kp + (size_t) kk * kv_row)) : make_float2(0.f, 0.f); }
+    for (int b = 0; b < AD_B; b++) cur[b] = ld_key(k_lo + warp + b * AD_WARPS);
     for (int k = k_lo + warp; k < k_hi; k += AD_B * AD_WARPS) {
 #pragma unroll
-        for (int b = 0; b < AD_B; b++) { const int kk = k + (AD_B + b) * AD_WARPS; nxt[b] = kk < k_hi ? __ldg(reinterpret_cast<const float2 *>(kp + (size_t) kk * kv_row)) : make_float2(0.f, 0.f); }
+        for (int b = 0; b < AD_B; b++) nxt[b] = ld_key(k + (AD_B + b) * AD_WARPS);
 #pragma unroll
         for (int b = 0; b < AD_B; b++) {
             const int kk = k + b * AD_WARPS;
@@ -198,9 +236,11 @@ __global__ void __launch_bounds__(AD_THREADS, 6) attn_dec_values_kernel(const At
     const int nk = k_hi - k_lo;
     const size_t kv_row = (size_t) a.n_head_kv * 64;
     trace_begin(a.trace);
+    const int n_used = splits_used(T);                            // splits 0 .. n_used - 1 hold keys
+    if (nk > 0) {
     if (tid < AD_G) {
         float mx = -INFINITY;
-        if (tid < G) for (int s = 0; s < AD_SPLITS; s++) mx = fmaxf(mx, a.pmax[(size_t) (h0 + tid) * AD_SPLITS + s]);
+        if (tid < G) for (int s = 0; s < n_used; s++) mx = fmaxf(mx, a.pmax[(size_t) (h0 + tid) * AD_SPLITS + s]);
         gmax[tid] = mx;
     }
     __syncthreads();
@@ -264,6 +304,7 @@ __global__ void __launch_bounds__(AD_THREADS, 6) attn_dec_values_kernel(const At
         for (int w = 1; w < AD_WARPS; w++) { r.x += oacc[w][h][l].x; r.y += oacc[w][h][l].y; }
         if (h < G) *reinterpret_cast<float2 *>(a.opart + ((size_t) (split * a.n_head + h0 + h)) * 64 + 2 * l) = r;
     }
+    }   // nk > 0
     // the last CTA of this KV head combines the splits
     __threadfence();
     __syncthreads();
@@ -274,7 +315,7 @@ __global__ void __launch_bounds__(AD_THREADS, 6) attn_dec_values_kernel(const At
     __threadfence();
     if (tid < AD_G) {
         double s = 0.0;
-        if (tid < G) for (int sp = 0; sp < AD_SPLITS; sp++) s += __ldcg(a.psum + (size_t) (h0 + tid) * AD_SPLITS + sp);
+        if (tid < G) for (int sp = 0; sp < n_used; sp++) s += __ldcg(a.psum + (size_t) (h0 + tid) * AD_SPLITS + sp);
         inv_s[tid] = (float) (1.0 / s);
     }
     __syncthreads();
@@ -286,13 +327,14 @@ __global__ void __launch_bounds__(AD_THREADS, 6) attn_dec_values_kernel(const At
         const float * base = a.opart + (size_t) h0 * 64;
         const int hA = tid / 8;
 #pragma unroll 1
-        for (int sp = 0; sp < AD_SPLITS; sp += 8) {
+        for (int sp = 0; sp < n_used; sp += 8) {
             float4 t0[8], t1[8];
 #pragma unroll
             for (int u = 0; u < 8; u++) {
                 const float * ps = base + (size_t) (sp + u) * a.n_head * 64;
-                t0[u] = hA < G ? __ldcg(reinterpret_cast<const float4 *>(ps) + i0) : make_float4(0.f, 0.f, 0.f, 0.f);
-                t1[u] = hA < G ? __ldcg(reinterpret_cast<const float4 *>(ps) + i1) : make_float4(0.f, 0.f, 0.f, 0.f);
+                const bool live = hA < G && sp + u < n_used;              // partials of splits without keys were never written
+                t0[u] = live ? __ldcg(reinterpret_cast<const float4 *>(ps) + i0) : make_float4(0.f, 0.f, 0.f, 0.f);
+                t1[u] = live ? __ldcg(reinterpret_cast<const float4 *>(ps) + i1) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
 #pragma unroll
             for (int u = 0; u < 8; u++) {                                   // fixed split order: deterministic
@@ -329,7 +371,7 @@ static bool launch_attention_split(const float * qkv, const float * k_cache, con
     if (!scratch || p.n_tok != 1 || p.head_dim != 64 || p.n_head % p.n_head_kv || getenv("B200_ATTN_NOSPLIT")) return false;
     const int G = p.n_head / p.n_head_kv, groups = (G + AD_G - 1) / AD_G;
     if ((size_t) p.n_head_kv * groups * 4 > AD_CTR_BYTES) return false;
-    const int per_max = (p.n_ctx + AD_SPLITS - 1) / AD_SPLITS;
+    const int per_max = max(AD_MIN_KEYS, (p.n_ctx + AD_SPLITS - 1) / AD_SPLITS);
     const size_t smem = (size_t) per_max * AD_G * 4;
     if (smem > 160 * 1024) return false;
     AttnDecArgs a;
@@ -342,6 +384,8 @@ static bool launch_attention_split(const float * qkv, const float * k_cache, con
     a.qkv = qkv; a.kc = k_cache; a.vc = v_cache; a.out = out;
     a.n_head = p.n_head; a.n_head_kv = p.n_head_kv; a.G = p.n_head / p.n_head_kv; a.n_past = p.n_past; a.n_past_dev = p.n_past_dev; a.n_ctx = p.n_ctx;
     a.qkv_stride = p.qkv_stride;
+    a.fuse_rope = p.fuse_rope; a.theta_scale = p.rope_theta_scale; a.kc_w = const_cast<float *>(k_cache); a.vc_w = const_cast<float *>(v_cache);
+    a.k16 = p.k16; a.vt16 = p.vt16; a.ctx_pad = attention_ctx_pad(p.n_ctx);
     // Q8_K blocks are 256 outputs = 4 heads: they must not straddle the 16-head groups the CTAs combine
     a.has_q = p.qout != nullptr && (p.qout->type != T_Q8_K || G % 4 == 0);
     if (a.has_q) a.qA = *p.qout;
@@ -368,6 +412,10 @@ int launch_attention(const float * qkv, const float * k_cache, const float * v_c
                       const AttnParams & p, float * scratch, cudaStream_t stream) {
     if (p.n_tok <= 0) return 0;
     if (launch_attention_split(qkv, k_cache, v_cache, out, p, scratch, stream)) return 2;
+    if (p.fuse_rope) {                                         // fallback kernel: RoPE + append in their own kernel, in place, as before
+        AttnParams pr = p; pr.fuse_rope = 0;
+        launch_rope_kv_append(const_cast<float *>(qkv), const_cast<float *>(k_cache), const_cast<float *>(v_cache), pr, p.rope_theta_scale, stream);
+    }
     B200_ASSERT(p.qout == nullptr && "attention: a quantised output copy needs the split-KV kernels");
     B200_ASSERT(p.head_dim % 4 == 0 && ATT_THREADS % p.head_dim == 0);
     // shared memory is sized for the worst case so that a captured graph stays valid while n_past grows

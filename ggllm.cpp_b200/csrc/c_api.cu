@@ -266,7 +266,7 @@ void b200_layernorm_q(float * x, int64_t x_stride, const float * ra, const float
 int b200_attention_decode(float * qkv, float * kc, float * vc, float * out, int n_head, int n_head_kv, int head_dim, int n_past, int n_ctx,
                           int n_ctx_rope, b200_actq * qout) {
     AttnParams p = { n_head, n_head_kv, head_dim, 1, n_past, nullptr, n_ctx, (int64_t) (n_head + 2 * n_head_kv) * head_dim, nullptr, nullptr };
-    launch_rope_kv_append(qkv, kc, vc, p, rope_theta_scale_host(head_dim, n_ctx_rope ? n_ctx_rope : n_ctx, 1, 2.0f, 0), g_stream);
+    p.fuse_rope = 1; p.rope_theta_scale = rope_theta_scale_host(head_dim, n_ctx_rope ? n_ctx_rope : n_ctx, 1, 2.0f, 0);      // as the engine: RoPE + append inside
     const size_t sb = attention_scratch_bytes(p);
     float * sc = sb ? (float *) scratch(sb) : nullptr;
     if (sc) B200_CUDA_CHECK(cudaMemsetAsync(sc, 0, 4096, g_stream));

@@ -546,7 +546,7 @@ static void enqueue_decode_fused(b200_falcon * f, int n_past, float theta_scale,
         const size_t kvoff = (size_t) l * f->hp.n_ctx * f->HKV * f->D;
         if (f->k16) { ap.k16 = f->k16 + (size_t) l * f->shadow_layer; ap.vt16 = f->vt16 + (size_t) l * f->shadow_layer; }
         if (!skip("attn")) {
-        launch_rope_kv_append(f->qkv, f->k_cache + kvoff, f->v_cache + kvoff, ap, theta_scale, sb);             // :2229-2281
+        ap.fuse_rope = 1; ap.rope_theta_scale = theta_scale;                                                    // :2229-2281: RoPE + KV append inside the attention launch
         // wo's activation quantisation: done by the attention kernel's combine step when its blocks fit the head groups,
         // else by a kernel of its own; either way off the critical path
         const bool fold_q = f->attn_dec_scratch && f->D == 64 && !getenv("B200_ATTN_NOSPLIT") && !getenv("B200_ATTN_NOFOLD") && (xatt.type != T_Q8_K || (f->H / f->HKV) % 4 == 0);
@@ -562,7 +562,7 @@ static void enqueue_decode_fused(b200_falcon * f, int n_past, float theta_scale,
         B200_CUDA_CHECK(cudaStreamWaitEvent(sa, f->e_join, 0));
         if (!skip("wo")) launch_mmv(L.wo, xatt, f->ao, E, none, sa);                                          // :2370
         if (!skip("down")) launch_mmv(L.down, xup, f->dn, E, none, sa);                                         // :2394
-        f->launches += 8;
+        f->launches += 7;
     }
     if (f->last) {
         launch_layernorm_q(f->inp, E, f->NL > 0 ? f->dn : nullptr, f->NL > 0 ? f->ao : nullptr, E, f->lnf_g, f->lnf_b, &xf, nullptr, nullptr, nullptr, E, 1, sa);   // :2399-2400, 2422-2431
@@ -609,7 +609,8 @@ static void enqueue_eval(b200_falcon * f, int N, int n_past, float theta_scale, 
         AttnParams ap = { f->H, f->HKV, f->D, N, n_past, graph_mode ? f->n_past_dev : nullptr, f->hp.n_ctx, (int64_t) f->QKV, nullptr };
         const size_t kvoff = (size_t) l * f->hp.n_ctx * f->HKV * f->D;
         if (f->k16) { ap.k16 = f->k16 + (size_t) l * f->shadow_layer; ap.vt16 = f->vt16 + (size_t) l * f->shadow_layer; }
-        launch_rope_kv_append(f->qkv, f->k_cache + kvoff, f->v_cache + kvoff, ap, theta_scale, sa);             // :2229-2281
+        if (N == 1) { ap.fuse_rope = 1; ap.rope_theta_scale = theta_scale; }                                    // decode: RoPE + KV append inside the attention launch
+        else launch_rope_kv_append(f->qkv, f->k_cache + kvoff, f->v_cache + kvoff, ap, theta_scale, sa);        // :2229-2281
         if (N > 1 && !graph_mode) {
             // tensor-core kernel (no scratch); the CUDA-core fallback (N <= 8 or head_dim != 64) materialises the score matrix
             if (launch_attention_ws(f->qkv, f->att, E, ap, sa)) {}

@@ -73,6 +73,10 @@ struct AttnParams {
     // optional fp16 shadow of this layer's cache for the prompt kernel (attention_ws.cu): k16 [n_ctx][n_head_kv][64],
     // vt16 [n_head_kv][64][attention_ctx_pad(n_ctx)] (V transposed); rope_kv_append keeps it in step with the fp32 cache
     __half * k16; __half * vt16;
+    // decode (n_tok == 1): RoPE of Q / K and the KV append are done by launch_attention itself (inside the split-KV scores kernel, or by
+    // rope_kv_append_kernel in front of the fallback kernel) instead of by a separate launch_rope_kv_append: one kernel less on the
+    // decode step's attention chain.  qkv is then NOT rotated in place.
+    int fuse_rope; float rope_theta_scale;
 };
 // fused: rope(Q), rope(K) -> K cache append, V cache append      (libfalcon.cpp:2229-2281)
 void   launch_rope_kv_append(float * qkv, float * k_cache, float * v_cache, const AttnParams & p, float theta_scale, cudaStream_t stream);
