@@ -147,6 +147,7 @@ __global__ void __launch_bounds__(AD_THREADS, 6) attn_dec_scores_kernel(const At
     const int h0 = kvh * a.G + blockIdx.z * AD_G, G = min(AD_G, a.G - (int) blockIdx.z * AD_G);      // this CTA's query heads: h0 .. h0 + G - 1
     const int n_past = a.n_past_dev ? *a.n_past_dev : a.n_past, T = n_past + 1;
     int k_lo, k_hi; split_range(T, split, k_lo, k_hi);
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the values kernel may take its place on the SMs now (it waits for this grid to finish)
     if (k_lo >= k_hi) { trace_end(a.trace); return; }            // a split without keys (short context): nothing to score, nobody reads its pmax
     const float scale = 1.0f / sqrtf(64.0f);
     const size_t kv_row = (size_t) a.n_head_kv * 64;
@@ -237,6 +238,7 @@ __global__ void __launch_bounds__(AD_THREADS, 6) attn_dec_values_kernel(const At
     const size_t kv_row = (size_t) a.n_head_kv * 64;
     trace_begin(a.trace);
     const int n_used = splits_used(T);                            // splits 0 .. n_used - 1 hold keys
+    asm volatile("griddepcontrol.wait;" ::: "memory");            // launched programmatically behind the scores kernel: its S / pmax / KV append are complete from here on
     if (nk > 0) {
     if (tid < AD_G) {
         float mx = -INFINITY;
@@ -305,6 +307,12 @@ __global__ void __launch_bounds__(AD_THREADS, 6) attn_dec_values_kernel(const At
         if (h < G) *reinterpret_cast<float2 *>(a.opart + ((size_t) (split * a.n_head + h0 + h)) * 64 + 2 * l) = r;
     }
     }   // nk > 0
+    if (n_used == 1) {
+        // short context: split 0 holds every key, its CTA combines its own partials (written above, visible to the CTA after the
+        // barrier) without the fence / counter round trips; the other CTAs of the fixed grid have nothing to do
+        if (split != 0) { trace_end(a.trace); return; }
+        __syncthreads();
+    } else {
     // the last CTA of this KV head combines the splits
     __threadfence();
     __syncthreads();
@@ -313,6 +321,7 @@ __global__ void __launch_bounds__(AD_THREADS, 6) attn_dec_values_kernel(const At
     __syncthreads();
     if (!s_last) { trace_end(a.trace); return; }
     __threadfence();
+    }
     if (tid < AD_G) {
         double s = 0.0;
         if (tid < G) for (int sp = 0; sp < n_used; sp++) s += __ldcg(a.psum + (size_t) (h0 + tid) * AD_SPLITS + sp);
@@ -402,8 +411,14 @@ static bool launch_attention_split(const float * qkv, const float * k_cache, con
     attn_dec_scores_kernel<<<grid, AD_THREADS, 0, stream>>>(a);
     B200_CUDA_CHECK(cudaGetLastError());
     a.trace = b200_trace_slot("attn_values");
-    attn_dec_values_kernel<<<grid, AD_THREADS, smem, stream>>>(a, per_max);
-    B200_CUDA_CHECK(cudaGetLastError());
+    {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = grid; cfg.blockDim = dim3(AD_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr; cfg.numAttrs = getenv("B200_NO_PDL") ? 0 : 1;
+        B200_CUDA_CHECK(cudaLaunchKernelEx(&cfg, attn_dec_values_kernel, a, per_max));
+    }
     return true;
 }
 

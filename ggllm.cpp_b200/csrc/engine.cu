@@ -532,7 +532,7 @@ static void enqueue_decode_fused(b200_falcon * f, int n_past, float theta_scale,
     auto skip = [&](const char * what) { return dbg && strstr(dbg, what) != nullptr; };
     // All four mat-vecs of a layer go back to back on ONE stream (each is launched with programmatic dependent launch,
     // so its weight prefetch overlaps the previous one's tail); the small attention kernels run beside ffn_up on the
-    // second stream:   s_main: LN -> qkv -> ffn_up(+GELU) -> wo -> ffn_down        s_mlp: rope+kv append -> attention
+    // second stream:   s_main: LN -> qkv -> ffn_up(+GELU) -> ffn_down -> wo   (7B: wo -> ffn_down)     s_mlp: attention (RoPE + KV append inside)
     for (int l = 0; l < f->NL; l++) {
         const Layer & L = f->layers[l];
         const float * ra = l > 0 ? f->dn : nullptr, * rb = l > 0 ? f->ao : nullptr;
@@ -556,12 +556,15 @@ static void enqueue_decode_fused(b200_falcon * f, int n_past, float theta_scale,
         }
         B200_CUDA_CHECK(cudaEventRecord(f->e_join, sb));
         if (!skip("up")) launch_mmv(L.up, xm, f->up, f->FF, gelu, sa);                                           // :2389-2392
-        // wo before ffn_down: the attention kernels of the side stream run BESIDE ffn_up (its 256-thread CTAs leave them registers);
-        // ffn_down's CTAs own the whole register file, so attention work still pending when ffn_up ends would otherwise be shut out
-        // until ffn_down has drained and wo would start after that (Falcon-7B: the attention chain is longer than ffn_up)
+        // The attention kernels of the side stream run BESIDE ffn_up, and beside ffn_down too when its CTAs leave them registers
+        // (Falcon-40B / 180B: at long contexts the attention outlasts ffn_up, 132 tok/s at 8k that way against 109 with wo first).
+        // Falcon-7B's ffn_down shape fills the SMs: attention work still pending when ffn_up ends would be shut out until it had
+        // drained, so there wo (which has to wait for the attention anyway) goes first.
+        const bool wo_first = mmv_fast_fills_sm(L.down);
+        if (!wo_first && !skip("down")) launch_mmv(L.down, xup, f->dn, E, none, sa);                            // :2394
         B200_CUDA_CHECK(cudaStreamWaitEvent(sa, f->e_join, 0));
         if (!skip("wo")) launch_mmv(L.wo, xatt, f->ao, E, none, sa);                                          // :2370
-        if (!skip("down")) launch_mmv(L.down, xup, f->dn, E, none, sa);                                         // :2394
+        if (wo_first && !skip("down")) launch_mmv(L.down, xup, f->dn, E, none, sa);
         f->launches += 7;
     }
     if (f->last) {

@@ -262,6 +262,13 @@ bool mmv_fast_supports(int wtype, int K, int mode) {
     const int P = wtype == T_Q4_K ? K / 32 : K / 32;
     return K <= 64 * 1024 && P <= (mode == 2 ? 512 : 2048);
 }
+// true when the shape chosen for W (3 CTAs of 192 threads at 96 registers) leaves no room on an SM for a side-stream kernel:
+// the decode step then schedules wo BEFORE this mat-vec (engine.cu).  The 512-thread shapes leave ~14k registers: one attention CTA fits.
+bool mmv_fast_fills_sm(const WPlanes & W) {
+    if ((W.type != T_Q4_K && W.type != T_Q4_0) || getenv("B200_NO_NT192")) return false;
+    const int P = W.K / 32;
+    return P > 512 && P <= 576;
+}
 bool launch_mmv_fast(const WPlanes & W, const ActQ & A, float * y, int64_t y_stride, MmvEpilogue e, cudaStream_t stream) {
     FastX X{}; X.mode = 0; X.A = A; X.N = A.N;
     return launch_mmv_fast_x(W, X, y, y_stride, e, stream);
