@@ -14,7 +14,7 @@
 // libfalcon.cpp:2256-2281, is replaced by a plain append -- values are identical).
 //
 // v1 kernel: one CTA per (query head, query token); scores live in shared memory (T floats).  Exact oracle
-// semantics (global max before exp).  Fine for decode; the prompt path gets a tiled tensor-core kernel later.
+// semantics (global max before exp).  Fine for decode; prompts go through attention_ws.cu.
 #include "kernels.h"
 #include "actquant.cuh"
 

@@ -148,7 +148,6 @@ size_t attention_prefill_scratch_bytes(int n_head, int n_tok, int T) {
 
 void launch_attention_prefill(const float * qkv, const float * k_cache, const float * v_cache, float * out, int64_t out_stride,
                               const AttnParams & p, float * scratch, cudaStream_t stream) {
-    if (launch_attention_tc(qkv, k_cache, v_cache, out, out_stride, p, stream)) return;     // tensor-core path (head_dim 64)
     B200_ASSERT(p.head_dim <= PT && p.n_past_dev == nullptr);
     PrefillArgs a;
     a.qkv = qkv; a.kc = k_cache; a.vc = v_cache; a.out = out;

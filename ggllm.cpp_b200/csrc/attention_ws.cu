@@ -6,9 +6,9 @@
 // the tensor cores only to find the row maxima, pass 2 recomputes each S tile, turns it into e = LUT(s - max) -- an fp16 value by
 // construction, so the fp16 A operand of the second product is EXACT -- and accumulates O += e V in tensor memory.
 //
-// What changed against the first tcgen05 version (attention_tc.cu, kept as the fallback for caches without a shadow): there all
+// What changed against round 1's tcgen05 kernel (removed; profiles/r1_attention_tc.md): there all
 // 256 threads of a CTA converted K and V from fp32 and transposed V with 2-byte stores IN BOTH PASSES, then ran the softmax, then
-// one thread issued the MMAs -- three serialised phases, tensor pipe 5 % busy (profiles/r1_attention_tc.md).  Here
+// one thread issued the MMAs -- three serialised phases, tensor pipe 5 % busy.  Here
 //   * K and V^T live in HBM as fp16 shadows written ONCE, by the kernel that appends a token to the fp32 cache
 //     (rope_kv_append_kernel / kv_shadow_refresh_kernel), in exactly the layouts the MMA operands want:
 //       k16  [n_ctx][n_head_kv][64]       a key row is 128 bytes = one SWIZZLE_128B row of the K-major B operand of Q K^T
@@ -339,9 +339,9 @@ void launch_kv_shadow_refresh(const float * k_cache, const float * v_cache, __ha
     B200_CUDA_CHECK(cudaGetLastError());
 }
 
-// false: not covered (no shadow, head_dim != 64, small batch) -> the caller falls back to attention_tc.cu / attention_prefill.cu
+// false: not covered (no shadow, head_dim != 64, small batch) -> the caller falls back to attention_prefill.cu
 bool launch_attention_ws(const float * qkv, float * out, int64_t out_stride, const AttnParams & p, cudaStream_t stream) {
-    if (!p.k16 || !p.vt16 || p.head_dim != D || p.n_past_dev != nullptr || getenv("B200_ATTN_V1") || getenv("B200_ATTN_SIMT")) return false;
+    if (!p.k16 || !p.vt16 || p.head_dim != D || p.n_past_dev != nullptr || getenv("B200_ATTN_SIMT")) return false;
     if (p.n_tok <= b200_mmv_max_n() && !getenv("B200_ATTN_TC")) return false;     // small batches keep fp32 attention (reassociation-level parity)
     if ((p.qkv_stride % 4) != 0 || (out_stride % 4) != 0) return false;
     WsArgs a;

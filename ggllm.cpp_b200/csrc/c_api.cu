@@ -214,8 +214,7 @@ void b200_attention(float * qkv, float * kc, float * vc, float * out, int n_head
             p.k16 = sh; p.vt16 = sh + need;
             launch_kv_shadow_refresh(kc, vc, p.k16, p.vt16, n_head_kv, n_ctx, 0, n_past + n_tok, g_stream);
         }
-        if (launch_attention_ws(qkv, out, (int64_t) n_head * head_dim, p, g_stream)) {}
-        else if (!launch_attention_tc(qkv, kc, vc, out, (int64_t) n_head * head_dim, p, g_stream)) {
+        if (!launch_attention_ws(qkv, out, (int64_t) n_head * head_dim, p, g_stream)) {
             float * sc = (float *) scratch(attention_prefill_scratch_bytes(n_head, n_tok, n_past + n_tok));
             launch_attention_prefill(qkv, kc, vc, out, (int64_t) n_head * head_dim, p, sc, g_stream);
         }

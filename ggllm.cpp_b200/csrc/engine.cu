@@ -616,8 +616,7 @@ static void enqueue_eval(b200_falcon * f, int N, int n_past, float theta_scale, 
         else launch_rope_kv_append(f->qkv, f->k_cache + kvoff, f->v_cache + kvoff, ap, theta_scale, sa);        // :2229-2281
         if (N > 1 && !graph_mode) {
             // tensor-core kernel (no scratch); the CUDA-core fallback (N <= 8 or head_dim != 64) materialises the score matrix
-            if (launch_attention_ws(f->qkv, f->att, E, ap, sa)) {}
-            else if (!launch_attention_tc(f->qkv, f->k_cache + kvoff, f->v_cache + kvoff, f->att, E, ap, sa)) {
+            if (!launch_attention_ws(f->qkv, f->att, E, ap, sa)) {
                 if (!f->attn_scratch) B200_CUDA_CHECK(cudaMalloc(&f->attn_scratch, attention_prefill_scratch_bytes(f->H, f->hp.n_batch, f->hp.n_ctx)));
                 launch_attention_prefill(f->qkv, f->k_cache + kvoff, f->v_cache + kvoff, f->att, E, ap, f->attn_scratch, sa); f->launches++;
             }

@@ -91,8 +91,6 @@ bool   launch_attention_ws(const float * qkv, float * out, int64_t out_stride, c
 int    attention_ctx_pad(int n_ctx);
 size_t attention_shadow_halves(int n_head_kv, int n_ctx);           // halves per layer, for k16 and for vt16 each
 void   launch_kv_shadow_refresh(const float * k_cache, const float * v_cache, __half * k16, __half * vt16, int n_head_kv, int n_ctx, int pos, int n, cudaStream_t stream);
-bool   launch_attention_tc(const float * qkv, const float * k_cache, const float * v_cache, float * out, int64_t out_stride,
-                           const AttnParams & p, cudaStream_t stream);       // attention_tc.cu: N > 1 on tcgen05 (head_dim 64)
 size_t attention_prefill_scratch_bytes(int n_head, int n_tok, int T);
 void   launch_attention_prefill(const float * qkv, const float * k_cache, const float * v_cache, float * out, int64_t out_stride,
                                 const AttnParams & p, float * scratch, cudaStream_t stream);
