@@ -88,39 +88,136 @@ __device__ __forceinline__ Chunks dequant_generic(const WPlanes & W, size_t row,
     }
     return o;
 }
+// ---- per-type producers.  Prod<TYPE>::Raw = the bytes one thread needs for its 16 weights of a K block (loaded two blocks ahead),
+//      ptr / next / load walk the planes, deq turns them into the two fp16 chunks.  Every variant produces the SAME bits as
+//      "dequantize_row_* in fp32, then one rounding to fp16" (checked against dequant_elem by tests/test_kernels_gpu.py).
+template <int TYPE> struct Prod { static constexpr bool FAST = false; struct Raw {}; struct Ptr {}; };
+
 // Q4_K: w = (d*sc)*q - dmin*m with the fp32 roundings of dequantize_row_q4_K (k_quants.c:607-631), then one rounding to fp16.
 // d*sc and dmin*m are exact in fp32 (11-bit x 6-bit significands) and so is (d*sc)*q (17 x 4 bits), hence fma(d*sc, q, -dmin*m) rounds
 // exactly once where the CPU's fmul + fsub rounds exactly once: same bits, one instruction less per weight (the producers bound this kernel).
-struct RawQ4K { uint2 q; uint32_t sm, dd; };
-// K block kb (64 weights) of a row: quant bytes at 32 kb + 8 h, the (sc, sc, min, min) word at 4 kb, (d, dmin) at 4 (kb / 4): running pointers
-struct PtrQ4K { const uint8_t * q, * sm, * dd; };
-__device__ __forceinline__ PtrQ4K ptr_q4k(const WPlanes & W, size_t row, int kb, int h) {      // h = 0..3: bytes 8h .. 8h+7 of the 32
-    return { W.p[0] + row * W.stride[0] + (size_t) kb * 32 + h * 8, W.p[1] + row * W.stride[1] + (size_t) kb * 4, W.p[2] + row * W.stride[2] };
-}
-__device__ __forceinline__ RawQ4K load_q4k(const PtrQ4K & p, int kb) {
-    RawQ4K r;
-    r.q = ldg_stream_v2(p.q); r.sm = ldg_u32(p.sm); r.dd = ldg_u32(p.dd + (size_t) (kb >> 2) * 4);
-    return r;
-}
-__device__ __forceinline__ Chunks dequant_q4k(const RawQ4K & r) {
-    const float2 dm = __half22float2(*reinterpret_cast<const __half2 *>(&r.dd));
-    const float d0 = __fmul_rn(dm.x, (float) (r.sm & 0xff)), d1 = __fmul_rn(dm.x, (float) ((r.sm >> 8) & 0xff));
-    const float m0 = __fmul_rn(dm.y, (float) ((r.sm >> 16) & 0xff)), m1 = __fmul_rn(dm.y, (float) (r.sm >> 24));
-    const uint32_t w[2] = { r.q.x, r.q.y };
-    float lo[8], hi[8];
+template <> struct Prod<T_Q4_K> {
+    static constexpr bool FAST = true;
+    struct Raw { uint2 q; uint32_t sm, dd; };
+    // K block kb (64 weights) of a row: quant bytes at 32 kb + 8 h, the (sc, sc, min, min) word at 4 kb, (d, dmin) at 4 (kb / 4): running pointers
+    struct Ptr { const uint8_t * q, * sm, * dd; };
+    static __device__ __forceinline__ Ptr ptr(const WPlanes & W, size_t row, int kb, int h) {      // h = 0..3: bytes 8h .. 8h+7 of the 32
+        return { W.p[0] + row * W.stride[0] + (size_t) kb * 32 + h * 8, W.p[1] + row * W.stride[1] + (size_t) kb * 4, W.p[2] + row * W.stride[2] };
+    }
+    static __device__ __forceinline__ void next(Ptr & p) { p.q += 32; p.sm += 4; }
+    static __device__ __forceinline__ Raw load(const Ptr & p, int kb, int) {
+        Raw r;
+        r.q = ldg_stream_v2(p.q); r.sm = ldg_u32(p.sm); r.dd = ldg_u32(p.dd + (size_t) (kb >> 2) * 4);
+        return r;
+    }
+    static __device__ __forceinline__ Chunks deq(const Raw & r, int, int) {
+        const float2 dm = __half22float2(*reinterpret_cast<const __half2 *>(&r.dd));
+        const float d0 = __fmul_rn(dm.x, (float) (r.sm & 0xff)), d1 = __fmul_rn(dm.x, (float) ((r.sm >> 8) & 0xff));
+        const float m0 = __fmul_rn(dm.y, (float) ((r.sm >> 16) & 0xff)), m1 = __fmul_rn(dm.y, (float) (r.sm >> 24));
+        const uint32_t w[2] = { r.q.x, r.q.y };
+        float lo[8], hi[8];
 #pragma unroll
-    for (int i = 0; i < 2; i++)
+        for (int i = 0; i < 2; i++)
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const uint32_t byte = (w[i] >> (8 * j)) & 0xff;
-            lo[4 * i + j] = __fmaf_rn(d0, (float) (byte & 0xF), -m0);
-            hi[4 * i + j] = __fmaf_rn(d1, (float) (byte >> 4), -m1);
+            for (int j = 0; j < 4; j++) {
+                const uint32_t byte = (w[i] >> (8 * j)) & 0xff;
+                lo[4 * i + j] = __fmaf_rn(d0, (float) (byte & 0xF), -m0);
+                hi[4 * i + j] = __fmaf_rn(d1, (float) (byte >> 4), -m1);
+            }
+        Chunks o;
+        o.c[0] = make_uint4(pack_h2(lo[0], lo[1]), pack_h2(lo[2], lo[3]), pack_h2(lo[4], lo[5]), pack_h2(lo[6], lo[7]));
+        o.c[1] = make_uint4(pack_h2(hi[0], hi[1]), pack_h2(hi[2], hi[3]), pack_h2(hi[4], hi[5]), pack_h2(hi[6], hi[7]));
+        return o;
+    }
+};
+
+// The legacy and 3-bit types dequantise in HALF arithmetic without losing a bit: code (and code * scale) are small integers, exact in
+// fp16, and one fp16 multiply by the fp16 block scale d rounds the exact product once -- which is what "fp32 product (exact: <= 20
+// significant bits), then round to fp16" does.  Four codes of a 32-bit word come out of two LOP3s as the halves 1024 + code of bytes
+// (0, 2) and (1, 3) (the 0x6400 exponent trick); two PRMTs put them back in element order.
+__device__ __forceinline__ uint32_t h2_sub(uint32_t a, uint32_t b) { uint32_t r; asm("sub.rn.f16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+__device__ __forceinline__ uint32_t h2_mul(uint32_t a, uint32_t b) { uint32_t r; asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+__device__ __forceinline__ uint32_t h2_dup(uint32_t two_halves, bool high) { return __byte_perm(two_halves, 0, high ? 0x3232 : 0x1010); }
+// a = halves of elements (0, 2), b = halves of elements (1, 3)  ->  (0, 1) and (2, 3)
+__device__ __forceinline__ void h2_order(uint32_t a, uint32_t b, uint32_t & e01, uint32_t & e23) { e01 = __byte_perm(a, b, 0x5410); e23 = __byte_perm(a, b, 0x7632); }
+
+// Q4_0: w = (q - 8) * d (ggml.c:1509-1527); element j of a block sits in the low nibble of qs[j], j + 16 in the high nibble.  The K block
+// holds two blocks; thread h owns elements 8h .. 8h+7 of each: low (h < 2) or high nibbles of qs[8 (h & 1) .. +7].
+template <> struct Prod<T_Q4_0> {
+    static constexpr bool FAST = true;
+    struct Raw { uint2 qa, qb; uint32_t dd; };
+    struct Ptr { const uint8_t * q, * d; };
+    static __device__ __forceinline__ Ptr ptr(const WPlanes & W, size_t row, int kb, int h) {
+        return { W.p[0] + row * W.stride[0] + (size_t) kb * 32 + (h & 1) * 8, W.p[1] + row * W.stride[1] + (size_t) kb * 4 };
+    }
+    static __device__ __forceinline__ void next(Ptr & p) { p.q += 32; p.d += 4; }
+    static __device__ __forceinline__ Raw load(const Ptr & p, int, int) {
+        Raw r;
+        r.qa = ldg_stream_v2(p.q); r.qb = ldg_stream_v2(p.q + 16); r.dd = ldg_u32(p.d);
+        return r;
+    }
+    static __device__ __forceinline__ uint4 block(uint2 q, uint32_t d2, int sh) {
+        uint32_t o[4];
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+            const uint32_t w = (i ? q.y : q.x) >> sh;
+            const uint32_t a = h2_mul(h2_sub((w & 0x000F000Fu) | 0x64006400u, 0x64086408u), d2);          // (1024 + q) - 1032 = q - 8
+            const uint32_t b = h2_mul(h2_sub(((w >> 8) & 0x000F000Fu) | 0x64006400u, 0x64086408u), d2);
+            h2_order(a, b, o[2 * i], o[2 * i + 1]);
         }
-    Chunks o;
-    o.c[0] = make_uint4(pack_h2(lo[0], lo[1]), pack_h2(lo[2], lo[3]), pack_h2(lo[4], lo[5]), pack_h2(lo[6], lo[7]));
-    o.c[1] = make_uint4(pack_h2(hi[0], hi[1]), pack_h2(hi[2], hi[3]), pack_h2(hi[4], hi[5]), pack_h2(hi[6], hi[7]));
-    return o;
-}
+        return make_uint4(o[0], o[1], o[2], o[3]);
+    }
+    static __device__ __forceinline__ Chunks deq(const Raw & r, int, int h) {
+        const int sh = (h >> 1) * 4;
+        Chunks o;
+        o.c[0] = block(r.qa, h2_dup(r.dd, false), sh);
+        o.c[1] = block(r.qb, h2_dup(r.dd, true), sh);
+        return o;
+    }
+};
+
+// Q3_K: w = d * (sc - 32) * (q2 + 4 hbit - 4) (k_quants.c:472-521).  K block kb is quarter c = kb % 4 of super-block kb / 4: half n = c / 2,
+// 2-bit fields j0 = 2 (c % 2) and j0 + 1 of qs[32 n + l], high bits 4 n + j of hmask[l]; thread h owns l = 8h .. 8h+7 for both fields; their
+// two scales are bytes j0, j0 + 1 of one word of the expanded scale plane (formats.cuh: q3_scale16).
+template <> struct Prod<T_Q3_K> {
+    static constexpr bool FAST = true;
+    struct Raw { uint2 q, hm; uint32_t sc; uint16_t d; };
+    struct Ptr { const uint8_t * q, * hm, * sc, * d; };
+    static __device__ __forceinline__ Ptr ptr(const WPlanes & W, size_t row, int, int h) {
+        return { W.p[0] + row * W.stride[0] + h * 8, W.p[1] + row * W.stride[1] + h * 8, W.p[2] + row * W.stride[2] + (h >> 1) * 4, W.p[3] + row * W.stride[3] };
+    }
+    static __device__ __forceinline__ void next(Ptr &) {}
+    static __device__ __forceinline__ Raw load(const Ptr & p, int kb, int) {
+        const int b = kb >> 2, n = (kb >> 1) & 1;
+        Raw r;
+        r.q = ldg_stream_v2(p.q + (size_t) b * 64 + n * 32); r.hm = ldg_stream_v2(p.hm + (size_t) b * 32);
+        r.sc = ldg_u32(p.sc + (size_t) b * 16 + n * 8); r.d = __ldg(reinterpret_cast<const uint16_t *>(p.d) + b);
+        return r;
+    }
+    static __device__ __forceinline__ uint4 field(uint2 q, uint2 hm, int qsh, int hsh, uint32_t sc2, uint32_t d2) {
+        uint32_t o[4];
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+            const uint32_t w = (i ? q.y : q.x) >> qsh, m = (i ? hm.y : hm.x) >> hsh;
+            // q2 | hbit << 2 = q2 + 4 hbit in 0..7; minus 4 = the signed code; times the scale: |.| <= 128, exact in fp16
+            const uint32_t va = (w & 0x00030003u) | ((m & 0x00010001u) << 2) | 0x64006400u;
+            const uint32_t vb = ((w >> 8) & 0x00030003u) | (((m >> 8) & 0x00010001u) << 2) | 0x64006400u;
+            const uint32_t a = h2_mul(h2_mul(h2_sub(va, 0x64046404u), sc2), d2), b = h2_mul(h2_mul(h2_sub(vb, 0x64046404u), sc2), d2);
+            h2_order(a, b, o[2 * i], o[2 * i + 1]);
+        }
+        return make_uint4(o[0], o[1], o[2], o[3]);
+    }
+    static __device__ __forceinline__ Chunks deq(const Raw & r, int kb, int) {
+        const int n = (kb >> 1) & 1, j0 = 2 * (kb & 1);
+        const uint32_t d2 = (uint32_t) r.d | ((uint32_t) r.d << 16);
+        const int s0 = (int) (int8_t) (r.sc >> (8 * j0)), s1 = (int) (int8_t) (r.sc >> (8 * j0 + 8));
+        const __half2 h0 = __float2half2_rn((float) s0), h1 = __float2half2_rn((float) s1);
+        Chunks o;
+        o.c[0] = field(r.q, r.hm, 2 * j0, 4 * n + j0, *reinterpret_cast<const uint32_t *>(&h0), d2);
+        o.c[1] = field(r.q, r.hm, 2 * j0 + 2, 4 * n + j0 + 1, *reinterpret_cast<const uint32_t *>(&h1), d2);
+        return o;
+    }
+};
 
 struct GemmArgs {
     WPlanes W;
@@ -200,19 +297,24 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
         // ===== dequant producers (2 threads per weight row) =====
         const int t = threadIdx.x - 64, r = t >> 2, h = t & 3;
         const size_t row = (size_t) min(m0 + r, a.W.M - 1);                // rows past M are computed from row M-1 and never stored
-        RawQ4K raw, raw1;                                                  // the bytes of K blocks kb and kb + 1: two loads in flight per thread
-        PtrQ4K pq = ptr_q4k(a.W, row, kb0 + (KB > 1 ? 1 : 0), h);
-        if (TYPE == T_Q4_K) { const PtrQ4K p0 = ptr_q4k(a.W, row, kb0, h); raw = load_q4k(p0, kb0); raw1 = load_q4k(pq, kb0 + (KB > 1 ? 1 : 0)); }
+        using P = Prod<TYPE>;
+        typename P::Raw raw, raw1;                                         // the bytes of K blocks kb and kb + 1: two loads in flight per thread
+        typename P::Ptr pq;
+        if constexpr (P::FAST) {
+            const typename P::Ptr p0 = P::ptr(a.W, row, kb0, h);
+            pq = P::ptr(a.W, row, kb0 + (KB > 1 ? 1 : 0), h);
+            raw = P::load(p0, kb0, h); raw1 = P::load(pq, kb0 + (KB > 1 ? 1 : 0), h);
+        }
         const int sw = r & 7;
         const uint32_t st0 = smem_u32(sA) + (uint32_t) (r * 128 + ((h ^ sw) << 4)), st1 = smem_u32(sA) + (uint32_t) (r * 128 + (((4 + h) ^ sw) << 4));
         for (int kb = 0; kb < KB; kb++) {
             const int s = kb % SA;
             Chunks ch;
-            if (TYPE == T_Q4_K) {
-                ch = dequant_q4k(raw);
+            if constexpr (P::FAST) {
+                ch = P::deq(raw, kb0 + kb, h);
                 raw = raw1;
-                pq.q += 32; pq.sm += 4;                                     // -> K block kb0 + kb + 2
-                if (kb + 2 < KB) raw1 = load_q4k(pq, kb0 + kb + 2);         // two blocks ahead: an L2 / HBM round trip is longer than one block's MMA time
+                P::next(pq);                                                // -> K block kb0 + kb + 2
+                if (kb + 2 < KB) raw1 = P::load(pq, kb0 + kb + 2, h);       // two blocks ahead: an L2 / HBM round trip is longer than one block's MMA time
             } else ch = dequant_generic(a.W, row, (kb0 + kb) * BK, h);
             if (kb >= SA) mbar_wait(a_empty + s, (uint32_t) ((kb / SA - 1) & 1));
             asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" :: "r"(st0 + (uint32_t) s * A_STAGE), "r"(ch.c[0].x), "r"(ch.c[0].y), "r"(ch.c[0].z), "r"(ch.c[0].w) : "memory");   // elements 8h .. 8h+7
@@ -354,20 +456,25 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_pair_kernel(const __grid_c
         // ===== dequant producers (4 threads per weight row), then the epilogue: exactly the single-CTA kernel's, except for the arrival =====
         const int t = threadIdx.x - 64, r = t >> 2, h = t & 3;
         const size_t row = (size_t) min(m0 + r, a.W.M - 1);
-        RawQ4K raw, raw1;
-        PtrQ4K pq = ptr_q4k(a.W, row, kb0 + (KB > 1 ? 1 : 0), h);
-        if (TYPE == T_Q4_K) { const PtrQ4K p0 = ptr_q4k(a.W, row, kb0, h); raw = load_q4k(p0, kb0); raw1 = load_q4k(pq, kb0 + (KB > 1 ? 1 : 0)); }
+        using P = Prod<TYPE>;
+        typename P::Raw raw, raw1;
+        typename P::Ptr pq;
+        if constexpr (P::FAST) {
+            const typename P::Ptr p0 = P::ptr(a.W, row, kb0, h);
+            pq = P::ptr(a.W, row, kb0 + (KB > 1 ? 1 : 0), h);
+            raw = P::load(p0, kb0, h); raw1 = P::load(pq, kb0 + (KB > 1 ? 1 : 0), h);
+        }
         const int sw = r & 7;
         const uint32_t st0 = smem_u32(sA) + (uint32_t) (r * 128 + ((h ^ sw) << 4)), st1 = smem_u32(sA) + (uint32_t) (r * 128 + (((4 + h) ^ sw) << 4));
         const uint32_t full0 = map_to_rank(smem_u32(a_full), 0);          // the leader's a_full[0] as a shared::cluster address
         for (int kb = 0; kb < KB; kb++) {
             const int s = kb % SA;
             Chunks ch;
-            if (TYPE == T_Q4_K) {
-                ch = dequant_q4k(raw);
+            if constexpr (P::FAST) {
+                ch = P::deq(raw, kb0 + kb, h);
                 raw = raw1;
-                pq.q += 32; pq.sm += 4;
-                if (kb + 2 < KB) raw1 = load_q4k(pq, kb0 + kb + 2);
+                P::next(pq);
+                if (kb + 2 < KB) raw1 = P::load(pq, kb0 + kb + 2, h);
             } else ch = dequant_generic(a.W, row, (kb0 + kb) * BK, h);
             if (kb >= SA) mbar_wait(a_empty + s, (uint32_t) ((kb / SA - 1) & 1));
             asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" :: "r"(st0 + (uint32_t) s * A_STAGE), "r"(ch.c[0].x), "r"(ch.c[0].y), "r"(ch.c[0].z), "r"(ch.c[0].w) : "memory");
@@ -464,6 +571,8 @@ bool launch_gemm_tc(const WPlanes & W, const __half * X, int64_t x_stride, int N
     if (pair) {
         switch (W.type) {
             case T_Q4_K: launch_typed_pair<T_Q4_K>(map, a, stream); break;
+            case T_Q4_0: launch_typed_pair<T_Q4_0>(map, a, stream); break;
+            case T_Q3_K: launch_typed_pair<T_Q3_K>(map, a, stream); break;
             default:     launch_typed_pair<-1>(map, a, stream); break;
         }
         return true;
@@ -472,6 +581,8 @@ bool launch_gemm_tc(const WPlanes & W, const __half * X, int64_t x_stride, int N
     const size_t smem = 1024 + (size_t) SA * A_STAGE + SB * b_stage + 256;
     switch (W.type) {
         case T_Q4_K: launch_typed<T_Q4_K>(map, a, smem, stream); break;
+        case T_Q4_0: launch_typed<T_Q4_0>(map, a, smem, stream); break;
+        case T_Q3_K: launch_typed<T_Q3_K>(map, a, smem, stream); break;
         default:     launch_typed<-1>(map, a, smem, stream); break;        // generic element-wise dequantiser
     }
     return true;

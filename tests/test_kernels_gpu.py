@@ -240,7 +240,8 @@ def test_attention(gpu, orc, n_head, n_head_kv, n_tok, n_past):
 
 @pytest.mark.parametrize("t,M,K,N,gelu", [(po.Q4_K, 256, 512, 40, 0), (po.Q4_K, 1000, 1024, 300, 0), (po.Q4_K, 384, 2048, 512, 1),
                                           (po.Q4_0, 200, 256, 17, 0), (po.Q6_K, 128, 512, 64, 0), (po.Q4_K, 128, 8192, 9, 0), (po.Q4_K, 640, 1024, 512, 0),
-                                          (po.Q6_K, 300, 512, 260, 0), (po.Q4_K, 520, 2048, 400, 1)])      # N > 256: the 256-row x 256-token tile shape
+                                          (po.Q6_K, 300, 512, 260, 0), (po.Q4_K, 520, 2048, 400, 1),       # N > 256: the CTA-pair kernel
+                                          (po.Q4_0, 300, 4544, 512, 0), (po.Q3_K, 520, 2048, 400, 0), (po.Q3_K, 130, 1024, 77, 1), (po.Q4_0, 71, 576, 130, 0)])
 def test_tensor_core_gemm_matches_cuda_core_gemm(gpu, orc, t, M, K, N, gelu):
     """tcgen05 kernel vs the CUDA-core kernel on identical fp16 operands: only the fp32 accumulation order differs.
     Then both against the exact fp64 product of the fp16-rounded operands."""
@@ -261,6 +262,25 @@ def test_tensor_core_gemm_matches_cuda_core_gemm(gpu, orc, t, M, K, N, gelu):
         budget = np.maximum(budget, np.abs(exact) * 2.0 ** -9 + 1e-6)        # fp16 rounding of the GELU input and of its output
     assert np.all(np.abs(b - exact) <= budget), float(np.abs(b - exact).max())
     assert np.all(np.abs(a - exact) <= budget), float(np.abs(a - exact).max())
+
+
+@pytest.mark.parametrize("t", [po.Q4_K, po.Q4_0, po.Q3_K, po.Q6_K, po.Q5_0])
+@pytest.mark.parametrize("N", [512, 200])
+def test_tensor_core_gemm_operand_is_the_exact_fp16_weight(gpu, orc, t, N):
+    """One-hot activation rows read the dequantised A operand back through the tensor cores: Y[n][m] = fp16(w[m][k_n]) exactly.
+    Pins the per-type dequantisation producers of gemm_tc.cu (Q4_K fp32 fma; Q4_0 / Q3_K half arithmetic; generic for the rest),
+    in the single-CTA kernel (N = 200) and the CTA-pair kernel (N = 512), to dequantize_row_* + one fp16 rounding."""
+    M, K = 300, 1024
+    wq = _weights(orc, t, M, K, seed=11)
+    W = gpu.Weight(t, K, M, wq)
+    want = orc.dequantize(t, wq, K).astype(np.float16).astype(np.float32)          # [M][K]
+    for off in range(0, K, N):
+        cols = (off + np.arange(N)) % K
+        xh = np.zeros((N, K), np.float16); xh[np.arange(N), cols] = 1.0
+        xd, yd = gpu.DevBuf(src=xh), gpu.DevBuf(N * M * 4)
+        assert gpu.lib().b200_mul_mat_f16(W.h, xd.ptr, K, N, yd.ptr, M, 0, 0) == 1
+        got = yd.download(np.float32, (N, M))
+        assert np.array_equal(got, want[:, cols].T), (t, N, off)
 
 
 @pytest.mark.parametrize("t,K,M", [(po.Q4_K, 8192, 700), (po.Q4_K, 14848, 300), (po.Q4_0, 4544, 333), (po.Q4_K, 256, 64)])
