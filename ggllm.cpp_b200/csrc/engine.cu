@@ -86,7 +86,12 @@ struct b200_falcon {
     bool ring_mode = false;                     // set while the generation-step graph is being captured
     int32_t * tok_next = nullptr, * gen_hist = nullptr; int * gen_step = nullptr;   // sampled id, ids so far, step counter (device)
     SamplerState * sampler = nullptr; SamplerParams sampler_p{}; bool use_sampler = false; float * sampler_work = nullptr;   // generation with the sampling chain (sampling.cu)
-    int act_type = -1;
+    int act_type = -1;                // the ONE activation format every layer matrix takes (fast paths), -1: see generic_layers
+    // Files the reference evaluates but the fused paths do not cover: F16 / F32 matrices (an unquantised model, or lm_head kept in F16
+    // by --leave-output-tensor, libfalcon.cpp:3609) and legacy + K-quant types mixed in one model.  They run through enqueue_eval_generic:
+    // one fp32 LayerNorm per norm, activations quantised per matrix for ITS type (what ggml's MUL_MAT INIT pass does, ggml.c:11462-11476).
+    bool classified = false, generic_layers = false, generic_head = false;
+    float * gen_na = nullptr, * gen_nm = nullptr; void * gen_actq = nullptr; __half * gen_xh = nullptr;
     unsigned * q_ctr = nullptr;                 // chunk counters of the quantise-on-completion epilogue (ffn_up -> ffn_down)
     ncclComm_t comm = nullptr;
     int launches = 0; float last_ms = 0.f;
@@ -161,13 +166,25 @@ static void invalidate_graphs(b200_falcon * f) {
     }
 }
 
-static void note_act_type(b200_falcon * f, int wtype) {
-    const int at = act_type_for(wtype);
-    if (at < 0) return;                           // f16 / f32 weights: no quantised activations
-    if (f->act_type < 0) f->act_type = at;
-    // one activation format per model keeps the fused LayerNorm->quantise producers simple; the reference's
-    // quantiser writes every 2-D weight with one type (libfalcon.cpp:3606-3624), so this always holds for its files
-    B200_ASSERT(f->act_type == at && "mixed legacy/K-quant weight types in one model are not supported");
+static void note_act_type(b200_falcon * f, int) { f->classified = false; }
+
+// Which path the model's matrices allow (re-derived after every tensor change).  The reference's quantiser writes every 2-D weight with
+// one type (libfalcon.cpp:3606-3624), so its files take the fast paths; anything else still evaluates, through the generic path.
+static void classify(b200_falcon * f) {
+    int at = -2; bool uniform = true;
+    for (const auto & L : f->layers)
+        for (const WPlanes * W : { &L.wqkv, &L.wo, &L.up, &L.down }) {
+            if (!W->p[0]) continue;
+            const int a = act_type_for(W->type);
+            if (at == -2) at = a; else if (a != at) uniform = false;
+        }
+    const int nat = (uniform && at >= 0) ? at : -1;
+    if (nat != f->act_type && f->actq_mem) { B200_CUDA_CHECK(cudaDeviceSynchronize()); B200_CUDA_CHECK(cudaFree(f->actq_mem)); f->actq_mem = nullptr; }
+    f->act_type = nat;
+    f->generic_layers = f->NL > 0 && nat < 0;
+    f->generic_head = f->last && f->lm_head.p[0] && (f->generic_layers || (f->NL > 0 && act_type_for(f->lm_head.type) != nat));
+    if (f->NL == 0 && f->last && f->lm_head.p[0]) { f->act_type = act_type_for(f->lm_head.type); f->generic_head = f->act_type < 0; }
+    f->classified = true;
 }
 
 extern "C" {
@@ -217,8 +234,18 @@ static void ensure_actq(b200_falcon * f) {
         if (sb) { B200_CUDA_CHECK(cudaMalloc(&f->attn_dec_scratch, sb)); B200_CUDA_CHECK(cudaMemset(f->attn_dec_scratch, 0, sb)); }
     }
     if (!f->q_ctr) { B200_CUDA_CHECK(cudaMalloc(&f->q_ctr, (size_t) (f->FF / 256 + 1) * sizeof(unsigned))); B200_CUDA_CHECK(cudaMemset(f->q_ctr, 0, (size_t) (f->FF / 256 + 1) * sizeof(unsigned))); }
+    if (!f->classified) classify(f);
+    const int NB = f->hp.n_batch > 0 ? f->hp.n_batch : 1;
+    if ((f->generic_layers || f->generic_head) && !f->gen_na) {
+        B200_CUDA_CHECK(cudaMalloc(&f->gen_na, (size_t) NB * f->E * 4)); B200_CUDA_CHECK(cudaMalloc(&f->gen_nm, (size_t) NB * f->E * 4));
+        size_t ab = 0;
+        for (int t : { T_Q8_0, T_Q8_1, T_Q8_K }) { const size_t b = actq_bytes(t, f->FF, NB); if (b > ab) ab = b; }
+        B200_CUDA_CHECK(cudaMalloc(&f->gen_actq, ab));
+        B200_CUDA_CHECK(cudaMalloc(&f->gen_xh, (size_t) NB * f->FF * 2));
+        if (!f->gemm_ws_a) { f->gemm_ws_bytes = 256; B200_CUDA_CHECK(cudaMalloc(&f->gemm_ws_a, 256)); B200_CUDA_CHECK(cudaMalloc(&f->gemm_ws_b, 256)); }
+    }
     if (f->actq_mem || f->act_type < 0) return;
-    const int at = f->act_type; const int NB = f->hp.n_batch > 0 ? f->hp.n_batch : 1;
+    const int at = f->act_type;
     const size_t bE = actq_bytes(at, f->E, NB), bF = actq_bytes(at, f->FF, NB);
     B200_CUDA_CHECK(cudaMalloc(&f->actq_mem, 4 * bE + bF));
     uint8_t * p = (uint8_t *) f->actq_mem;
@@ -226,11 +253,13 @@ static void ensure_actq(b200_falcon * f) {
     actq_bind(f->xatt, at, f->E, NB, p); p += bE; actq_bind(f->xf, at, f->E, NB, p); p += bE;
     actq_bind(f->xup, at, f->FF, NB, p);
     if (NB > b200_mmv_max_n()) {
-        B200_CUDA_CHECK(cudaMalloc(&f->xh_a, (size_t) NB * f->E * 2)); B200_CUDA_CHECK(cudaMalloc(&f->xh_b, (size_t) NB * f->FF * 2));
-        B200_CUDA_CHECK(cudaMalloc(&f->xh_m, (size_t) NB * f->E * 2));
-        WPlanes big{}; big.type = T_Q4_K; big.K = f->FF; big.M = f->FF > f->V ? f->FF : f->V;
-        f->gemm_ws_bytes = mmq_gemm_workspace_bytes(big, NB);
-        B200_CUDA_CHECK(cudaMalloc(&f->gemm_ws_a, f->gemm_ws_bytes)); B200_CUDA_CHECK(cudaMalloc(&f->gemm_ws_b, f->gemm_ws_bytes));
+        if (!f->xh_a) { B200_CUDA_CHECK(cudaMalloc(&f->xh_a, (size_t) NB * f->E * 2)); B200_CUDA_CHECK(cudaMalloc(&f->xh_b, (size_t) NB * f->FF * 2));
+            B200_CUDA_CHECK(cudaMalloc(&f->xh_m, (size_t) NB * f->E * 2)); }
+        if (!f->gemm_ws_a) {
+            WPlanes big{}; big.type = T_Q4_K; big.K = f->FF; big.M = f->FF > f->V ? f->FF : f->V;
+            f->gemm_ws_bytes = mmq_gemm_workspace_bytes(big, NB);
+            B200_CUDA_CHECK(cudaMalloc(&f->gemm_ws_a, f->gemm_ws_bytes)); B200_CUDA_CHECK(cudaMalloc(&f->gemm_ws_b, f->gemm_ws_bytes));
+        }
     }
 }
 
@@ -459,7 +488,7 @@ void b200_falcon_free(b200_falcon * f) {
     free_matrix(f, f->tok_emb); free_matrix(f, f->lm_head);
     cudaFree(f->lnf_g); cudaFree(f->lnf_b); cudaFree(f->k_cache); cudaFree(f->v_cache); cudaFree(f->k16); cudaFree(f->vt16);
     cudaFree(f->inp); cudaFree(f->qkv); cudaFree(f->att); cudaFree(f->ao); cudaFree(f->up); cudaFree(f->dn); cudaFree(f->logits);
-    cudaFree(f->attn_scratch); cudaFree(f->actq_mem); cudaFree(f->xh_a); cudaFree(f->xh_b); cudaFree(f->xh_m); cudaFree(f->gemm_ws_a); cudaFree(f->gemm_ws_b);
+    cudaFree(f->attn_scratch); cudaFree(f->actq_mem); cudaFree(f->gen_na); cudaFree(f->gen_nm); cudaFree(f->gen_actq); cudaFree(f->gen_xh); cudaFree(f->xh_a); cudaFree(f->xh_b); cudaFree(f->xh_m); cudaFree(f->gemm_ws_a); cudaFree(f->gemm_ws_b);
     cudaFree(f->tokens_dev); cudaFree(f->n_past_dev); cudaFree(f->q_ctr); cudaFree(f->attn_dec_scratch);
     cudaFreeHost(f->tokens_h); cudaFreeHost(f->n_past_h); cudaFreeHost(f->logits_h);
     for (int i = 0; i < 3; i++) if (f->graph[i]) cudaGraphExecDestroy(f->graph[i]);
@@ -487,6 +516,40 @@ static void mm(b200_falcon * f, const WPlanes & W, const ActQ & A, int N, float 
         launch_mmq_gemm(W, xh, W.K, N, y, y_stride, epi == EPI_GELU, ws, f->gemm_ws_bytes, st);
         f->launches++;
     }
+}
+
+// Y = W x for ANY weight type, from fp32 activation rows (stride K): the activation format is made on the spot for this matrix --
+// Q8_0 / Q8_1 / Q8_K codes for a quantised one (the INIT pass of ggml's MUL_MAT, ggml.c:11462-11476), fp16-rounded rows for F16
+// weights (ggml_compute_forward_mul_mat_f16_f32, ggml.c:11232-11251), the rows themselves for F32.  Slow path: see b200_falcon::generic_layers.
+static void mm_any(b200_falcon * f, const WPlanes & W, const float * x, int N, float * y, int64_t y_stride, bool gelu, cudaStream_t st) {
+    const int at = act_type_for(W.type);
+    if (at >= 0) {
+        ActQ a; actq_bind(a, at, W.K, N, f->gen_actq);
+        if (N > b200_mmv_max_n()) a.h = f->gen_xh;
+        launch_quantize_act(x, W.K, a, st); f->launches++;
+        mm(f, W, a, N, y, y_stride, gelu ? EPI_GELU : EPI_NONE, nullptr, nullptr, f->gen_xh, f->gemm_ws_a, st);
+        return;
+    }
+    if (W.type == T_F16 && N > b200_mmv_max_n()) {
+        launch_f32_to_f16(x, f->gen_xh, (int64_t) N * W.K, st);
+        launch_mmq_gemm(W, f->gen_xh, W.K, N, y, y_stride, 0, f->gemm_ws_a, f->gemm_ws_bytes, st); f->launches += 2;
+    } else { launch_mmv_f(W, x, W.K, N, y, y_stride, st); f->launches++; }
+    if (gelu) { B200_ASSERT(y_stride == W.M); launch_gelu(y, y, (int64_t) N * W.M, st); f->launches++; }                // ggml.c:10298-10337
+}
+
+// final LayerNorm + lm_head over rows x[0 .. nr) of the (already summed) residual stream: libfalcon.cpp:2422-2440
+static void enqueue_head(b200_falcon * f, float * x, int nr, cudaStream_t sa) {
+    const int E = f->E;
+    if (f->generic_head) {
+        launch_layernorm(x, E, f->lnf_g, f->lnf_b, f->gen_na, E, E, nr, sa); f->launches++;
+        mm_any(f, f->lm_head, f->gen_na, nr, f->logits, f->V, false, sa);
+        return;
+    }
+    ActQ xfr = f->xf; xfr.N = nr;
+    if (nr > b200_mmv_max_n()) xfr.h = f->xh_a;
+    launch_layernorm_q(x, E, nullptr, nullptr, 0, f->lnf_g, f->lnf_b, &xfr, nullptr, nullptr, nullptr, E, nr, sa);
+    f->launches++;
+    mm(f, f->lm_head, xfr, nr, f->logits, f->V, EPI_NONE, nullptr, nullptr, f->xh_a, f->gemm_ws_a, sa);
 }
 
 // ---- decode (N == 1) with everything that is not a mat-vec folded into the mat-vec kernels' prologues / epilogues:
@@ -567,7 +630,11 @@ static void enqueue_decode_fused(b200_falcon * f, int n_past, float theta_scale,
         if (wo_first && !skip("down")) launch_mmv(L.down, xup, f->dn, E, none, sa);
         f->launches += 7;
     }
-    if (f->last) {
+    if (f->last && f->generic_head) {                                                // lm_head kept in F16 / F32 (--leave-output-tensor)
+        if (f->NL > 0) { launch_add3(f->dn, f->ao, f->inp, f->inp, E, sa); f->launches++; }
+        enqueue_head(f, f->inp, 1, sa);
+        ring_token_out(f);
+    } else if (f->last) {
         launch_layernorm_q(f->inp, E, f->NL > 0 ? f->dn : nullptr, f->NL > 0 ? f->ao : nullptr, E, f->lnf_g, f->lnf_b, &xf, nullptr, nullptr, nullptr, E, 1, sa);   // :2399-2400, 2422-2431
         launch_mmv(f->lm_head, xf, f->logits, f->V, none, sa); f->launches += 2;      // :2440
         ring_token_out(f);
@@ -577,17 +644,52 @@ static void enqueue_decode_fused(b200_falcon * f, int n_past, float theta_scale,
     }
 }
 
+// The eval for models the fused paths do not cover (see b200_falcon::generic_layers): one stream, one kernel per graph node of
+// libfalcon.cpp:2120-2440, activations kept in fp32 between the nodes exactly as ggml keeps them.
+static void enqueue_eval_generic(b200_falcon * f, int N, int n_past, float theta_scale, bool graph_mode, int logits_rows_from) {
+    cudaStream_t sa = f->s_main;
+    const int E = f->E, FF = f->FF;
+    const bool dual = f->hp.falcon_type == 40;
+    if (f->first) { ring_token_in(f); launch_dequant_rows(f->tok_emb, f->tokens_dev, N, f->inp, E, sa); f->launches++; }
+    else B200_NCCL_CHECK(nccl().Recv(f->inp, (size_t) N * E, ncclFloat, f->hp.rank - 1, f->comm, sa));
+    for (int l = 0; l < f->NL; l++) {
+        const Layer & L = f->layers[l];
+        if (l > 0) { launch_add3(f->dn, f->ao, f->inp, f->inp, (int64_t) N * E, sa); f->launches++; }                 // :2399-2400
+        launch_layernorm(f->inp, E, L.ln_mlp_g, L.ln_mlp_b, f->gen_nm, E, E, N, sa); f->launches++;                     // :2166-2185
+        if (dual) { launch_layernorm(f->inp, E, L.ln_attn_g, L.ln_attn_b, f->gen_na, E, E, N, sa); f->launches++; }
+        mm_any(f, L.wqkv, dual ? f->gen_na : f->gen_nm, N, f->qkv, f->QKV, false, sa);                                   // :2192
+        AttnParams ap = { f->H, f->HKV, f->D, N, n_past, graph_mode ? f->n_past_dev : nullptr, f->hp.n_ctx, (int64_t) f->QKV, nullptr };
+        const size_t kvoff = (size_t) l * f->hp.n_ctx * f->HKV * f->D;
+        if (f->k16) { ap.k16 = f->k16 + (size_t) l * f->shadow_layer; ap.vt16 = f->vt16 + (size_t) l * f->shadow_layer; }
+        launch_rope_kv_append(f->qkv, f->k_cache + kvoff, f->v_cache + kvoff, ap, theta_scale, sa); f->launches++;      // :2229-2281
+        if (N > 1 && !graph_mode) {
+            if (!launch_attention_ws(f->qkv, f->att, E, ap, sa)) {
+                if (!f->attn_scratch) B200_CUDA_CHECK(cudaMalloc(&f->attn_scratch, attention_prefill_scratch_bytes(f->H, f->hp.n_batch, f->hp.n_ctx)));
+                launch_attention_prefill(f->qkv, f->k_cache + kvoff, f->v_cache + kvoff, f->att, E, ap, f->attn_scratch, sa); f->launches++;
+            }
+        } else launch_attention(f->qkv, f->k_cache + kvoff, f->v_cache + kvoff, f->att, E, ap, N == 1 ? f->attn_dec_scratch : nullptr, sa);   // :2285-2366
+        f->launches++;
+        mm_any(f, L.wo, f->att, N, f->ao, E, false, sa);                                                                 // :2370
+        mm_any(f, L.up, f->gen_nm, N, f->up, FF, true, sa);                                                              // :2389-2392
+        mm_any(f, L.down, f->up, N, f->dn, E, false, sa);                                                                // :2394
+    }
+    if (f->NL > 0) { launch_add3(f->dn, f->ao, f->inp, f->inp, (int64_t) N * E, sa); f->launches++; }
+    if (f->last) { enqueue_head(f, f->inp + (size_t) logits_rows_from * E, N - logits_rows_from, sa); ring_token_out(f); }
+    else B200_NCCL_CHECK(nccl().Send(f->inp, (size_t) N * E, ncclFloat, f->hp.rank + 1, f->comm, sa));
+}
+
 // Enqueue one eval of N tokens on (s_main, s_mlp).  Device scalars carry n_past when `graph_mode`.
 static void enqueue_eval(b200_falcon * f, int N, int n_past, float theta_scale, bool graph_mode, int logits_rows_from) {
+    ensure_actq(f);
+    if (f->generic_layers) { enqueue_eval_generic(f, N, n_past, theta_scale, graph_mode, logits_rows_from); return; }
     if (N == 1 && fused_decode_ok(f)) { enqueue_decode_fused(f, n_past, theta_scale, graph_mode); return; }
     cudaStream_t sa = f->s_main, sb = f->s_mlp;
     const int E = f->E, FF = f->FF;
     const bool dual = f->hp.falcon_type == 40;
-    B200_ASSERT(f->act_type >= 0 && "f16/f32-weight models are not wired into the engine yet");
-    ensure_actq(f);
-    ActQ xa = f->xa, xm = f->xm, xatt = f->xatt, xup = f->xup, xf = f->xf;
-    xa.N = xm.N = xatt.N = xup.N = xf.N = N;
-    if (N > b200_mmv_max_n()) { xa.h = f->xh_a; xm.h = f->xh_m; xatt.h = f->xh_a; xup.h = f->xh_b; xf.h = f->xh_a; }     // GEMM path: fp16 operands come with the codes
+    B200_ASSERT(f->act_type >= 0);
+    ActQ xa = f->xa, xm = f->xm, xatt = f->xatt, xup = f->xup;
+    xa.N = xm.N = xatt.N = xup.N = N;
+    if (N > b200_mmv_max_n()) { xa.h = f->xh_a; xm.h = f->xh_m; xatt.h = f->xh_a; xup.h = f->xh_b; }     // GEMM path: fp16 operands come with the codes
 
     if (f->first) { ring_token_in(f); launch_dequant_rows(f->tok_emb, f->tokens_dev, N, f->inp, E, sa); f->launches++; }           // libfalcon.cpp:2120
     else B200_NCCL_CHECK(nccl().Recv(f->inp, (size_t) N * E, ncclFloat, f->hp.rank - 1, f->comm, sa));
@@ -629,11 +731,7 @@ static void enqueue_eval(b200_falcon * f, int N, int n_past, float theta_scale, 
     if (f->NL > 0) { launch_add3(f->dn, f->ao, f->inp, f->inp, (int64_t) N * E, sa); f->launches++; }           // :2399-2400 of the last local layer
 
     if (f->last) {
-        const int r0 = logits_rows_from, nr = N - r0;
-        ActQ xfr = xf; xfr.N = nr;
-        launch_layernorm_q(f->inp + (size_t) r0 * E, E, nullptr, nullptr, 0, f->lnf_g, f->lnf_b, &xfr, nullptr, nullptr, nullptr, E, nr, sa);   // :2422-2431
-        f->launches++;
-        mm(f, f->lm_head, xfr, nr, f->logits, f->V, EPI_NONE, nullptr, nullptr, f->xh_a, f->gemm_ws_a, sa);     // :2440
+        enqueue_head(f, f->inp + (size_t) logits_rows_from * E, N - logits_rows_from, sa);                        // :2422-2440
         ring_token_out(f);
     } else B200_NCCL_CHECK(nccl().Send(f->inp, (size_t) N * E, ncclFloat, f->hp.rank + 1, f->comm, sa));
 }

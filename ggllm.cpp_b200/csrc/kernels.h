@@ -50,6 +50,7 @@ void   launch_layernorm_q(float * x, int64_t x_stride, const float * ra, const f
                           const float * g1, const float * b1, const ActQ * A1,
                           const float * g2, const float * b2, const ActQ * A2, int n, int rows, cudaStream_t stream);
 void   launch_gelu(const float * x, float * y, int64_t n, cudaStream_t stream);
+void   launch_f32_to_f16(const float * x, __half * y, int64_t n, cudaStream_t stream);     // the fp16 activation rows of an F16-weight mat-mul
 void   launch_add(const float * a, const float * b, float * y, int64_t n, cudaStream_t stream);
 void   launch_add3(const float * a, const float * b, const float * c, float * y, int64_t n, cudaStream_t stream);   // (a+b)+c
 void   launch_mul_bcast(const float * a, const float * b, float * y, int64_t n, int64_t nb, cudaStream_t stream);  // y[i] = a[i]*b[i%nb]

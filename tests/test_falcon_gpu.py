@@ -65,6 +65,37 @@ def test_prompt_and_decode_match_oracle(gpu, hp, wt, seed):
     assert launches > 0
 
 
+@pytest.mark.parametrize("hp,wt,overrides,what", [
+    (TINY_40B, po.Q4_K, {"lm_head": po.F16}, "quantised layers, lm_head left in F16 (--leave-output-tensor)"),
+    (TINY_7B, po.Q4_0, {"lm_head": po.F32, "word_embeddings": po.F16}, "F32 lm_head, F16 embeddings"),
+    (TINY_40B, po.F16, {}, "unquantised F16 model"),
+    (TINY_7B, po.F32, {}, "unquantised F32 model"),
+    (TINY_40B, po.Q4_K, {"dense_4h_to_h": po.Q6_K, "query_key_value": po.Q5_0, "lm_head": po.Q8_0}, "K-quants and legacy types mixed"),
+    (TINY_7B, po.Q4_0, {"h.1.": po.F16}, "one whole layer in F16"),
+])
+def test_float_and_mixed_weight_models(gpu, hp, wt, overrides, what):
+    """Files the reference evaluates although its quantiser never writes them in one go: float matrices and mixed quantisation types
+    (ggml picks the activation format per MUL_MAT, ggml.c:11462-11476).  They run through the engine's generic path (only lm_head
+    differing keeps the fused layers).  Same tolerance contract as every eval; prompt (mat-vec batches of 8), then decode steps
+    through the CUDA graph."""
+    tensors = synth_model(hp, wt, seed=1234, overrides=overrides)
+    outs, launches = run_model(gpu, hp, tensors, n_ctx=64, n_batch=8, prompt=[11, 100, 101, 102, 103, 104, 105, 106, 107, 108, 109], n_decode=4)
+    assert_mostly_tight([assert_logits_close(got, want, "%s step %d" % (what, i)) for i, (got, want) in enumerate(outs)], what)
+    assert launches > 0
+
+
+@pytest.mark.parametrize("hp,wt,overrides", [(TINY_40B, po.F16, {}), (TINY_40B, po.Q4_K, {"lm_head": po.F16, "dense_h_to_4h": po.Q4_0})])
+def test_float_and_mixed_weight_models_prompt_gemm(gpu, hp, wt, overrides):
+    """the same through the tensor-core GEMM (n_batch 32 > the mat-vec limit): F16 weights meet fp16-rounded activations there exactly as
+    ggml_compute_forward_mul_mat_f16_f32 prescribes; tolerance of test_prompt_batch_uses_gemm_path"""
+    tensors = synth_model(hp, wt, seed=77, overrides=overrides)
+    outs, _ = run_model(gpu, hp, tensors, n_ctx=128, n_batch=32, prompt=list(range(12, 12 + 40)), n_decode=2)
+    for i, (got, want) in enumerate(outs):
+        scale = float(np.abs(want).max())
+        d = np.abs(got - want)
+        assert d.max() <= 3e-2 * scale and np.median(d) <= 5e-3 * scale, (i, float(d.max()), float(np.median(d)), scale)
+
+
 def test_prompt_batch_uses_gemm_path(gpu):
     """n_tokens > b200_mmv_max_n(): activations (already Q8-quantised, bit-exact with the CPU) -> fp16 (d*q), weights
     dequantised bit-exactly then rounded once to fp16, tensor-core GEMM with fp32 accumulation.
