@@ -148,13 +148,15 @@ __global__ void __launch_bounds__(AD_THREADS, 6) attn_dec_scores_kernel(const At
     const int n_past = a.n_past_dev ? *a.n_past_dev : a.n_past, T = n_past + 1;
     int k_lo, k_hi; split_range(T, split, k_lo, k_hi);
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the values kernel may take its place on the SMs now (it waits for this grid to finish)
-    if (k_lo >= k_hi) { trace_end(a.trace); return; }            // a split without keys (short context): nothing to score, nobody reads its pmax
-    const float scale = 1.0f / sqrtf(64.0f);
-    const size_t kv_row = (size_t) a.n_head_kv * 64;
+    // the query rows do not depend on n_past: their loads are in flight while the device scalar arrives (every dependent round trip
+    // counts here: beside ffn_up's streaming each one takes > 1 us, and at short contexts this kernel is nothing but such a chain)
     float2 q[AD_G];
 #pragma unroll
     for (int h = 0; h < AD_G; h++)
         q[h] = h < G ? *reinterpret_cast<const float2 *>(a.qkv + (size_t) (h0 + h) * 64 + 2 * lane) : make_float2(0.f, 0.f);
+    if (k_lo >= k_hi) { trace_end(a.trace); return; }            // a split without keys (short context): nothing to score, nobody reads its pmax
+    const float scale = 1.0f / sqrtf(64.0f);
+    const size_t kv_row = (size_t) a.n_head_kv * 64;
     // Fused RoPE + KV append (libfalcon.cpp:2229-2281).  A lane holds elements (2l, 2l+1) of a head; NeoX pairs element i < 32 with i + 32,
     // i.e. with the same component of lane l ^ 16.  Angles as rope_pair (ops.cu): theta = n_past * theta_scale^i by repeated fp32 products.
     float2 knew = make_float2(0.f, 0.f);
@@ -222,6 +224,20 @@ __global__ void __launch_bounds__(AD_THREADS, 6) attn_dec_scores_kernel(const At
     trace_end(a.trace);
 }
 
+// thread tid's 8 consecutive outputs (head hA of the CTA's group) -> the attention output row, plus wo's activation quantisation
+__device__ __forceinline__ void attn_dec_store(const AttnDecArgs & a, const float (&y)[8], int h0, int hA, int G, int tid, int lane) {
+    if (hA < G) {
+        float4 * dst = reinterpret_cast<float4 *>(a.out + (size_t) h0 * 64) + 2 * tid;
+        dst[0] = make_float4(y[0], y[1], y[2], y[3]); dst[1] = make_float4(y[4], y[5], y[6], y[7]);
+    }
+    if (a.has_q) {                                                      // here instead of in a kernel of its own
+        const int k0 = h0 * 64 + 8 * tid;                               // a warp = 256 consecutive outputs = 4 heads
+        if (a.qA.type == T_Q8_K) quantize_chunk8<T_Q8_K>(y, lane, a.qA, 0, k0, hA < G);
+        else if (a.qA.type == T_Q8_1) quantize_chunk8<T_Q8_1>(y, lane, a.qA, 0, k0, hA < G);
+        else quantize_chunk8<T_Q8_0>(y, lane, a.qA, 0, k0, hA < G);
+    }
+}
+
 __global__ void __launch_bounds__(AD_THREADS, 6) attn_dec_values_kernel(const AttnDecArgs a, const int per_max) {
     extern __shared__ __align__(16) float sm_dyn[];                // es[per_max][AD_G]
     __shared__ float gmax[AD_G];
@@ -238,8 +254,23 @@ __global__ void __launch_bounds__(AD_THREADS, 6) attn_dec_values_kernel(const At
     const size_t kv_row = (size_t) a.n_head_kv * 64;
     trace_begin(a.trace);
     const int n_used = splits_used(T);                            // splits 0 .. n_used - 1 hold keys
+    // V rows of EARLIER positions have been in the cache since their own decode steps: the first batch is fetched while the scores kernel
+    // still runs (this position's row is appended by that kernel: loaded after the wait)
+    const float * vp = a.vc + (size_t) kvh * 64 + 2 * lane;
+    float2 cur[AD_B], nxt[AD_B];
+#pragma unroll
+    for (int b = 0; b < AD_B; b++) { const int jj = warp + b * AD_WARPS; cur[b] = jj < nk && k_lo + jj < n_past ? __ldg(reinterpret_cast<const float2 *>(vp + (size_t) (k_lo + jj) * kv_row)) : make_float2(0.f, 0.f); }
     asm volatile("griddepcontrol.wait;" ::: "memory");            // launched programmatically behind the scores kernel: its S / pmax / KV append are complete from here on
     if (nk > 0) {
+    // the scores of the CTA's first AD_SPRE keys per thread are requested together with the split maxima (one round trip instead of two)
+    constexpr int AD_SPRE = 8;
+    const int eh = tid % AD_G, ej = tid / AD_G;
+    const float * Sr = a.S + (size_t) (h0 + min(eh, G - 1)) * a.n_ctx + k_lo;
+    float spre[AD_SPRE];
+#pragma unroll
+    for (int i = 0; i < AD_SPRE; i++) { const int j = ej + i * (AD_THREADS / AD_G); spre[i] = j < nk ? __ldcg(Sr + j) : 0.f; }
+#pragma unroll
+    for (int b = 0; b < AD_B; b++) { const int jj = warp + b * AD_WARPS; if (jj < nk && k_lo + jj >= n_past) cur[b] = *reinterpret_cast<const float2 *>(vp + (size_t) (k_lo + jj) * kv_row); }
     if (tid < AD_G) {
         float mx = -INFINITY;
         if (tid < G) for (int s = 0; s < n_used; s++) mx = fmaxf(mx, a.pmax[(size_t) (h0 + tid) * AD_SPLITS + s]);
@@ -248,19 +279,23 @@ __global__ void __launch_bounds__(AD_THREADS, 6) attn_dec_values_kernel(const At
     __syncthreads();
     // e = table_exp_f16[f16(s - max)] (ggml.c:12427-12440) for the CTA's keys, sums in double
     {
-        const int h = tid % AD_G;
         double s = 0.0;
-        if (h < G) {
-            const float * Sr = a.S + (size_t) (h0 + h) * a.n_ctx + k_lo;
-            for (int j = tid / AD_G; j < nk; j += AD_THREADS / AD_G) {
-                const float e = exp_f16lut(__fsub_rn(__ldcg(Sr + j), gmax[h]));
-                es[j * AD_G + h] = e; s += (double) e;
+        if (eh < G) {
+            const float gm = gmax[eh];
+#pragma unroll
+            for (int i = 0; i < AD_SPRE; i++) {
+                const int j = ej + i * (AD_THREADS / AD_G);
+                if (j < nk) { const float e = exp_f16lut(__fsub_rn(spre[i], gm)); es[j * AD_G + eh] = e; s += (double) e; }
             }
-        } else for (int j = tid / AD_G; j < nk; j += AD_THREADS / AD_G) es[j * AD_G + h] = 0.f;
-        dsum[tid / AD_G][h] = s;
+            for (int j = ej + AD_SPRE * (AD_THREADS / AD_G); j < nk; j += AD_THREADS / AD_G) {
+                const float e = exp_f16lut(__fsub_rn(__ldcg(Sr + j), gm));
+                es[j * AD_G + eh] = e; s += (double) e;
+            }
+        } else for (int j = ej; j < nk; j += AD_THREADS / AD_G) es[j * AD_G + eh] = 0.f;
+        dsum[ej][eh] = s;
     }
     __syncthreads();
-    if (tid < G) {
+    if (tid < G && n_used > 1) {
         double s = 0.0;
 #pragma unroll
         for (int r = 0; r < AD_THREADS / AD_G; r++) s += dsum[r][tid];
@@ -270,10 +305,6 @@ __global__ void __launch_bounds__(AD_THREADS, 6) attn_dec_values_kernel(const At
     float2 acc[AD_G];
 #pragma unroll
     for (int h = 0; h < AD_G; h++) acc[h] = make_float2(0.f, 0.f);
-    const float * vp = a.vc + (size_t) kvh * 64 + 2 * lane;
-    float2 cur[AD_B], nxt[AD_B];
-#pragma unroll
-    for (int b = 0; b < AD_B; b++) { const int jj = warp + b * AD_WARPS; cur[b] = jj < nk ? __ldg(reinterpret_cast<const float2 *>(vp + (size_t) (k_lo + jj) * kv_row)) : make_float2(0.f, 0.f); }
     for (int j = warp; j < nk; j += AD_B * AD_WARPS) {
 #pragma unroll
         for (int b = 0; b < AD_B; b++) { const int jj = j + (AD_B + b) * AD_WARPS; nxt[b] = jj < nk ? __ldg(reinterpret_cast<const float2 *>(vp + (size_t) (k_lo + jj) * kv_row)) : make_float2(0.f, 0.f); }
@@ -299,6 +330,7 @@ __global__ void __launch_bounds__(AD_THREADS, 6) attn_dec_values_kernel(const At
 #pragma unroll
     for (int h = 0; h < AD_G; h++) oacc[warp][h][lane] = acc[h];
     __syncthreads();
+    if (n_used > 1)
     for (int i = tid; i < AD_G * 32; i += AD_THREADS) {             // fixed warp order: deterministic
         const int h = i / 32, l = i % 32;
         float2 r = oacc[0][h][l];
@@ -308,10 +340,29 @@ __global__ void __launch_bounds__(AD_THREADS, 6) attn_dec_values_kernel(const At
     }
     }   // nk > 0
     if (n_used == 1) {
-        // short context: split 0 holds every key, its CTA combines its own partials (written above, visible to the CTA after the
-        // barrier) without the fence / counter round trips; the other CTAs of the fixed grid have nothing to do
+        // short context: split 0 holds every key; its CTA finishes from its own shared memory -- the same sums in the same order as the
+        // general path below (warps, then the single split), no scratch round trip, no fence, no counter
         if (split != 0) { trace_end(a.trace); return; }
+        if (tid < AD_G) {
+            double s = 0.0;
+#pragma unroll
+            for (int r = 0; r < AD_THREADS / AD_G; r++) s += dsum[r][tid];
+            inv_s[tid] = (float) (1.0 / s);
+        }
         __syncthreads();
+        const int hA = tid / 8, l0 = 4 * (tid % 8);                          // thread = 8 consecutive outputs of head tid / 8 = lanes l0 .. l0 + 3 of oacc
+        float y[8];
+        const float sc = hA < G ? inv_s[hA] : 0.f;
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            float2 r = oacc[0][hA][l0 + u];
+#pragma unroll
+            for (int w = 1; w < AD_WARPS; w++) { r.x += oacc[w][hA][l0 + u].x; r.y += oacc[w][hA][l0 + u].y; }
+            y[2 * u] = __fmul_rn(r.x, sc); y[2 * u + 1] = __fmul_rn(r.y, sc);
+        }
+        attn_dec_store(a, y, h0, hA, G, tid, lane);
+        trace_end(a.trace);
+        return;
     } else {
     // the last CTA of this KV head combines the splits
     __threadfence();
@@ -354,16 +405,7 @@ __global__ void __launch_bounds__(AD_THREADS, 6) attn_dec_values_kernel(const At
         const float s = hA < G ? inv_s[hA] : 0.f;
         const float y[8] = { __fmul_rn(r0.x, s), __fmul_rn(r0.y, s), __fmul_rn(r0.z, s), __fmul_rn(r0.w, s),
                              __fmul_rn(r1.x, s), __fmul_rn(r1.y, s), __fmul_rn(r1.z, s), __fmul_rn(r1.w, s) };
-        if (hA < G) {
-            float4 * dst = reinterpret_cast<float4 *>(a.out + (size_t) h0 * 64) + i0;
-            dst[0] = make_float4(y[0], y[1], y[2], y[3]); dst[1] = make_float4(y[4], y[5], y[6], y[7]);
-        }
-        if (a.has_q) {                                                      // wo's activation quantisation, here instead of in a kernel of its own
-            const int k0 = h0 * 64 + 8 * tid;                               // a warp = 256 consecutive outputs = 4 heads
-            if (a.qA.type == T_Q8_K) quantize_chunk8<T_Q8_K>(y, lane, a.qA, 0, k0, hA < G);
-            else if (a.qA.type == T_Q8_1) quantize_chunk8<T_Q8_1>(y, lane, a.qA, 0, k0, hA < G);
-            else quantize_chunk8<T_Q8_0>(y, lane, a.qA, 0, k0, hA < G);
-        }
+        attn_dec_store(a, y, h0, hA, G, tid, lane);
     }
     trace_end(a.trace);
 }
