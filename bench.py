@@ -661,12 +661,15 @@ def main():
         return
 
     mv_ms, mv_n, mv_bytes = d.pop("_probe")
-    traffic = None
-    try:
-        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as tf:
-            traffic = float(json.load(tf)["dram_bytes_per_matvec_launch"])
-    except Exception:
-        pass
+    traffic, traffic_src = None, None
+    for tname in ("r2_traffic.json", "r1_traffic.json"):          # ncu launch list of this command, summarised by tools/launch_list.py
+        try:
+            with open(os.path.join(ROOT, "profiles", tname)) as tf:
+                tj = json.load(tf)
+            traffic, traffic_src = float(tj["dram_bytes_per_matvec_launch"]), tj.get("source", tname)
+            break
+        except Exception:
+            pass
     ach = mv_bytes / (mv_ms / 1e3) / 1e9
     if sel == "3":
         value, unit, metric_name, ms_step = prompt["tok_s"], "tok/s", "falcon40b_q4_k_prompt_tokens_per_s", prompt["seconds"] * 1e3 / 4
@@ -682,7 +685,7 @@ def main():
            "step_roofline_frac": d["step_frac"],
            "roofline": {"bound": "hbm", "kernel": "mmv_fast_kernel<%s> (register-resident fused dequantise + int8 dot mat-vec)" % TYPE_NAME[wtype], "achieved": ach, "peak": peak,
                         "unit": "GB/s", "frac": ach / peak, "peak_source": peak_src, "traffic": traffic,
-                        "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum per mat-vec launch, profiles/r1_bench_launches.csv" if traffic else None,
+                        "traffic_source": ("ncu dram__bytes_read.sum + dram__bytes_write.sum per mat-vec launch: " + traffic_src) if traffic else None,
                         "launches_timed": int(mv_n), "avg_launch_us": mv_ms * 1e3 / max(mv_n, 1), "algorithmic_bytes_per_launch": mv_bytes / max(mv_n, 1),
                         "how": "all resident mat-vecs of rank 0 (4 per layer + lm_head) launched back to back x3 on the eval stream, CUDA events around the region; "
                                "each launch reads a different matrix, one pass >> L2",

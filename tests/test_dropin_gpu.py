@@ -14,14 +14,15 @@ HOOK = os.path.join(po.HERE, "_ref", "libfalcon_hook.so")
 
 @pytest.mark.skipif(not os.path.exists(HOOK), reason="oracle/_ref/libfalcon_hook.so not present (built where /root/reference exists)")
 @pytest.mark.parametrize("takeover", [True, False])
-@pytest.mark.parametrize("hp,wt,ftype", [(TINY_40B, po.Q4_K, 15), (TINY_7B, po.Q4_0, 2)])
-def test_reference_eval_runs_on_our_operator_surface(gpu, tmp_path, hp, wt, ftype, takeover, monkeypatch):
+@pytest.mark.parametrize("hp,wt,ftype,overrides", [(TINY_40B, po.Q4_K, 15, None), (TINY_7B, po.Q4_0, 2, None),
+                                                   (TINY_40B, po.Q4_K, 15, {"lm_head": po.F16})])      # a --leave-output-tensor file
+def test_reference_eval_runs_on_our_operator_surface(gpu, tmp_path, hp, wt, ftype, overrides, takeover, monkeypatch):
     """takeover=True: from the second falcon_eval on, the hook recognises the Falcon graph and evaluates it whole on the device-resident
     engine (ggml_surface.cu "whole-graph takeover"); False (B200_NO_TAKEOVER=1): every claimed node goes through the per-node protocol."""
     if not takeover:
         monkeypatch.setenv("B200_NO_TAKEOVER", "1")
     taken0 = gpu.lib().b200_surface_takeover_evals()
-    tensors = synth_model(hp, wt, seed=1234)
+    tensors = synth_model(hp, wt, seed=1234, overrides=overrides)
     path = str(tmp_path / "m.ggcc")
     ggcc.write_ggcc(path, hp, tensors, ftype=ftype)
     gpu.lib()                                      # libggml_b200.so is in the global symbol scope (RTLD_GLOBAL)
