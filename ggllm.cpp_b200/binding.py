@@ -23,7 +23,7 @@ PART_A = ["b200_event_create", "b200_event_destroy", "b200_event_record", "b200_
 PART_B = ["b200_falcon_create", "b200_falcon_set_tensor", "b200_falcon_set_tensor_random", "b200_falcon_load_ggcc",
           "b200_ggcc_read_hparams", "b200_falcon_free", "b200_falcon_weight_bytes", "b200_nccl_unique_id",
           "b200_falcon_init_pipeline", "b200_falcon_eval", "b200_falcon_decode_dev", "b200_falcon_logits_dev", "b200_falcon_generate_greedy",
-          "b200_falcon_last_launches", "b200_falcon_last_ms", "b200_falcon_stream", "b200_falcon_profile_matvec",
+          "b200_falcon_last_launches", "b200_attention_long_launches", "b200_falcon_last_ms", "b200_falcon_stream", "b200_falcon_profile_matvec",
           "b200_falcon_kv_read", "b200_falcon_kv_write", "b200_falcon_kv_fill_random", "b200_falcon_generate", "b200_falcon_load_seconds", "b200_falcon_save_kv", "b200_falcon_load_kv"]
 
 
@@ -80,6 +80,7 @@ def lib():
             fn = getattr(L, name)
             fn.restype, fn.argtypes = res, args
         L.b200_surface_takeover_evals.restype, L.b200_surface_takeover_evals.argtypes = C.c_long, []      # ggml_surface.cu test hook
+        L.b200_attention_long_launches.restype, L.b200_attention_long_launches.argtypes = C.c_int, []
         _lib = L
     return _lib
 

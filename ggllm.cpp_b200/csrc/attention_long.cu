@@ -1,0 +1,417 @@
+// attention_long.cu -- split-KV decode attention (n_tok == 1, head_dim 64, grouped-query models) for LONG contexts.
+//
+// Same contract and scratch layout as the split-KV kernels of attention.cu (see there for the numerics, libfalcon.cpp:2285-2366); what
+// differs is how the work is laid out, because at thousands of keys these kernels stop being hidden beside ffn_up / ffn_down:
+//   * ONE WAVE: n_splits x n_head_kv x head groups ~ the SM count.  Beside the mat-vec CTAs an SM has registers for exactly one of these
+//     128-thread CTAs, so the 256-CTA grid of attention.cu runs as two waves of latency-bound CTAs
+//   * rows stream through a warp-private cp.async ring (AL_R stages of AL_B rows): a lane reads back exactly the bytes it copied, so no
+//     barrier is involved and AL_R - 1 stages stay in flight per warp without holding registers
+//   * scores: ncu on attention.cu's kernel at 8k keys (profiles/r2_notes.md): 151 instructions per key, one warp per scheduler, issue slot
+//     29 % busy, no memory stall -- a latency-bound instruction stream.  Here a warp step covers AL_B = 4 keys, lane = (key, octet of the
+//     head dimension), the rotated query rows sit in shared memory, and the 16 per-head partials are reduced over the 8 lanes of a key
+//     only (14 shuffles per 4 keys instead of 64): 79 instructions per key
+//   * values: the exp of a key's 16 scores is taken by lanes 0..15 right where the key is consumed (no separate pass, no [key][head] array
+//     in shared memory), so the scores travel through the same ring as the V rows
+// Measured (Falcon-40B Q4_K, tok/s at n_past 8 / 2000 / 8000): attention.cu 210 / 195 / 135, this file 208 / 201 / 147; Falcon-180B
+// geometry at 8000: +10 %.  Falcon-7B (one KV head, five head groups re-reading it) is 8-10 % SLOWER with it at every length, and so are
+// short contexts in general (more shared memory per CTA of the fixed grid): launch_attention picks this path only for n_head_kv > 1 and
+// more than attention_long_threshold() keys; the decode graphs of engine.cu are captured per tier.
+#include "kernels.h"
+#include "actquant.cuh"
+
+__device__ __forceinline__ float exp_f16lut_l(float v) {      // table_exp_f16[f16(v)], ggml.c:4281-4290
+    return __half2float(__float2half_rn(expf(__half2float(__float2half_rn(v)))));
+}
+
+#define AL_THREADS 128                   // small CTAs at <= 85 registers: one fits beside ffn_up's two 256-thread CTAs on every SM
+#define AL_WARPS (AL_THREADS / 32)
+#define AL_MAX_SPLITS 32                 // the scratch holds this many partials per head (attention.cu's layout); the launcher picks n_splits <= it
+#define AL_B 4                           // key rows per warp and ring stage
+#define AL_R 4                           // ring stages per warp
+#define AL_G 16                          // query heads per KV head handled together (n_head / n_head_kv <= 16 per CTA, more in grid.z)
+
+struct AttnLongArgs {
+    const float * qkv; const float * kc; const float * vc; float * out;
+    float * S; float * pmax; double * psum; float * opart; unsigned * ctr;
+    int n_head, n_head_kv, G, n_past; const int * n_past_dev; int n_ctx; int64_t qkv_stride;
+    int n_splits;
+    unsigned long long * trace;
+    ActQ qA; int has_q;          // optional quantised copy of the output row (see AttnParams::qout)
+    int fuse_rope; float theta_scale; float * kc_w; float * vc_w; __half * k16; __half * vt16; int ctx_pad;     // see AttnParams::fuse_rope
+};
+
+__device__ __forceinline__ void cp_async8(void * smem, const void * g) { asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(smem_u32(smem)), "l"(g) : "memory"); }
+__device__ __forceinline__ void cp_async16(void * smem, const void * g) { asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(smem_u32(smem)), "l"(g) : "memory"); }
+__device__ __forceinline__ void cp_async4(void * smem, const void * g) { asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(smem_u32(smem)), "l"(g) : "memory"); }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+
+// keys per split: at least AL_MIN_KEYS, so that a short context occupies few CTAs and the combine step reads few partials (at
+// n_past < 64 one CTA per KV-head group does everything; the other CTAs of the fixed grid only check in at the counter)
+#define AL_MIN_KEYS 64
+__device__ __forceinline__ int split_keys(int T, int ns) { return max(AL_MIN_KEYS, (T + ns - 1) / ns); }
+__device__ __forceinline__ int splits_used(int T, int ns) { const int per = split_keys(T, ns); return (T + per - 1) / per; }
+__device__ __forceinline__ void split_range(int T, int ns, int split, int & k_lo, int & k_hi) {
+    const int per = split_keys(T, ns);
+    k_lo = min(T, split * per); k_hi = min(T, k_lo + per);
+}
+// ring stages warp `warp` needs for its keys jj = warp + AL_WARPS * (AL_B * stage + b) < nk
+__device__ __forceinline__ int warp_stages(int nk, int warp) { return nk > warp ? (nk - warp + AL_WARPS * AL_B - 1) / (AL_WARPS * AL_B) : 0; }
+
+// 16 per-lane values -> summed over the 8 lanes of an aligned group; lane o of the group ends up with values 2o and 2o + 1
+__device__ __forceinline__ void butterfly16x8(const float (&v)[16], int lane, float & r0, float & r1) {
+    float w8[8], w4[4];
+    const bool b2 = lane & 4, b1 = lane & 2, b0 = lane & 1;
+#pragma unroll
+    for (int i = 0; i < 8; i++) { const float keep = b2 ? v[8 + i] : v[i], send = b2 ? v[i] : v[8 + i]; w8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4); }
+#pragma unroll
+    for (int i = 0; i < 4; i++) { const float keep = b1 ? w8[4 + i] : w8[i], send = b1 ? w8[i] : w8[4 + i]; w4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2); }
+    const float k0 = b0 ? w4[2] : w4[0], s0 = b0 ? w4[0] : w4[2], k1 = b0 ? w4[3] : w4[1], s1 = b0 ? w4[1] : w4[3];
+    r0 = k0 + __shfl_xor_sync(0xffffffffu, s0, 1);
+    r1 = k1 + __shfl_xor_sync(0xffffffffu, s1, 1);
+}
+
+// Scores.  ncu on the first version (lane = 2 dims of ONE key, 16 heads reduced over the 32 lanes per key: 151 instructions per key, one
+// warp per scheduler, issue slot 29 % busy, no memory stall to speak of) showed a latency-bound instruction stream, not a memory-bound one.
+// Here a warp step covers AL_B = 4 keys: lane = (key kb = lane / 8, octet oc = lane % 8) holds 8 dims of its key, the rotated query rows sit
+// in shared memory ([head][64], read as broadcasts), 128 independent FMAs per lane and step, and the 16 per-head partials are reduced over
+// the 8 lanes of a key only (14 shuffles per 4 keys instead of 64): ~60 instructions per key.
+__global__ void __launch_bounds__(AL_THREADS, 6) attn_long_scores_kernel(const AttnLongArgs a) {
+    __shared__ float wmax[AL_WARPS][AL_G];
+    __shared__ __align__(16) float ring[AL_WARPS][AL_R][AL_B][64];         // 16 KB: K rows in flight (a lane reads back the 32 bytes it copied)
+    __shared__ __align__(16) float qs[AL_G][64];                           // this position's query rows, rotated
+    __shared__ __align__(16) float knew_s[64];                             // this position's key row, rotated (not in the cache yet)
+    trace_begin(a.trace);
+    const int split = blockIdx.x, kvh = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int h0 = kvh * a.G + blockIdx.z * AL_G, G = min(AL_G, a.G - (int) blockIdx.z * AL_G);      // this CTA's query heads: h0 .. h0 + G - 1
+    const int n_past = a.n_past_dev ? *a.n_past_dev : a.n_past, T = n_past + 1;
+    int k_lo, k_hi; split_range(T, a.n_splits, split, k_lo, k_hi);
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the values kernel may take its place on the SMs now (it waits for this grid to finish)
+    // RoPE work of thread t: pair i = t % 32 (elements i, i + 32) of heads t / 32 + 4 r and, for t < 32, of the key row.  The rows do not
+    // depend on n_past: their loads are in flight while the device scalar arrives.
+    const int ri = tid & 31, rh = tid >> 5;
+    float qa[AL_G / AL_WARPS], qb[AL_G / AL_WARPS];
+#pragma unroll
+    for (int r = 0; r < AL_G / AL_WARPS; r++) {
+        const int h = rh + AL_WARPS * r;
+        const float * src = a.qkv + (size_t) (h0 + min(h, G - 1)) * 64;
+        qa[r] = src[ri]; qb[r] = src[ri + 32];
+    }
+    const float * ksrc = a.qkv + (size_t) (a.n_head + kvh) * 64;
+    const float ka = ksrc[ri], kb_ = ksrc[ri + 32];
+    if (k_lo >= k_hi) { trace_end(a.trace); return; }            // a split without keys (short context): nothing to score, nobody reads its pmax
+    const int nk = k_hi - k_lo, nst = warp_stages(nk, warp);
+    const int j_new = a.fuse_rope ? n_past - k_lo : -1;           // this position's key is not in the cache yet (another CTA may be writing it right now)
+    const size_t kv_row = (size_t) a.n_head_kv * 64;
+    const int kb = lane >> 3, oc = lane & 7;
+    const float * kp = a.kc + (size_t) kvh * 64 + 8 * oc + (size_t) k_lo * kv_row;
+    auto issue = [&](int i) {
+        if (i < nst) {
+            const int jj = warp + AL_WARPS * (AL_B * i + kb);
+            if (jj < nk && jj != j_new) {
+                float * dst = &ring[warp][i % AL_R][kb][8 * oc];
+                cp_async16(dst, kp + (size_t) jj * kv_row); cp_async16(dst + 4, kp + (size_t) jj * kv_row + 4);
+            }
+        }
+        cp_async_commit();
+    };
+#pragma unroll
+    for (int i = 0; i < AL_R - 1; i++) issue(i);                 // the first rows travel while RoPE runs
+    // Fused RoPE + KV append (libfalcon.cpp:2229-2281), arithmetic of rope_pair (ops.cu): theta = n_past * theta_scale^i by repeated fp32 products
+    {
+        float c = 1.f, sn = 0.f;
+        if (a.fuse_rope) {
+            float th = (float) n_past;
+            for (int k = 0; k < ri; k++) th = __fmul_rn(th, a.theta_scale);
+            c = cosf(th); sn = sinf(th);
+        }
+        auto rot = [&](float x0, float x1, float & y0, float & y1) {
+            if (a.fuse_rope) { y0 = __fsub_rn(__fmul_rn(x0, c), __fmul_rn(x1, sn)); y1 = __fadd_rn(__fmul_rn(x0, sn), __fmul_rn(x1, c)); }
+            else { y0 = x0; y1 = x1; }
+        };
+#pragma unroll
+        for (int r = 0; r < AL_G / AL_WARPS; r++) {
+            const int h = rh + AL_WARPS * r;
+            float y0, y1; rot(qa[r], qb[r], y0, y1);
+            qs[h][ri] = h < G ? y0 : 0.f; qs[h][ri + 32] = h < G ? y1 : 0.f;
+        }
+        if (a.fuse_rope && warp == 0) {
+            float y0, y1; rot(ka, kb_, y0, y1);
+            knew_s[ri] = y0; knew_s[ri + 32] = y1;
+            if (blockIdx.z == 0 && n_past >= k_lo && n_past < k_hi) {                                                  // one warp appends K and V to the cache
+                const size_t o = ((size_t) n_past * a.n_head_kv + kvh) * 64;
+                const float * vsrc = a.qkv + (size_t) (a.n_head + a.n_head_kv + kvh) * 64;
+                const float v0 = vsrc[ri], v1 = vsrc[ri + 32];
+                a.kc_w[o + ri] = y0; a.kc_w[o + ri + 32] = y1;
+                a.vc_w[o + ri] = v0; a.vc_w[o + ri + 32] = v1;
+                if (a.k16) {
+                    a.k16[o + ri] = __float2half_rn(y0); a.k16[o + ri + 32] = __float2half_rn(y1);
+                    __half * vt = a.vt16 + (size_t) kvh * 64 * a.ctx_pad + n_past;
+                    vt[(size_t) ri * a.ctx_pad] = __float2half_rn(v0); vt[(size_t) (ri + 32) * a.ctx_pad] = __float2half_rn(v1);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    const float scale = 1.0f / sqrtf(64.0f);
+    float lmax0 = -INFINITY, lmax1 = -INFINITY;                   // heads 2 oc, 2 oc + 1 over this lane's keys
+    const float4 * q4 = reinterpret_cast<const float4 *>(&qs[0][8 * oc]);
+    for (int i = 0; i < nst; i++) {
+        issue(i + AL_R - 1);                                      // refills the stage consumed in the previous iteration
+        cp_async_wait<AL_R - 1>();                                // stage i has landed (a lane reads only what it copied itself)
+        const int jj = warp + AL_WARPS * (AL_B * i + kb);
+        const float * src = jj == j_new ? &knew_s[8 * oc] : &ring[warp][i % AL_R][kb][8 * oc];
+        float4 k0 = *reinterpret_cast<const float4 *>(src), k1 = *reinterpret_cast<const float4 *>(src + 4);
+        if (jj >= nk) { k0 = make_float4(0.f, 0.f, 0.f, 0.f); k1 = k0; }
+        float part[AL_G];
+#pragma unroll
+        for (int h = 0; h < AL_G; h++) {
+            const float4 qa4 = q4[h * 16], qb4 = q4[h * 16 + 1];
+            part[h] = k0.x * qa4.x + k0.y * qa4.y + k0.z * qa4.z + k0.w * qa4.w + k1.x * qb4.x + k1.y * qb4.y + k1.z * qb4.z + k1.w * qb4.w;
+        }
+        float s0, s1; butterfly16x8(part, lane, s0, s1);
+        s0 = __fmul_rn(s0, scale); s1 = __fmul_rn(s1, scale);   // libfalcon.cpp:2313-2317
+        if (jj < nk) {
+            if (2 * oc < G)     { a.S[(size_t) (h0 + 2 * oc) * a.n_ctx + k_lo + jj] = s0; lmax0 = fmaxf(lmax0, s0); }
+            if (2 * oc + 1 < G) { a.S[(size_t) (h0 + 2 * oc + 1) * a.n_ctx + k_lo + jj] = s1; lmax1 = fmaxf(lmax1, s1); }
+        }
+    }
+    cp_async_wait<0>();
+    lmax0 = fmaxf(lmax0, __shfl_xor_sync(0xffffffffu, lmax0, 8)); lmax0 = fmaxf(lmax0, __shfl_xor_sync(0xffffffffu, lmax0, 16));
+    lmax1 = fmaxf(lmax1, __shfl_xor_sync(0xffffffffu, lmax1, 8)); lmax1 = fmaxf(lmax1, __shfl_xor_sync(0xffffffffu, lmax1, 16));
+    if (lane < 8) { wmax[warp][2 * lane] = lmax0; wmax[warp][2 * lane + 1] = lmax1; }
+    __syncthreads();
+    if (tid < G) {
+        float mx = wmax[0][tid];
+#pragma unroll
+        for (int w = 1; w < AL_WARPS; w++) mx = fmaxf(mx, wmax[w][tid]);
+        a.pmax[(size_t) (h0 + tid) * AL_MAX_SPLITS + split] = mx;
+    }
+    trace_end(a.trace);
+}
+
+// thread tid's 8 consecutive outputs (head hA of the CTA's group) -> the attention output row, plus wo's activation quantisation
+__device__ __forceinline__ void attn_long_store(const AttnLongArgs & a, const float (&y)[8], int h0, int hA, int G, int tid, int lane) {
+    if (hA < G) {
+        float4 * dst = reinterpret_cast<float4 *>(a.out + (size_t) h0 * 64) + 2 * tid;
+        dst[0] = make_float4(y[0], y[1], y[2], y[3]); dst[1] = make_float4(y[4], y[5], y[6], y[7]);
+    }
+    if (a.has_q) {                                                      // here instead of in a kernel of its own
+        const int k0 = h0 * 64 + 8 * tid;                               // a warp = 256 consecutive outputs = 4 heads
+        if (a.qA.type == T_Q8_K) quantize_chunk8<T_Q8_K>(y, lane, a.qA, 0, k0, hA < G);
+        else if (a.qA.type == T_Q8_1) quantize_chunk8<T_Q8_1>(y, lane, a.qA, 0, k0, hA < G);
+        else quantize_chunk8<T_Q8_0>(y, lane, a.qA, 0, k0, hA < G);
+    }
+}
+
+__global__ void __launch_bounds__(AL_THREADS, 6) attn_long_values_kernel(const AttnLongArgs a) {
+    // V rows in flight; once a warp has consumed its rows the same 4 KB hold its partial outputs [head][lane] = dims 2l, 2l+1
+    __shared__ __align__(16) float2 vring[AL_WARPS][AL_R * AL_B * 32];
+    __shared__ float sring[AL_WARPS][AL_R][AL_B][AL_G];            // the scores of those rows: [head], copied by lanes 0 .. 15
+    __shared__ float gmax[AL_G];
+    __shared__ double dsum[AL_WARPS][AL_G];
+    __shared__ float inv_s[AL_G];
+    __shared__ int s_last;
+    static_assert(AL_R * AL_B * 32 == AL_G * 32, "a warp's ring doubles as its [AL_G][32] partial-output block");
+    const int split = blockIdx.x, kvh = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int h0 = kvh * a.G + blockIdx.z * AL_G, G = min(AL_G, a.G - (int) blockIdx.z * AL_G);
+    const int n_past = a.n_past_dev ? *a.n_past_dev : a.n_past, T = n_past + 1;
+    int k_lo, k_hi; split_range(T, a.n_splits, split, k_lo, k_hi);
+    const int nk = k_hi - k_lo, nst = warp_stages(nk, warp);
+    const size_t kv_row = (size_t) a.n_head_kv * 64;
+    trace_begin(a.trace);
+    const int n_used = splits_used(T, a.n_splits);                // splits 0 .. n_used - 1 hold keys
+    const int j_new = n_past - k_lo;                              // this position's V row is appended by the scores kernel: read after the wait
+    const float * vp = a.vc + (size_t) kvh * 64 + 2 * lane + (size_t) k_lo * kv_row;
+    const float * Sr = a.S + (size_t) (h0 + min(lane, G - 1)) * a.n_ctx + k_lo;
+    float2 (*vr)[AL_B][32] = reinterpret_cast<float2 (*)[AL_B][32]>(vring[warp]);
+    auto issue = [&](int i, bool v, bool s) {
+        if (i < nst) {
+#pragma unroll
+            for (int b = 0; b < AL_B; b++) {
+                const int jj = warp + AL_WARPS * (AL_B * i + b);
+                if (jj < nk) {
+                    if (v && jj != j_new) cp_async8(&vr[i % AL_R][b][lane], vp + (size_t) jj * kv_row);
+                    if (s && lane < AL_G) cp_async4(&sring[warp][i % AL_R][b][lane], Sr + jj);
+                }
+            }
+        }
+        cp_async_commit();
+    };
+    // V rows of EARLIER positions have been in the cache since their own decode steps: the first stages travel while the scores kernel still runs
+#pragma unroll
+    for (int i = 0; i < AL_R - 1; i++) issue(i, true, false);
+    asm volatile("griddepcontrol.wait;" ::: "memory");            // launched programmatically behind the scores kernel: its S / pmax / KV append are complete from here on
+    if (nk > 0) {
+#pragma unroll
+    for (int i = 0; i < AL_R - 1; i++) issue(i, false, true);     // their scores, together with the split maxima: one round trip
+    const float2 vnew = j_new >= 0 && j_new < nk ? *reinterpret_cast<const float2 *>(vp + (size_t) j_new * kv_row) : make_float2(0.f, 0.f);
+    if (tid < AL_G) {
+        float mx = -INFINITY;
+        if (tid < G) for (int s = 0; s < n_used; s++) mx = fmaxf(mx, a.pmax[(size_t) (h0 + tid) * AL_MAX_SPLITS + s]);
+        gmax[tid] = mx;
+    }
+    __syncthreads();
+    const float gm = gmax[lane & (AL_G - 1)];
+    double lsum = 0.0;                                             // lane h < 16: sum of head h's e over the warp's keys
+    // O_partial[h][2l..2l+1] = sum over the warp's keys of V[key][2l..2l+1] * e[key][h],  e = table_exp_f16[f16(s - max)] (ggml.c:12427-12440)
+    float2 acc[AL_G];
+#pragma unroll
+    for (int h = 0; h < AL_G; h++) acc[h] = make_float2(0.f, 0.f);
+    for (int i = 0; i < nst; i++) {
+        issue(i + AL_R - 1, true, true);
+        cp_async_wait<AL_R - 1>();
+#pragma unroll
+        for (int b = 0; b < AL_B; b++) {
+            const int jj = warp + AL_WARPS * (AL_B * i + b);
+            if (jj < nk) {                                                    // warp-uniform
+                float e = 0.f;
+                if (lane < G) { e = exp_f16lut_l(__fsub_rn(sring[warp][i % AL_R][b][lane], gm)); lsum += (double) e; }
+                const float2 vv = jj == j_new ? vnew : vr[i % AL_R][b][lane];
+#pragma unroll
+                for (int h = 0; h < AL_G; h++) {
+                    const float eh = __shfl_sync(0xffffffffu, e, h);
+                    acc[h].x += vv.x * eh; acc[h].y += vv.y * eh;
+                }
+            }
+        }
+    }
+    cp_async_wait<0>();
+    if (lane < AL_G) dsum[warp][lane] = lsum;
+    __syncwarp();                                                              // every lane is done with the ring: it becomes the warp's partial-output block
+    float2 (*oacc)[32] = reinterpret_cast<float2 (*)[32]>(vring[warp]);
+#pragma unroll
+    for (int h = 0; h < AL_G; h++) oacc[h][lane] = acc[h];
+    __syncthreads();
+    if (n_used > 1) {
+        if (tid < G) a.psum[(size_t) (h0 + tid) * AL_MAX_SPLITS + split] = ((dsum[0][tid] + dsum[1][tid]) + dsum[2][tid]) + dsum[3][tid];
+        for (int i = tid; i < AL_G * 32; i += AL_THREADS) {             // fixed warp order: deterministic
+            const int h = i / 32, l = i % 32;
+            float2 r = vring[0][h * 32 + l];
+#pragma unroll
+            for (int w = 1; w < AL_WARPS; w++) { r.x += vring[w][h * 32 + l].x; r.y += vring[w][h * 32 + l].y; }
+            if (h < G) *reinterpret_cast<float2 *>(a.opart + ((size_t) (split * a.n_head + h0 + h)) * 64 + 2 * l) = r;
+        }
+    }
+    }   // nk > 0
+    static_assert(AL_WARPS == 4, "dsum is summed as four terms");
+    if (n_used == 1) {
+        // short context: split 0 holds every key; its CTA finishes from its own shared memory -- the same sums in the same order as the
+        // general path below (warps, then the single split), no scratch round trip, no fence, no counter
+        if (split != 0) { trace_end(a.trace); return; }
+        if (tid < AL_G) inv_s[tid] = (float) (1.0 / (((dsum[0][tid] + dsum[1][tid]) + dsum[2][tid]) + dsum[3][tid]));
+        __syncthreads();
+        const int hA = tid / 8, l0 = 4 * (tid % 8);                          // thread = 8 consecutive outputs of head tid / 8 = lanes l0 .. l0 + 3 of the partial blocks
+        float y[8];
+        const float sc = hA < G ? inv_s[hA] : 0.f;
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            float2 r = vring[0][hA * 32 + l0 + u];
+#pragma unroll
+            for (int w = 1; w < AL_WARPS; w++) { r.x += vring[w][hA * 32 + l0 + u].x; r.y += vring[w][hA * 32 + l0 + u].y; }
+            y[2 * u] = __fmul_rn(r.x, sc); y[2 * u + 1] = __fmul_rn(r.y, sc);
+        }
+        attn_long_store(a, y, h0, hA, G, tid, lane);
+        trace_end(a.trace);
+        return;
+    }
+    // the last CTA of this KV head group combines the splits
+    __threadfence();
+    __syncthreads();
+    unsigned * ctr = a.ctr + kvh * gridDim.z + blockIdx.z;
+    if (tid == 0) { const unsigned old = atomicAdd(ctr, 1u); s_last = old == (unsigned) a.n_splits - 1; if (s_last) *ctr = 0; }
+    __syncthreads();
+    if (!s_last) { trace_end(a.trace); return; }
+    __threadfence();
+    if (tid < AL_G) {
+        double s = 0.0;
+        if (tid < G) for (int sp = 0; sp < n_used; sp++) s += __ldcg(a.psum + (size_t) (h0 + tid) * AL_MAX_SPLITS + sp);
+        inv_s[tid] = (float) (1.0 / s);
+    }
+    __syncthreads();
+    // 16 x 64 outputs as 256 float4 items, two per thread, every split's partial read once: batches of 8 splits x 2 items in
+    // flight (this tail is the fixed cost of the kernel, keep it short)
+    {
+        const int i0 = 2 * tid, i1 = 2 * tid + 1;                           // float4 items: thread = 8 consecutive outputs of head tid / 8
+        float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0;
+        const float * base = a.opart + (size_t) h0 * 64;
+        const int hA = tid / 8;
+#pragma unroll 1
+        for (int sp = 0; sp < n_used; sp += 8) {
+            float4 t0[8], t1[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const float * ps = base + (size_t) (sp + u) * a.n_head * 64;
+                const bool live = hA < G && sp + u < n_used;              // partials of splits without keys were never written
+                t0[u] = live ? __ldcg(reinterpret_cast<const float4 *>(ps) + i0) : make_float4(0.f, 0.f, 0.f, 0.f);
+                t1[u] = live ? __ldcg(reinterpret_cast<const float4 *>(ps) + i1) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < 8; u++) {                                   // fixed split order: deterministic
+                r0.x += t0[u].x; r0.y += t0[u].y; r0.z += t0[u].z; r0.w += t0[u].w;
+                r1.x += t1[u].x; r1.y += t1[u].y; r1.z += t1[u].z; r1.w += t1[u].w;
+            }
+        }
+        const float s = hA < G ? inv_s[hA] : 0.f;
+        const float y[8] = { __fmul_rn(r0.x, s), __fmul_rn(r0.y, s), __fmul_rn(r0.z, s), __fmul_rn(r0.w, s),
+                             __fmul_rn(r1.x, s), __fmul_rn(r1.y, s), __fmul_rn(r1.z, s), __fmul_rn(r1.w, s) };
+        attn_long_store(a, y, h0, hA, G, tid, lane);
+    }
+    trace_end(a.trace);
+}
+
+static size_t align256(size_t v) { return (v + 255) & ~(size_t) 255; }
+#define AL_CTR_BYTES 4096                 // as AD_CTR_BYTES in attention.cu: the two variants share one scratch block
+// scratch: attention_scratch_bytes(p) bytes whose first AL_CTR_BYTES were zeroed once by the owner (the counters re-arm themselves)
+static int g_long_launches = 0;
+extern "C" int b200_attention_long_launches(void) { return g_long_launches; }       // diagnostics / tests: launches (eager or captured) of this path
+
+bool launch_attention_long(const float * qkv, const float * k_cache, const float * v_cache, float * out, const AttnParams & p, float * scratch, cudaStream_t stream) {
+    if (!scratch || p.n_tok != 1 || p.head_dim != 64 || p.n_head % p.n_head_kv || getenv("B200_ATTN_NOLONG")) return false;
+    const int G = p.n_head / p.n_head_kv, groups = (G + AL_G - 1) / AL_G;
+    if ((size_t) p.n_head_kv * groups * 4 > AL_CTR_BYTES) return false;
+    AttnLongArgs a;
+    uint8_t * s = reinterpret_cast<uint8_t *>(scratch);
+    a.ctr = reinterpret_cast<unsigned *>(s); s += AL_CTR_BYTES;
+    a.S = reinterpret_cast<float *>(s); s += align256((size_t) p.n_head * p.n_ctx * 4);
+    a.pmax = reinterpret_cast<float *>(s); s += align256((size_t) p.n_head * AL_MAX_SPLITS * 4);
+    a.psum = reinterpret_cast<double *>(s); s += align256((size_t) p.n_head * AL_MAX_SPLITS * 8);
+    a.opart = reinterpret_cast<float *>(s);
+    a.qkv = qkv; a.kc = k_cache; a.vc = v_cache; a.out = out;
+    a.n_head = p.n_head; a.n_head_kv = p.n_head_kv; a.G = p.n_head / p.n_head_kv; a.n_past = p.n_past; a.n_past_dev = p.n_past_dev; a.n_ctx = p.n_ctx;
+    a.qkv_stride = p.qkv_stride;
+    a.fuse_rope = p.fuse_rope; a.theta_scale = p.rope_theta_scale; a.kc_w = const_cast<float *>(k_cache); a.vc_w = const_cast<float *>(v_cache);
+    a.k16 = p.k16; a.vt16 = p.vt16; a.ctx_pad = attention_ctx_pad(p.n_ctx);
+    // one wave: as many key splits as SMs divided by the (KV head, head group) pairs -- Falcon-40B 18, 180B 9, 7B 29
+    static int sms = 0, force = -1;
+    if (!sms) { int dev; B200_CUDA_CHECK(cudaGetDevice(&dev)); B200_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)); }
+    if (force < 0) { const char * e = getenv("B200_ATTN_SPLITS"); force = e ? atoi(e) : 0; }
+    a.n_splits = force > 0 ? force : sms / (p.n_head_kv * groups);
+    a.n_splits = a.n_splits < 4 ? 4 : a.n_splits > AL_MAX_SPLITS ? AL_MAX_SPLITS : a.n_splits;
+    // Q8_K blocks are 256 outputs = 4 heads: they must not straddle the 16-head groups the CTAs combine
+    a.has_q = p.qout != nullptr && (p.qout->type != T_Q8_K || G % 4 == 0);
+    if (a.has_q) a.qA = *p.qout;
+    B200_ASSERT(p.qout == nullptr || a.has_q);
+    static bool set = false;
+    if (!set) {
+        B200_CUDA_CHECK(cudaFuncSetAttribute(attn_long_scores_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, B200_CARVEOUT));
+        B200_CUDA_CHECK(cudaFuncSetAttribute(attn_long_values_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, B200_CARVEOUT));
+        set = true;
+    }
+    dim3 grid((unsigned) a.n_splits, (unsigned) p.n_head_kv, (unsigned) groups);
+    g_long_launches++;
+    a.trace = b200_trace_slot("attn_scores");
+    attn_long_scores_kernel<<<grid, AL_THREADS, 0, stream>>>(a);
+    B200_CUDA_CHECK(cudaGetLastError());
+    a.trace = b200_trace_slot("attn_values");
+    {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = grid; cfg.blockDim = dim3(AL_THREADS); cfg.dynamicSmemBytes = 0; cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr; cfg.numAttrs = getenv("B200_NO_PDL") ? 0 : 1;
+        B200_CUDA_CHECK(cudaLaunchKernelEx(&cfg, attn_long_values_kernel, a));
+    }
+    return true;
+}
+

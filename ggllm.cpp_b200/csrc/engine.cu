@@ -82,7 +82,11 @@ struct b200_falcon {
     cudaEvent_t e_fork = nullptr, e_join = nullptr, e_t0 = nullptr, e_t1 = nullptr;
     // decode graphs: [0] = device-resident step, [1] = host-to-host step (token H2D + logits D2H nodes inside)
     // [2] = generation step: [0] plus the sampler; in a pipeline the sampled id travels last rank -> rank 0 by ncclSend/ncclRecv
-    cudaGraphExec_t graph[3] = { nullptr, nullptr, nullptr }; float graph_theta[3] = { -1.f, -1.f, -1.f }; int graph_launches = 0;
+    // decode step graphs: [which + 3 * tier], which = 0 device token in / logits stay on the device, 1 host token in / host logits out,
+    // 2 generation step (token ring, sampler); tier 1 = captured with the long-context attention kernels (attention_long.cu), used above
+    // attention_long_threshold() keys
+    cudaGraphExec_t graph[6] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr }; float graph_theta[6] = { -1.f, -1.f, -1.f, -1.f, -1.f, -1.f };
+    int graph_launches = 0, cur_tier = 0;
     bool ring_mode = false;                     // set while the generation-step graph is being captured
     int32_t * tok_next = nullptr, * gen_hist = nullptr; int * gen_step = nullptr;   // sampled id, ids so far, step counter (device)
     SamplerState * sampler = nullptr; SamplerParams sampler_p{}; bool use_sampler = false; float * sampler_work = nullptr;   // generation with the sampling chain (sampling.cu)
@@ -160,7 +164,7 @@ static void expected_shape(const b200_falcon * f, const Slot & s, int64_t & K, i
 // the instantiated decode graphs bake in device pointers (weights, LayerNorm vectors, the pinned logits buffer):
 // whenever one of those is replaced the graphs are dropped and rebuilt by the next decode
 static void invalidate_graphs(b200_falcon * f) {
-    for (int i = 0; i < 3; i++) if (f->graph[i]) {
+    for (int i = 0; i < 6; i++) if (f->graph[i]) {
         B200_CUDA_CHECK(cudaStreamSynchronize(f->s_main));
         B200_CUDA_CHECK(cudaGraphExecDestroy(f->graph[i])); f->graph[i] = nullptr; f->graph_theta[i] = -1.f;
     }
@@ -491,7 +495,7 @@ void b200_falcon_free(b200_falcon * f) {
     cudaFree(f->attn_scratch); cudaFree(f->actq_mem); cudaFree(f->gen_na); cudaFree(f->gen_nm); cudaFree(f->gen_actq); cudaFree(f->gen_xh); cudaFree(f->xh_a); cudaFree(f->xh_b); cudaFree(f->xh_m); cudaFree(f->gemm_ws_a); cudaFree(f->gemm_ws_b);
     cudaFree(f->tokens_dev); cudaFree(f->n_past_dev); cudaFree(f->q_ctr); cudaFree(f->attn_dec_scratch);
     cudaFreeHost(f->tokens_h); cudaFreeHost(f->n_past_h); cudaFreeHost(f->logits_h);
-    for (int i = 0; i < 3; i++) if (f->graph[i]) cudaGraphExecDestroy(f->graph[i]);
+    for (int i = 0; i < 6; i++) if (f->graph[i]) cudaGraphExecDestroy(f->graph[i]);
     cudaFree(f->tok_next); cudaFree(f->gen_hist); cudaFree(f->gen_step); cudaFree(f->sampler_work); sampler_state_free(f->sampler);
     if (f->comm) nccl().CommDestroy(f->comm);
     cudaEventDestroy(f->e_fork); cudaEventDestroy(f->e_join); cudaEventDestroy(f->e_t0); cudaEventDestroy(f->e_t1);
@@ -606,6 +610,7 @@ static void enqueue_decode_fused(b200_falcon * f, int n_past, float theta_scale,
         B200_CUDA_CHECK(cudaEventRecord(f->e_fork, sa));
         B200_CUDA_CHECK(cudaStreamWaitEvent(sb, f->e_fork, 0));
         AttnParams ap = { f->H, f->HKV, f->D, 1, n_past, graph_mode ? f->n_past_dev : nullptr, f->hp.n_ctx, (int64_t) f->QKV, nullptr };
+        ap.long_ctx = graph_mode ? f->cur_tier : 0;
         const size_t kvoff = (size_t) l * f->hp.n_ctx * f->HKV * f->D;
         if (f->k16) { ap.k16 = f->k16 + (size_t) l * f->shadow_layer; ap.vt16 = f->vt16 + (size_t) l * f->shadow_layer; }
         if (!skip("attn")) {
@@ -659,6 +664,7 @@ static void enqueue_eval_generic(b200_falcon * f, int N, int n_past, float theta
         if (dual) { launch_layernorm(f->inp, E, L.ln_attn_g, L.ln_attn_b, f->gen_na, E, E, N, sa); f->launches++; }
         mm_any(f, L.wqkv, dual ? f->gen_na : f->gen_nm, N, f->qkv, f->QKV, false, sa);                                   // :2192
         AttnParams ap = { f->H, f->HKV, f->D, N, n_past, graph_mode ? f->n_past_dev : nullptr, f->hp.n_ctx, (int64_t) f->QKV, nullptr };
+        ap.long_ctx = graph_mode ? f->cur_tier : 0;
         const size_t kvoff = (size_t) l * f->hp.n_ctx * f->HKV * f->D;
         if (f->k16) { ap.k16 = f->k16 + (size_t) l * f->shadow_layer; ap.vt16 = f->vt16 + (size_t) l * f->shadow_layer; }
         launch_rope_kv_append(f->qkv, f->k_cache + kvoff, f->v_cache + kvoff, ap, theta_scale, sa); f->launches++;      // :2229-2281
@@ -712,6 +718,7 @@ static void enqueue_eval(b200_falcon * f, int N, int n_past, float theta_scale, 
         // attention branch on s_main
         mm(f, L.wqkv, attn_in, N, f->qkv, f->QKV, EPI_NONE, nullptr, nullptr, f->xh_a, f->gemm_ws_a, sa);      // :2192
         AttnParams ap = { f->H, f->HKV, f->D, N, n_past, graph_mode ? f->n_past_dev : nullptr, f->hp.n_ctx, (int64_t) f->QKV, nullptr };
+        ap.long_ctx = graph_mode ? f->cur_tier : 0;
         const size_t kvoff = (size_t) l * f->hp.n_ctx * f->HKV * f->D;
         if (f->k16) { ap.k16 = f->k16 + (size_t) l * f->shadow_layer; ap.vt16 = f->vt16 + (size_t) l * f->shadow_layer; }
         if (N == 1) { ap.fuse_rope = 1; ap.rope_theta_scale = theta_scale; }                                    // decode: RoPE + KV append inside the attention launch
@@ -738,8 +745,11 @@ static void enqueue_eval(b200_falcon * f, int N, int n_past, float theta_scale, 
 
 __global__ void set_i32_kernel(int * p, int v) { *p = v; }
 
-static void build_decode_graph(b200_falcon * f, int which, float theta_scale) {
-    if (f->graph[which]) { B200_CUDA_CHECK(cudaGraphExecDestroy(f->graph[which])); f->graph[which] = nullptr; }
+static int tier_of(const b200_falcon * f, int n_past) { return f->HKV > 1 && n_past + 1 > attention_long_threshold() ? 1 : 0; }
+static void build_decode_graph(b200_falcon * f, int which, float theta_scale, int tier) {
+    const int gi = which + 3 * tier;
+    if (f->graph[gi]) { B200_CUDA_CHECK(cudaGraphExecDestroy(f->graph[gi])); f->graph[gi] = nullptr; }
+    f->cur_tier = tier;
     // one eager pass first: sets the kernels' shared-memory attributes and allocates the activation arena outside
     // the capture (it recomputes the same token at the same position, which the replay then overwrites identically)
     if (which == 1) {
@@ -760,9 +770,9 @@ static void build_decode_graph(b200_falcon * f, int which, float theta_scale) {
     f->ring_mode = false;
     if (which == 1 && f->last) B200_CUDA_CHECK(cudaMemcpyAsync(f->logits_h, f->logits, (size_t) f->V * 4, cudaMemcpyDeviceToHost, f->s_main));
     B200_CUDA_CHECK(cudaStreamEndCapture(f->s_main, &g));
-    B200_CUDA_CHECK(cudaGraphInstantiate(&f->graph[which], g, 0));
+    B200_CUDA_CHECK(cudaGraphInstantiate(&f->graph[gi], g, 0));
     B200_CUDA_CHECK(cudaGraphDestroy(g));
-    f->graph_theta[which] = theta_scale; f->graph_launches = f->launches;
+    f->graph_theta[gi] = theta_scale; f->graph_launches = f->launches; f->cur_tier = 0;
 }
 
 extern "C" {
@@ -779,9 +789,10 @@ extern "C++" int falcon_eval_begin(b200_falcon * f, const int32_t * tokens, int 
     const float theta = rope_theta_scale_host(f->D, n_ctx_rope ? n_ctx_rope : f->hp.n_ctx, 1, 2.0f, 0);         // libfalcon.cpp:2229-2234
     if (n_tokens == 1) {
         f->tokens_h[0] = tokens ? tokens[0] : 0; *f->n_past_h = n_past;
-        if (!f->graph[1] || f->graph_theta[1] != theta) build_decode_graph(f, 1, theta);
+        const int tier = tier_of(f, n_past), gi = 1 + 3 * tier;
+        if (!f->graph[gi] || f->graph_theta[gi] != theta) build_decode_graph(f, 1, theta, tier);
         B200_CUDA_CHECK(cudaEventRecord(f->e_t0, f->s_main));
-        B200_CUDA_CHECK(cudaGraphLaunch(f->graph[1], f->s_main));
+        B200_CUDA_CHECK(cudaGraphLaunch(f->graph[gi], f->s_main));
         B200_CUDA_CHECK(cudaEventRecord(f->e_t1, f->s_main));
         f->launches = f->graph_launches;
         f->pending_floats = f->last ? (size_t) f->V : 0;
@@ -821,17 +832,18 @@ int b200_falcon_eval(b200_falcon * f, const int32_t * tokens, int n_tokens, int 
 int b200_falcon_decode_dev(b200_falcon * f, const int32_t * token_dev, int n_past, int n_ctx_rope) {
     if (n_past < 0 || n_past >= f->hp.n_ctx) return 1;                       // the KV append would leave this layer's cache slice
     const float theta = rope_theta_scale_host(f->D, n_ctx_rope ? n_ctx_rope : f->hp.n_ctx, 1, 2.0f, 0);
-    if (!f->graph[0] || f->graph_theta[0] != theta) {
+    const int tier = tier_of(f, n_past), gi = 3 * tier;
+    if (!f->graph[gi] || f->graph_theta[gi] != theta) {
         set_i32_kernel<<<1, 1, 0, f->s_main>>>(f->n_past_dev, n_past);
         if (f->first && token_dev) B200_CUDA_CHECK(cudaMemcpyAsync(f->tokens_dev, token_dev, 4, cudaMemcpyDeviceToDevice, f->s_main));
-        build_decode_graph(f, 0, theta);
+        build_decode_graph(f, 0, theta, tier);
     }
     // position and token id are device scalars the graph reads; both are set stream-ordered (the position travels
     // as a kernel argument, so the host may run ahead by any number of steps)
     set_i32_kernel<<<1, 1, 0, f->s_main>>>(f->n_past_dev, n_past);
     if (f->first && token_dev) B200_CUDA_CHECK(cudaMemcpyAsync(f->tokens_dev, token_dev, 4, cudaMemcpyDeviceToDevice, f->s_main));
-    if (getenv("B200_NO_GRAPH")) { f->launches = 0; enqueue_eval(f, 1, 0, theta, true, 0); return 0; }   // timing experiments: eager launches
-    B200_CUDA_CHECK(cudaGraphLaunch(f->graph[0], f->s_main));
+    if (getenv("B200_NO_GRAPH")) { f->launches = 0; f->cur_tier = tier; enqueue_eval(f, 1, 0, theta, true, 0); f->cur_tier = 0; return 0; }   // timing experiments: eager launches
+    B200_CUDA_CHECK(cudaGraphLaunch(f->graph[gi], f->s_main));
     f->launches = f->graph_launches;
     return 0;
 }
@@ -874,8 +886,11 @@ static int generate_impl(b200_falcon * f, int32_t first_token, int n_past, int n
     set_i32_kernel<<<1, 1, 0, st>>>(f->n_past_dev, n_past);
     if (f->first) { set_i32_kernel<<<1, 1, 0, st>>>((int *) f->tokens_dev, first_token); }
     // both step graphs on every rank, built in the same order (each build runs one eager pass with the pipeline's send / recv pairs)
-    if (!f->graph[0] || f->graph_theta[0] != theta) build_decode_graph(f, 0, theta);
-    if (!f->graph[2] || f->graph_theta[2] != theta) build_decode_graph(f, 2, theta);
+    // (a generation that crosses the long-context threshold needs both tiers)
+    for (int tier = tier_of(f, n_past); tier <= tier_of(f, n_past + n_steps - 1); tier++)
+        for (int which = 0; which <= 2; which += 2)
+            if (!f->graph[which + 3 * tier] || f->graph_theta[which + 3 * tier] != theta) build_decode_graph(f, which, theta, tier);
+    set_i32_kernel<<<1, 1, 0, st>>>(f->n_past_dev, n_past);
     set_i32_kernel<<<1, 1, 0, st>>>(f->gen_step, 0);
     if (f->first) { set_i32_kernel<<<1, 1, 0, st>>>((int *) f->tokens_dev, first_token); }
     B200_CUDA_CHECK(cudaEventRecord(f->e_t0, st));
@@ -883,7 +898,7 @@ static int generate_impl(b200_falcon * f, int32_t first_token, int n_past, int n
         set_i32_kernel<<<1, 1, 0, st>>>(f->n_past_dev, n_past + i);
         // rank 0 of a pipeline takes its first id from the caller and every later one from the last rank
         const int which = (f->last || (f->first && i > 0)) ? 2 : 0;
-        B200_CUDA_CHECK(cudaGraphLaunch(f->graph[(f->first && f->hp.world > 1 && i == 0) ? 0 : which], st));
+        B200_CUDA_CHECK(cudaGraphLaunch(f->graph[((f->first && f->hp.world > 1 && i == 0) ? 0 : which) + 3 * tier_of(f, n_past + i)], st));
     }
     if (f->first && f->hp.world > 1) B200_NCCL_CHECK(nccl().Recv(f->tokens_dev, 1, ncclInt32, f->hp.world - 1, f->comm, st));   // the id sampled after the last step
     B200_CUDA_CHECK(cudaEventRecord(f->e_t1, st));

@@ -79,7 +79,12 @@ struct AttnParams {
     // rope_kv_append_kernel in front of the fallback kernel) instead of by a separate launch_rope_kv_append: one kernel less on the
     // decode step's attention chain.  qkv is then NOT rotated in place.
     int fuse_rope; float rope_theta_scale;
+    // decode with n_past in a device scalar (graph replay): the caller's promise that this launch only serves contexts longer than
+    // attention_long_threshold() keys, so the long-context kernels (attention_long.cu) may be captured; with a host n_past the launcher
+    // decides by itself
+    int long_ctx;
 };
+int    attention_long_threshold();          // keys above which grouped-query decode attention switches to attention_long.cu
 // fused: rope(Q), rope(K) -> K cache append, V cache append      (libfalcon.cpp:2229-2281)
 void   launch_rope_kv_append(float * qkv, float * k_cache, float * v_cache, const AttnParams & p, float theta_scale, cudaStream_t stream);
 // out[t][h*head_dim + i] = softmax(scale * Q K^T + causal mask) V   (libfalcon.cpp:2285-2366)

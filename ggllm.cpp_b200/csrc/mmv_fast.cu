@@ -224,6 +224,9 @@ static bool launch_type(const WPlanes & W, const FastX & X, float * y, int64_t y
     if (P <= 128 && D1 == 4) launch_cfg<TYPE, 128, 1, D1>(W, X, y, y_stride, epi, stream);       // 64-weight pieces (Q3_K): K = 8192 is 128 pieces
     else if (P > 128 && P <= 160 && D1 == 8 && !getenv("B200_NO_NT160")) launch_cfg<TYPE, 160, 1, D1>(W, X, y, y_stride, epi, stream);   // Falcon-7B: K = 4544 is 142 pieces
     else if (P <= 256) launch_cfg<TYPE, 256, 1, D1>(W, X, y, y_stride, epi, stream);
+    // Falcon-180B (K = 14848: 464 pieces): two 256-thread CTAs at 96 registers instead of one 512-thread CTA at 128 leave a quarter of the
+    // register file to the attention kernels of the other stream, as the K = 8192 shape does
+    else if (P > 256 && P <= 512 && D1 == 8 && X.mode == 0 && !getenv("B200_NO_NT256J2")) launch_cfg<TYPE, 256, 2, D1 / 2>(W, X, y, y_stride, epi, stream);
     else if (P <= 512) launch_cfg<TYPE, 512, 1, D1>(W, X, y, y_stride, epi, stream);
     // Falcon-7B's ffn_down (K = 18176: 568 pieces): 3 pieces per thread of a 192-thread CTA use 568 of 576 slots; the 512 x 2 shape
     // below would leave 45 % of its lanes without a piece (and its 128-register CTAs own the whole register file)

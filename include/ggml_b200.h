@@ -227,6 +227,7 @@ void *        b200_falcon_stream(b200_falcon * f);
 float         b200_falcon_profile_matvec(b200_falcon * f, int reps, int * n_launches, size_t * bytes);
 /* number of kernel launches (graph nodes) issued by the most recent eval on this rank */
 int           b200_falcon_last_launches(const b200_falcon * f);
+int           b200_attention_long_launches(void);     /* diagnostics: launches (eager or captured) of the long-context decode attention kernels so far */
 /* CUDA-event time (ms) of the most recent eval's device work on this rank */
 float         b200_falcon_last_ms(const b200_falcon * f);
 

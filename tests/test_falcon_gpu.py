@@ -96,6 +96,33 @@ def test_float_and_mixed_weight_models_prompt_gemm(gpu, hp, wt, overrides):
         assert d.max() <= 3e-2 * scale and np.median(d) <= 5e-3 * scale, (i, float(d.max()), float(np.median(d)), scale)
 
 
+@pytest.mark.parametrize("hp", [TINY_40B, TINY_7B])
+def test_decode_across_the_long_context_tier(gpu, hp, monkeypatch):
+    """Grouped-query models switch to the one-wave cp.async attention kernels (attention_long.cu) above attention_long_threshold() keys;
+    the decode graphs are captured per tier.  With the threshold moved to 12 keys a tiny model crosses it in the middle of a decode run
+    and of a device-side greedy generation: every eval inside the tolerance contract, generation == host arg-max loop.  (Falcon-7B has
+    one KV head and stays on the short-context kernels: same run, same checks.)"""
+    monkeypatch.setenv("B200_ATTN_LONG_FROM", "12")
+    long0 = gpu.lib().b200_attention_long_launches()
+    tensors = synth_model(hp, po.Q4_K if hp is TINY_40B else po.Q4_0, seed=7)
+    outs, _ = run_model(gpu, hp, tensors, n_ctx=64, n_batch=8, prompt=[11, 100, 101, 102, 103, 104, 105, 106], n_decode=12)
+    assert_mostly_tight([assert_logits_close(got, want, "step %d" % i) for i, (got, want) in enumerate(outs)])
+    f = gpu.Falcon(hp, n_ctx=64, n_batch=8)
+    f.set_tensors(tensors)
+    prompt = np.array([11, 100, 101, 102, 103, 104], np.int32)
+    logits = f.eval(prompt, 0)
+    first = int(np.argmax(logits[0]))
+    want, tok, pos = [], first, len(prompt)
+    for _ in range(16):
+        lg = f.eval(np.array([tok], np.int32), pos)
+        tok = int(np.argmax(lg[0])); want.append(tok); pos += 1
+    f.eval(prompt, 0)                                   # same start state for the device loop
+    got = f.generate_greedy(first, len(prompt), 16)
+    assert list(got) == want
+    assert (gpu.lib().b200_attention_long_launches() > long0) == (hp["n_head_kv"] > 1)      # the long tier was really taken / really left alone
+    f.free()
+
+
 def test_prompt_batch_uses_gemm_path(gpu):
     """n_tokens > b200_mmv_max_n(): activations (already Q8-quantised, bit-exact with the CPU) -> fp16 (d*q), weights
     dequantised bit-exactly then rounded once to fp16, tensor-core GEMM with fp32 accumulation.
