@@ -25,8 +25,10 @@ def main():
         L[name] = v
     ls = list(launches.values())
     if "--all" not in sys.argv:
-        starts = [i for i, L in enumerate(ls) if L["kernel"].startswith("dequant_rows_kernel")]
-        if starts:
+        starts = [i for i, L in enumerate(ls) if "dequant_rows_kernel" in L["kernel"]]
+        if len(starts) >= 2:
+            ls = ls[starts[-2]:starts[-1]]          # the last COMPLETE step (the capture limit may cut the final one short)
+        elif starts:
             ls = ls[starts[-1]:]
     with open(out, "w") as f:
         f.write('"# %s ; launches %d..%d ; cold-cache, serialised (ncu)"\n' % (" ".join(sys.argv), ls[0]["id"], ls[-1]["id"]))
@@ -46,7 +48,7 @@ def main():
         print("| `%s` | %d | %.1f | %.1f %% | %.2f | %.2f |" % (k, a[0], a[1] / 1e3, 100 * a[1] / tot, a[1] / a[0] / 1e3, a[2] / a[0] / 1e6))
     print("total %.1f us over %d launches" % (tot / 1e3, len(ls)))
     if traffic:
-        mv = [L for L in ls if L["kernel"].startswith("mmv_fast_kernel") or L["kernel"].startswith("mmv_kernel")]
+        mv = [L for L in ls if "mmv_fast_kernel" in L["kernel"] or "mmv_kernel" in L["kernel"]]
         b = sum(L.get("dram__bytes_read.sum", 0) + L.get("dram__bytes_write.sum", 0) for L in mv)
         json.dump({"source": "%s (ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum, one decode step of bench.py)" % out,
                    "matvec_launches_per_step": len(mv), "dram_bytes_per_matvec_launch": b / max(1, len(mv)), "dram_bytes_matvecs_per_step": b},
