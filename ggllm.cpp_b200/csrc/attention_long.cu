@@ -204,12 +204,21 @@ __device__ __forceinline__ void attn_long_store(const AttnLongArgs & a, const fl
     }
 }
 
+// fixed order: deterministic
+__device__ __forceinline__ double dsum_total(const double (&d)[AL_WARPS][2][AL_G], int h) {
+    double s = 0.0;
+#pragma unroll
+    for (int w = 0; w < AL_WARPS; w++) s += d[w][0][h] + d[w][1][h];
+    return s;
+}
+
 __global__ void __launch_bounds__(AL_THREADS, 6) attn_long_values_kernel(const AttnLongArgs a) {
     // V rows in flight; once a warp has consumed its rows the same 4 KB hold its partial outputs [head][lane] = dims 2l, 2l+1
     __shared__ __align__(16) float2 vring[AL_WARPS][AL_R * AL_B * 32];
-    __shared__ float sring[AL_WARPS][AL_R][AL_B][AL_G];            // the scores of those rows: [head], copied by lanes 0 .. 15
+    __shared__ float sring[AL_WARPS][AL_R][AL_B][AL_G];            // the scores of those rows: [key of the stage][head]; lane l copies keys l / 16 and l / 16 + 2, head l % 16
+    __shared__ __align__(16) float es[AL_WARPS][AL_B][AL_G];       // e of the stage being consumed, read back as broadcasts
     __shared__ float gmax[AL_G];
-    __shared__ double dsum[AL_WARPS][AL_G];
+    __shared__ double dsum[AL_WARPS][2][AL_G];                     // per warp: the two lanes of a head (keys b = 0, 2 and b = 1, 3 of every stage)
     __shared__ float inv_s[AL_G];
     __shared__ int s_last;
     static_assert(AL_R * AL_B * 32 == AL_G * 32, "a warp's ring doubles as its [AL_G][32] partial-output block");
@@ -223,16 +232,23 @@ __global__ void __launch_bounds__(AL_THREADS, 6) attn_long_values_kernel(const A
     const int n_used = splits_used(T, a.n_splits);                // splits 0 .. n_used - 1 hold keys
     const int j_new = n_past - k_lo;                              // this position's V row is appended by the scores kernel: read after the wait
     const float * vp = a.vc + (size_t) kvh * 64 + 2 * lane + (size_t) k_lo * kv_row;
-    const float * Sr = a.S + (size_t) (h0 + min(lane, G - 1)) * a.n_ctx + k_lo;
+    const int eh = lane & (AL_G - 1), eb = lane >> 4;              // exp work of this lane: head eh of keys eb and eb + 2 of every stage
+    const float * Sr = a.S + (size_t) (h0 + min(eh, G - 1)) * a.n_ctx + k_lo;
     float2 (*vr)[AL_B][32] = reinterpret_cast<float2 (*)[AL_B][32]>(vring[warp]);
     auto issue = [&](int i, bool v, bool s) {
         if (i < nst) {
+            if (v) {
 #pragma unroll
-            for (int b = 0; b < AL_B; b++) {
-                const int jj = warp + AL_WARPS * (AL_B * i + b);
-                if (jj < nk) {
-                    if (v && jj != j_new) cp_async8(&vr[i % AL_R][b][lane], vp + (size_t) jj * kv_row);
-                    if (s && lane < AL_G) cp_async4(&sring[warp][i % AL_R][b][lane], Sr + jj);
+                for (int b = 0; b < AL_B; b++) {
+                    const int jj = warp + AL_WARPS * (AL_B * i + b);
+                    if (jj < nk && jj != j_new) cp_async8(&vr[i % AL_R][b][lane], vp + (size_t) jj * kv_row);
+                }
+            }
+            if (s) {
+#pragma unroll
+                for (int u = 0; u < 2; u++) {
+                    const int b = eb + 2 * u, jj = warp + AL_WARPS * (AL_B * i + b);
+                    if (jj < nk) cp_async4(&sring[warp][i % AL_R][b][eh], Sr + jj);
                 }
             }
         }
@@ -252,8 +268,8 @@ __global__ void __launch_bounds__(AL_THREADS, 6) attn_long_values_kernel(const A
         gmax[tid] = mx;
     }
     __syncthreads();
-    const float gm = gmax[lane & (AL_G - 1)];
-    double lsum = 0.0;                                             // lane h < 16: sum of head h's e over the warp's keys
+    const float gm = gmax[eh];
+    double lsum = 0.0;                                             // sum of head eh's e over this lane's keys
     // O_partial[h][2l..2l+1] = sum over the warp's keys of V[key][2l..2l+1] * e[key][h],  e = table_exp_f16[f16(s - max)] (ggml.c:12427-12440)
     float2 acc[AL_G];
 #pragma unroll
@@ -261,30 +277,42 @@ __global__ void __launch_bounds__(AL_THREADS, 6) attn_long_values_kernel(const A
     for (int i = 0; i < nst; i++) {
         issue(i + AL_R - 1, true, true);
         cp_async_wait<AL_R - 1>();
+        // the stage's 4 x 16 exponentials, two per lane, handed to the whole warp through shared memory (16 shuffles per key before)
+        __syncwarp();                                                         // the previous stage's es reads are done
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+            const int b = eb + 2 * u, jj = warp + AL_WARPS * (AL_B * i + b);
+            float e = 0.f;
+            if (jj < nk && eh < G) { e = exp_f16lut_l(__fsub_rn(sring[warp][i % AL_R][b][eh], gm)); lsum += (double) e; }
+            es[warp][b][eh] = e;
+        }
+        __syncwarp();
 #pragma unroll
         for (int b = 0; b < AL_B; b++) {
             const int jj = warp + AL_WARPS * (AL_B * i + b);
             if (jj < nk) {                                                    // warp-uniform
-                float e = 0.f;
-                if (lane < G) { e = exp_f16lut_l(__fsub_rn(sring[warp][i % AL_R][b][lane], gm)); lsum += (double) e; }
                 const float2 vv = jj == j_new ? vnew : vr[i % AL_R][b][lane];
+                const float4 * e4 = reinterpret_cast<const float4 *>(es[warp][b]);
 #pragma unroll
-                for (int h = 0; h < AL_G; h++) {
-                    const float eh = __shfl_sync(0xffffffffu, e, h);
-                    acc[h].x += vv.x * eh; acc[h].y += vv.y * eh;
+                for (int c = 0; c < AL_G / 4; c++) {
+                    const float4 e = e4[c];
+                    acc[4 * c].x += vv.x * e.x;     acc[4 * c].y += vv.y * e.x;
+                    acc[4 * c + 1].x += vv.x * e.y; acc[4 * c + 1].y += vv.y * e.y;
+                    acc[4 * c + 2].x += vv.x * e.z; acc[4 * c + 2].y += vv.y * e.z;
+                    acc[4 * c + 3].x += vv.x * e.w; acc[4 * c + 3].y += vv.y * e.w;
                 }
             }
         }
     }
     cp_async_wait<0>();
-    if (lane < AL_G) dsum[warp][lane] = lsum;
+    dsum[warp][eb][eh] = lsum;
     __syncwarp();                                                              // every lane is done with the ring: it becomes the warp's partial-output block
     float2 (*oacc)[32] = reinterpret_cast<float2 (*)[32]>(vring[warp]);
 #pragma unroll
     for (int h = 0; h < AL_G; h++) oacc[h][lane] = acc[h];
     __syncthreads();
     if (n_used > 1) {
-        if (tid < G) a.psum[(size_t) (h0 + tid) * AL_MAX_SPLITS + split] = ((dsum[0][tid] + dsum[1][tid]) + dsum[2][tid]) + dsum[3][tid];
+        if (tid < G) a.psum[(size_t) (h0 + tid) * AL_MAX_SPLITS + split] = dsum_total(dsum, tid);
         for (int i = tid; i < AL_G * 32; i += AL_THREADS) {             // fixed warp order: deterministic
             const int h = i / 32, l = i % 32;
             float2 r = vring[0][h * 32 + l];
@@ -294,12 +322,11 @@ __global__ void __launch_bounds__(AL_THREADS, 6) attn_long_values_kernel(const A
         }
     }
     }   // nk > 0
-    static_assert(AL_WARPS == 4, "dsum is summed as four terms");
     if (n_used == 1) {
         // short context: split 0 holds every key; its CTA finishes from its own shared memory -- the same sums in the same order as the
         // general path below (warps, then the single split), no scratch round trip, no fence, no counter
         if (split != 0) { trace_end(a.trace); return; }
-        if (tid < AL_G) inv_s[tid] = (float) (1.0 / (((dsum[0][tid] + dsum[1][tid]) + dsum[2][tid]) + dsum[3][tid]));
+        if (tid < AL_G) inv_s[tid] = (float) (1.0 / dsum_total(dsum, tid));
         __syncthreads();
         const int hA = tid / 8, l0 = 4 * (tid % 8);                          // thread = 8 consecutive outputs of head tid / 8 = lanes l0 .. l0 + 3 of the partial blocks
         float y[8];
