@@ -10,10 +10,12 @@
 //     29 % busy, no memory stall -- a latency-bound instruction stream.  Here a warp step covers AL_B = 4 keys, lane = (key, octet of the
 //     head dimension), the rotated query rows sit in shared memory, and the 16 per-head partials are reduced over the 8 lanes of a key
 //     only (14 shuffles per 4 keys instead of 64): 79 instructions per key
-//   * values: the exp of a key's 16 scores is taken by lanes 0..15 right where the key is consumed (no separate pass, no [key][head] array
-//     in shared memory), so the scores travel through the same ring as the V rows
-// Measured (Falcon-40B Q4_K, tok/s at n_past 8 / 2000 / 8000): attention.cu 210 / 195 / 135, this file 208 / 201 / 147; Falcon-180B
-// geometry at 8000: +10 %.  Falcon-7B (one KV head, five head groups re-reading it) is 8-10 % SLOWER with it at every length, and so are
+//   * values: the exponentials of a ring stage (4 keys x 16 heads) are taken two per lane right where the stage is consumed (no separate
+//     pass over a [key][head] array of the whole split) and handed to the warp through 256 bytes of shared memory (four broadcast
+//     LDS.128 per key instead of 16 shuffles); the scores travel through the same ring as the V rows: 97 instructions per key (119 with
+//     shuffles, profiles/r2_attention_long.md)
+// Measured (Falcon-40B Q4_K, tok/s at n_past 8 / 2000 / 8000): attention.cu 210 / 195 / 135, this file 210 / 204 / 160; Falcon-180B
+// geometry (10 layers) at 8000: 314 -> 377.  Falcon-7B (one KV head, five head groups re-reading it) is 8-10 % SLOWER with it at every length, and so are
 // short contexts in general (more shared memory per CTA of the fixed grid): launch_attention picks this path only for n_head_kv > 1 and
 // more than attention_long_threshold() keys; the decode graphs of engine.cu are captured per tier.
 #include "kernels.h"
