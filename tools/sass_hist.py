@@ -5,7 +5,7 @@ UTCBAR (tcgen05.commit), UBLKCP (TMA bulk copy), IDP.4A (dp4a) and no F2I.U8.F16
 import collections, glob, os, re, subprocess, sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-KEY = ["UTCHMMA", "UTCBAR", "UTMALDG", "UBLKCP", "LDTM", "STTM", "IDP", "MUFU", "F2FP", "HMMA", "SYNCS", "FENCE", "CCTL", "MEMBAR", "F2I"]
+KEY = ["UTCHMMA", "UTCBAR", "UTMALDG", "UBLKCP", "LDGSTS", "LDTM", "STTM", "IDP", "MUFU", "F2FP", "HMUL2", "HMMA", "SYNCS", "FENCE", "CCTL", "MEMBAR", "F2I"]
 print("# SASS opcode histograms of the shipped kernels (cuobjdump -sass ggllm.cpp_b200/csrc/*.o)\n")
 print("Per kernel: total instructions, then the counts of the opcodes that identify the hardware path.\n")
 for obj in sorted(glob.glob(os.path.join(ROOT, "ggllm.cpp_b200", "csrc", "*.o"))):
