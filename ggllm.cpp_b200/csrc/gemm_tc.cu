@@ -457,31 +457,38 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_pair_kernel(const __grid_c
         const int t = threadIdx.x - 64, r = t >> 2, h = t & 3;
         const size_t row = (size_t) min(m0 + r, a.W.M - 1);
         using P = Prod<TYPE>;
-        typename P::Raw raw, raw1;
+        // the raw bytes of K blocks kb .. kb + PF - 1 are in flight per thread (a few registers each): with the activation traffic halved by
+        // the pair, what the MMAs wait for next is these loads (ncu: long-scoreboard stalls of the producers)
+        constexpr int PF = 4;
+        typename P::Raw raw[PF];
         typename P::Ptr pq;
         if constexpr (P::FAST) {
-            const typename P::Ptr p0 = P::ptr(a.W, row, kb0, h);
-            pq = P::ptr(a.W, row, kb0 + (KB > 1 ? 1 : 0), h);
-            raw = P::load(p0, kb0, h); raw1 = P::load(pq, kb0 + (KB > 1 ? 1 : 0), h);
+            pq = P::ptr(a.W, row, kb0, h);
+#pragma unroll
+            for (int i = 0; i < PF; i++) { if (i < KB) raw[i] = P::load(pq, kb0 + i, h); P::next(pq); }
         }
         const int sw = r & 7;
         const uint32_t st0 = smem_u32(sA) + (uint32_t) (r * 128 + ((h ^ sw) << 4)), st1 = smem_u32(sA) + (uint32_t) (r * 128 + (((4 + h) ^ sw) << 4));
         const uint32_t full0 = map_to_rank(smem_u32(a_full), 0);          // the leader's a_full[0] as a shared::cluster address
-        for (int kb = 0; kb < KB; kb++) {
-            const int s = kb % SA;
-            Chunks ch;
-            if constexpr (P::FAST) {
-                ch = P::deq(raw, kb0 + kb, h);
-                raw = raw1;
-                P::next(pq);
-                if (kb + 2 < KB) raw1 = P::load(pq, kb0 + kb + 2, h);
-            } else ch = dequant_generic(a.W, row, (kb0 + kb) * BK, h);
-            if (kb >= SA) mbar_wait(a_empty + s, (uint32_t) ((kb / SA - 1) & 1));
-            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" :: "r"(st0 + (uint32_t) s * A_STAGE), "r"(ch.c[0].x), "r"(ch.c[0].y), "r"(ch.c[0].z), "r"(ch.c[0].w) : "memory");
-            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" :: "r"(st1 + (uint32_t) s * A_STAGE), "r"(ch.c[1].x), "r"(ch.c[1].y), "r"(ch.c[1].z), "r"(ch.c[1].w) : "memory");
-            fence_proxy_async();                                           // generic-proxy stores -> visible to the tensor cores (async proxy)
-            __syncwarp();
-            if (lane == 0) { if (rank == 0) mbar_arrive(a_full + s); else mbar_arrive_cluster(full0 + (uint32_t) s * 8); }   // one arrival per warp on the LEADER's barrier
+        for (int kbase = 0; kbase < KB; kbase += PF) {
+#pragma unroll
+            for (int u = 0; u < PF; u++) {
+                const int kb = kbase + u;
+                if (kb >= KB) break;
+                const int s = kb % SA;
+                Chunks ch;
+                if constexpr (P::FAST) {
+                    ch = P::deq(raw[u], kb0 + kb, h);
+                    if (kb + PF < KB) raw[u] = P::load(pq, kb0 + kb + PF, h);
+                    P::next(pq);
+                } else ch = dequant_generic(a.W, row, (kb0 + kb) * BK, h);
+                if (kb >= SA) mbar_wait(a_empty + s, (uint32_t) ((kb / SA - 1) & 1));
+                asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" :: "r"(st0 + (uint32_t) s * A_STAGE), "r"(ch.c[0].x), "r"(ch.c[0].y), "r"(ch.c[0].z), "r"(ch.c[0].w) : "memory");
+                asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" :: "r"(st1 + (uint32_t) s * A_STAGE), "r"(ch.c[1].x), "r"(ch.c[1].y), "r"(ch.c[1].z), "r"(ch.c[1].w) : "memory");
+                fence_proxy_async();                                           // generic-proxy stores -> visible to the tensor cores (async proxy)
+                __syncwarp();
+                if (lane == 0) { if (rank == 0) mbar_arrive(a_full + s); else mbar_arrive_cluster(full0 + (uint32_t) s * 8); }   // one arrival per warp on the LEADER's barrier
+            }
         }
         mbar_wait(acc_full, 0);
         tc_fence_after();
