@@ -593,7 +593,10 @@ static void enqueue_decode_fused(b200_falcon * f, int n_past, float theta_scale,
     else B200_NCCL_CHECK(nccl().Recv(f->inp, (size_t) E, ncclFloat, f->hp.rank - 1, f->comm, sa));
     const MmvEpilogue none = { EPI_NONE, nullptr, nullptr, nullptr, nullptr };
     // ffn_up applies GELU and, chunk by chunk as CTAs finish, quantises its output row for ffn_down (no INIT pass, no prologue work there)
-    const MmvEpilogue gelu = { EPI_GELU, nullptr, nullptr, &xup, f->q_ctr };
+    MmvEpilogue gelu = { EPI_GELU, nullptr, nullptr, &xup, f->q_ctr };
+    // ffn_up reads the LayerNorm's output and wo the attention's: neither reads what the mat-vec in front of it writes (MmvEpilogue::late_wait)
+    MmvEpilogue wo_epi = none;
+    gelu.late_wait = 1; wo_epi.late_wait = 1;
     // debugging aid for timing experiments only (results are wrong when anything is skipped): B200_DBG_SKIP=ln,qkv,attn,up,down,wo
     const char * dbg = getenv("B200_DBG_SKIP");
     auto skip = [&](const char * what) { return dbg && strstr(dbg, what) != nullptr; };
@@ -631,7 +634,7 @@ static void enqueue_decode_fused(b200_falcon * f, int n_past, float theta_scale,
         const bool wo_first = mmv_fast_fills_sm(L.down);
         if (!wo_first && !skip("down")) launch_mmv(L.down, xup, f->dn, E, none, sa);                            // :2394
         B200_CUDA_CHECK(cudaStreamWaitEvent(sa, f->e_join, 0));
-        if (!skip("wo")) launch_mmv(L.wo, xatt, f->ao, E, none, sa);                                          // :2370
+        if (!skip("wo")) launch_mmv(L.wo, xatt, f->ao, E, wo_epi, sa);                                        // :2370
         if (wo_first && !skip("down")) launch_mmv(L.down, xup, f->dn, E, none, sa);
         f->launches += 7;
     }

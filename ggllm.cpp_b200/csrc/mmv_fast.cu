@@ -54,7 +54,7 @@ __device__ __forceinline__ void mmv_body(const WPlanes & W, const FastX & X, flo
     if (pf.dist > 0 && tid == 0) l2_prefetch_rows(pf, min(row0 + D, row1), min(row0 + D + pf.dist, row1));
 
     // everything above touched only weights; the activation row is produced by the previous kernel(s) of the stream
-    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (!epi.late_wait) asm volatile("griddepcontrol.wait;" ::: "memory");
     typename T::XR xr[J];
     if (MODE == 0) {
         if (tid == 0) {
@@ -143,6 +143,7 @@ __device__ __forceinline__ void mmv_body(const WPlanes & W, const FastX & X, flo
             y[(size_t) n * y_stride + row] = v;
         },
         [&]() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }, pf);
+    if (epi.late_wait) asm volatile("griddepcontrol.wait;" ::: "memory");      // see MmvEpilogue::late_wait
     if (epi.qctr) {
         // Quantise the finished output row for the next mat-mul, 256 values at a time.  A chunk's rows belong to up to
         // three CTAs; each adds its row count to the chunk's counter once its own rows are stored and fenced, and the CTA
@@ -240,7 +241,7 @@ static bool launch_type(const WPlanes & W, const FastX & X, float * y, int64_t y
 // returns false if the shape / type is not covered (the caller then uses the generic ring kernel of mmv.cu)
 bool launch_mmv_fast_x(const WPlanes & W, const FastX & X, float * y, int64_t y_stride, MmvEpilogue e, cudaStream_t stream) {
     const char * nm = W.M > 40000 ? "mmv_lmhead" : W.K > 16384 ? "mmv_down" : W.M > 16384 ? "mmv_up" : W.M > 8192 ? "mmv_qkv" : "mmv_wo";
-    Epi epi = { e.kind, e.r1, e.r2, b200_trace_slot(nm), ActQ{}, nullptr };
+    Epi epi = { e.kind, e.r1, e.r2, b200_trace_slot(nm), ActQ{}, nullptr, getenv("B200_NO_LATE_WAIT") ? 0 : e.late_wait };
     if (e.qout && e.qctr) {
         B200_ASSERT(X.N == 1 && W.M % 256 == 0 && e.qout->K == W.M && (e.qout->type == T_Q8_K || e.qout->type == T_Q8_0));
         epi.qA = *e.qout; epi.qctr = e.qctr;

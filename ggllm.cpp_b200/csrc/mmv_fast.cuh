@@ -3,7 +3,7 @@
 #include "kernels.h"
 #include "actquant.cuh"
 
-struct Epi { int kind; const float * r1; const float * r2; unsigned long long * trace; ActQ qA; unsigned * qctr; };
+struct Epi { int kind; const float * r1; const float * r2; unsigned long long * trace; ActQ qA; unsigned * qctr; int late_wait; };
 
 // Where the activation row comes from (FastX, kernels.h):
 //   mode 0: already quantised (ActQ, written by quantize_act / layernorm_q)
