@@ -60,29 +60,39 @@ __device__ __forceinline__ void split_range(int T, int ns, int split, int & k_lo
 // ring stages warp `warp` needs for its keys jj = warp + AL_WARPS * (AL_B * stage + b) < nk
 __device__ __forceinline__ int warp_stages(int nk, int warp) { return nk > warp ? (nk - warp + AL_WARPS * AL_B - 1) / (AL_WARPS * AL_B) : 0; }
 
-// 16 per-lane values -> summed over the 8 lanes of an aligned group; lane o of the group ends up with values 2o and 2o + 1
-__device__ __forceinline__ void butterfly16x8(const float (&v)[16], int lane, float & r0, float & r1) {
-    float w8[8], w4[4];
-    const bool b2 = lane & 4, b1 = lane & 2, b0 = lane & 1;
-#pragma unroll
-    for (int i = 0; i < 8; i++) { const float keep = b2 ? v[8 + i] : v[i], send = b2 ? v[i] : v[8 + i]; w8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4); }
-#pragma unroll
-    for (int i = 0; i < 4; i++) { const float keep = b1 ? w8[4 + i] : w8[i], send = b1 ? w8[i] : w8[4 + i]; w4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2); }
-    const float k0 = b0 ? w4[2] : w4[0], s0 = b0 ? w4[0] : w4[2], k1 = b0 ? w4[3] : w4[1], s1 = b0 ? w4[1] : w4[3];
-    r0 = k0 + __shfl_xor_sync(0xffffffffu, s0, 1);
-    r1 = k1 + __shfl_xor_sync(0xffffffffu, s1, 1);
+// ---- tensor-core helpers.  The G <= 16 query heads of a KV head are exactly the M = 16 of a warp-level mma: scores = Q[16 x 64] K^T and
+// O += E[16 x keys] V run on the tensor cores (legacy mma.sync, the right size for a 16-row problem), which takes the instruction count
+// per key from 79 + 97 (CUDA cores, above) to ~15 + ~25.  fp32 operands are split into two fp16 terms (hi = fp16(x), lo = fp16(x - hi):
+// 22 significant bits); products of fp16 pairs are exact in the fp32 accumulator, the dropped lo x lo term is 2^-22 of the product -- the
+// fp32 dot product's own rounding level.  e = table_exp_f16[...] IS an fp16 value: the A operand of the second product is exact.
+__device__ __forceinline__ void split_h2(float x0, float x1, uint32_t & hi, uint32_t & lo) {
+    const __half2 h = __floats2half2_rn(x0, x1);
+    const float2 hf = __half22float2(h);
+    const __half2 l = __floats2half2_rn(__fsub_rn(x0, hf.x), __fsub_rn(x1, hf.y));
+    hi = *reinterpret_cast<const uint32_t *>(&h); lo = *reinterpret_cast<const uint32_t *>(&l);
 }
+// D[16 x 8] += A[16 x 16] B[16 x 8]   (fp16 operands, fp32 accumulate); fragment layouts: PTX ISA "mma.m16n8k16", gid = lane / 4, tig = lane % 4
+__device__ __forceinline__ void mma_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// D[16 x 8] += A[16 x 8] B[8 x 8]
+__device__ __forceinline__ void mma_1688(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t b0) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5}, {%6}, {%0, %1, %2, %3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a0), "r"(a1), "r"(b0));
+}
+#define AL_KB 8                          // keys per warp and ring stage = the N of one mma
+#define AL_KR 2                          // ring stages per warp (double buffer)
+#define AL_KS 72                         // floats per K row in the ring: 64 + 8 keeps the B-fragment LDS.64s of a half-warp on distinct banks
+#define AL_VS 68                         // floats per V row in the ring: 64 + 4 does the same for the LDS.32s of the second product
+// 8-key blocks of a split go round-robin to the warps: block b = stage * AL_WARPS + warp
+__device__ __forceinline__ int warp_blocks(int nk, int warp) { const int nb = (nk + AL_KB - 1) / AL_KB; return nb > warp ? (nb - warp + AL_WARPS - 1) / AL_WARPS : 0; }
 
-// Scores.  ncu on the first version (lane = 2 dims of ONE key, 16 heads reduced over the 32 lanes per key: 151 instructions per key, one
-// warp per scheduler, issue slot 29 % busy, no memory stall to speak of) showed a latency-bound instruction stream, not a memory-bound one.
-// Here a warp step covers AL_B = 4 keys: lane = (key kb = lane / 8, octet oc = lane % 8) holds 8 dims of its key, the rotated query rows sit
-// in shared memory ([head][64], read as broadcasts), 128 independent FMAs per lane and step, and the 16 per-head partials are reduced over
-// the 8 lanes of a key only (14 shuffles per 4 keys instead of 64): ~60 instructions per key.
-__global__ void __launch_bounds__(AL_THREADS, 6) attn_long_scores_kernel(const AttnLongArgs a) {
+__global__ void __launch_bounds__(AL_THREADS, 4) attn_long_scores_kernel(const AttnLongArgs a) {
     __shared__ float wmax[AL_WARPS][AL_G];
-    __shared__ __align__(16) float ring[AL_WARPS][AL_R][AL_B][64];         // 16 KB: K rows in flight (a lane reads back the 32 bytes it copied)
+    __shared__ __align__(16) float ring[AL_WARPS][AL_KR][AL_KB][AL_KS];    // 18 KB: K rows in flight
     __shared__ __align__(16) float qs[AL_G][64];                           // this position's query rows, rotated
-    __shared__ __align__(16) float knew_s[64];                             // this position's key row, rotated (not in the cache yet)
+    __shared__ __align__(16) float knew_s[AL_KS];                          // this position's key row, rotated (not in the cache yet)
     trace_begin(a.trace);
     const int split = blockIdx.x, kvh = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int h0 = kvh * a.G + blockIdx.z * AL_G, G = min(AL_G, a.G - (int) blockIdx.z * AL_G);      // this CTA's query heads: h0 .. h0 + G - 1
@@ -102,23 +112,25 @@ __global__ void __launch_bounds__(AL_THREADS, 6) attn_long_scores_kernel(const A
     const float * ksrc = a.qkv + (size_t) (a.n_head + kvh) * 64;
     const float ka = ksrc[ri], kb_ = ksrc[ri + 32];
     if (k_lo >= k_hi) { trace_end(a.trace); return; }            // a split without keys (short context): nothing to score, nobody reads its pmax
-    const int nk = k_hi - k_lo, nst = warp_stages(nk, warp);
+    const int nk = k_hi - k_lo, nst = warp_blocks(nk, warp);
     const int j_new = a.fuse_rope ? n_past - k_lo : -1;           // this position's key is not in the cache yet (another CTA may be writing it right now)
     const size_t kv_row = (size_t) a.n_head_kv * 64;
-    const int kb = lane >> 3, oc = lane & 7;
-    const float * kp = a.kc + (size_t) kvh * 64 + 8 * oc + (size_t) k_lo * kv_row;
-    auto issue = [&](int i) {
+    const int gid = lane >> 2, tig = lane & 3;
+    const float * kp = a.kc + (size_t) kvh * 64 + 16 * tig + (size_t) k_lo * kv_row;
+    auto issue = [&](int i) {                                     // lane copies 64 bytes: dims 16 tig .. 16 tig + 15 of key gid of the block
         if (i < nst) {
-            const int jj = warp + AL_WARPS * (AL_B * i + kb);
+            const int jj = (i * AL_WARPS + warp) * AL_KB + gid;
             if (jj < nk && jj != j_new) {
-                float * dst = &ring[warp][i % AL_R][kb][8 * oc];
-                cp_async16(dst, kp + (size_t) jj * kv_row); cp_async16(dst + 4, kp + (size_t) jj * kv_row + 4);
+                float * dst = &ring[warp][i % AL_KR][gid][16 * tig];
+                const float * src = kp + (size_t) jj * kv_row;
+#pragma unroll
+                for (int c = 0; c < 4; c++) cp_async16(dst + 4 * c, src + 4 * c);
             }
         }
         cp_async_commit();
     };
 #pragma unroll
-    for (int i = 0; i < AL_R - 1; i++) issue(i);                 // the first rows travel while RoPE runs
+    for (int i = 0; i < AL_KR - 1; i++) issue(i);                // the first rows travel while RoPE runs
     // Fused RoPE + KV append (libfalcon.cpp:2229-2281), arithmetic of rope_pair (ops.cu): theta = n_past * theta_scale^i by repeated fp32 products
     {
         float c = 1.f, sn = 0.f;
@@ -155,33 +167,47 @@ __global__ void __launch_bounds__(AL_THREADS, 6) attn_long_scores_kernel(const A
         }
     }
     __syncthreads();
-    const float scale = 1.0f / sqrtf(64.0f);
-    float lmax0 = -INFINITY, lmax1 = -INFINITY;                   // heads 2 oc, 2 oc + 1 over this lane's keys
-    const float4 * q4 = reinterpret_cast<const float4 *>(&qs[0][8 * oc]);
-    for (int i = 0; i < nst; i++) {
-        issue(i + AL_R - 1);                                      // refills the stage consumed in the previous iteration
-        cp_async_wait<AL_R - 1>();                                // stage i has landed (a lane reads only what it copied itself)
-        const int jj = warp + AL_WARPS * (AL_B * i + kb);
-        const float * src = jj == j_new ? &knew_s[8 * oc] : &ring[warp][i % AL_R][kb][8 * oc];
-        float4 k0 = *reinterpret_cast<const float4 *>(src), k1 = *reinterpret_cast<const float4 *>(src + 4);
-        if (jj >= nk) { k0 = make_float4(0.f, 0.f, 0.f, 0.f); k1 = k0; }
-        float part[AL_G];
+    // A fragments of Q (16 heads x 64 dims = 4 k-steps), hi and lo terms: rows gid / gid + 8, columns 16 t + 2 tig (+1) and + 8 (+9)
+    uint32_t ah[4][4], al[4][4];
 #pragma unroll
-        for (int h = 0; h < AL_G; h++) {
-            const float4 qa4 = q4[h * 16], qb4 = q4[h * 16 + 1];
-            part[h] = k0.x * qa4.x + k0.y * qa4.y + k0.z * qa4.z + k0.w * qa4.w + k1.x * qb4.x + k1.y * qb4.y + k1.z * qb4.z + k1.w * qb4.w;
+    for (int t = 0; t < 4; t++)
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            const float2 q2 = *reinterpret_cast<const float2 *>(&qs[gid + 8 * (r & 1)][16 * t + 2 * tig + 8 * (r >> 1)]);
+            split_h2(q2.x, q2.y, ah[t][r], al[t][r]);
         }
-        float s0, s1; butterfly16x8(part, lane, s0, s1);
-        s0 = __fmul_rn(s0, scale); s1 = __fmul_rn(s1, scale);   // libfalcon.cpp:2313-2317
-        if (jj < nk) {
-            if (2 * oc < G)     { a.S[(size_t) (h0 + 2 * oc) * a.n_ctx + k_lo + jj] = s0; lmax0 = fmaxf(lmax0, s0); }
-            if (2 * oc + 1 < G) { a.S[(size_t) (h0 + 2 * oc + 1) * a.n_ctx + k_lo + jj] = s1; lmax1 = fmaxf(lmax1, s1); }
+    const float scale = 1.0f / sqrtf(64.0f);
+    float lmax0 = -INFINITY, lmax1 = -INFINITY;                   // heads gid, gid + 8 over this lane's keys
+    for (int i = 0; i < nst; i++) {
+        issue(i + AL_KR - 1);                                     // refills the stage consumed in the previous iteration
+        cp_async_wait<AL_KR - 1>();
+        __syncwarp();                                             // the four lanes of a key copied a quarter of its row each
+        const int jj0 = (i * AL_WARPS + warp) * AL_KB;
+        const float * krow = jj0 + gid == j_new ? knew_s : &ring[warp][i % AL_KR][gid][0];     // B column gid = key jj0 + gid
+        float c[4] = { 0.f, 0.f, 0.f, 0.f };
+#pragma unroll
+        for (int t = 0; t < 4; t++) {
+            const float2 p0 = *reinterpret_cast<const float2 *>(krow + 16 * t + 2 * tig), p1 = *reinterpret_cast<const float2 *>(krow + 16 * t + 2 * tig + 8);
+            uint32_t bh0, bl0, bh1, bl1;
+            split_h2(p0.x, p0.y, bh0, bl0); split_h2(p1.x, p1.y, bh1, bl1);
+            mma_16816(c, ah[t], bh0, bh1); mma_16816(c, ah[t], bl0, bl1); mma_16816(c, al[t], bh0, bh1);
         }
+        // c0, c1: head gid, keys jj0 + 2 tig, + 1;  c2, c3: head gid + 8.  A key past the split's end had an unwritten ring row: its column is not stored
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+            const int jj = jj0 + 2 * tig + u;
+            if (jj < nk) {
+                const float s0 = __fmul_rn(c[u], scale), s1 = __fmul_rn(c[2 + u], scale);   // libfalcon.cpp:2313-2317
+                if (gid < G)     { a.S[(size_t) (h0 + gid) * a.n_ctx + k_lo + jj] = s0; lmax0 = fmaxf(lmax0, s0); }
+                if (gid + 8 < G) { a.S[(size_t) (h0 + gid + 8) * a.n_ctx + k_lo + jj] = s1; lmax1 = fmaxf(lmax1, s1); }
+            }
+        }
+        __syncwarp();                                             // all reads of this stage are done before the next iteration refills it
     }
     cp_async_wait<0>();
-    lmax0 = fmaxf(lmax0, __shfl_xor_sync(0xffffffffu, lmax0, 8)); lmax0 = fmaxf(lmax0, __shfl_xor_sync(0xffffffffu, lmax0, 16));
-    lmax1 = fmaxf(lmax1, __shfl_xor_sync(0xffffffffu, lmax1, 8)); lmax1 = fmaxf(lmax1, __shfl_xor_sync(0xffffffffu, lmax1, 16));
-    if (lane < 8) { wmax[warp][2 * lane] = lmax0; wmax[warp][2 * lane + 1] = lmax1; }
+    lmax0 = fmaxf(lmax0, __shfl_xor_sync(0xffffffffu, lmax0, 1)); lmax0 = fmaxf(lmax0, __shfl_xor_sync(0xffffffffu, lmax0, 2));
+    lmax1 = fmaxf(lmax1, __shfl_xor_sync(0xffffffffu, lmax1, 1)); lmax1 = fmaxf(lmax1, __shfl_xor_sync(0xffffffffu, lmax1, 2));
+    if (tig == 0) { wmax[warp][gid] = lmax0; wmax[warp][gid + 8] = lmax1; }
     __syncthreads();
     if (tid < G) {
         float mx = wmax[0][tid];
@@ -214,104 +240,112 @@ __device__ __forceinline__ double dsum_total(const double (&d)[AL_WARPS][2][AL_G
     return s;
 }
 
-__global__ void __launch_bounds__(AL_THREADS, 6) attn_long_values_kernel(const AttnLongArgs a) {
-    // V rows in flight; once a warp has consumed its rows the same 4 KB hold its partial outputs [head][lane] = dims 2l, 2l+1
-    __shared__ __align__(16) float2 vring[AL_WARPS][AL_R * AL_B * 32];
-    __shared__ float sring[AL_WARPS][AL_R][AL_B][AL_G];            // the scores of those rows: [key of the stage][head]; lane l copies keys l / 16 and l / 16 + 2, head l % 16
-    __shared__ __align__(16) float es[AL_WARPS][AL_B][AL_G];       // e of the stage being consumed, read back as broadcasts
+__global__ void __launch_bounds__(AL_THREADS, 4) attn_long_values_kernel(const AttnLongArgs a) {
+    // V rows in flight; once a warp has consumed its rows the same memory holds its partial outputs [head][64]
+    __shared__ __align__(16) float2 vring[AL_WARPS][AL_KR * AL_KB * AL_VS / 2];
+    __shared__ float sring[AL_WARPS][AL_KR][32][4];                // the scores of those rows, lane-private: (gid, 2 tig), (gid, 2 tig + 1), (gid + 8, ..)
     __shared__ float gmax[AL_G];
-    __shared__ double dsum[AL_WARPS][2][AL_G];                     // per warp: the two lanes of a head (keys b = 0, 2 and b = 1, 3 of every stage)
+    __shared__ double dsum[AL_WARPS][2][AL_G];
     __shared__ float inv_s[AL_G];
     __shared__ int s_last;
-    static_assert(AL_R * AL_B * 32 == AL_G * 32, "a warp's ring doubles as its [AL_G][32] partial-output block");
+    static_assert(AL_KR * AL_KB * AL_VS / 2 >= AL_G * 32, "a warp's ring doubles as its [AL_G][64] partial-output block");
     const int split = blockIdx.x, kvh = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int h0 = kvh * a.G + blockIdx.z * AL_G, G = min(AL_G, a.G - (int) blockIdx.z * AL_G);
     const int n_past = a.n_past_dev ? *a.n_past_dev : a.n_past, T = n_past + 1;
     int k_lo, k_hi; split_range(T, a.n_splits, split, k_lo, k_hi);
-    const int nk = k_hi - k_lo, nst = warp_stages(nk, warp);
+    const int nk = k_hi - k_lo, nst = warp_blocks(nk, warp);
     const size_t kv_row = (size_t) a.n_head_kv * 64;
     trace_begin(a.trace);
     const int n_used = splits_used(T, a.n_splits);                // splits 0 .. n_used - 1 hold keys
     const int j_new = n_past - k_lo;                              // this position's V row is appended by the scores kernel: read after the wait
-    const float * vp = a.vc + (size_t) kvh * 64 + 2 * lane + (size_t) k_lo * kv_row;
-    const int eh = lane & (AL_G - 1), eb = lane >> 4;              // exp work of this lane: head eh of keys eb and eb + 2 of every stage
-    const float * Sr = a.S + (size_t) (h0 + min(eh, G - 1)) * a.n_ctx + k_lo;
-    float2 (*vr)[AL_B][32] = reinterpret_cast<float2 (*)[AL_B][32]>(vring[warp]);
+    const int gid = lane >> 2, tig = lane & 3;
+    const float * vp = a.vc + (size_t) kvh * 64 + 16 * tig + (size_t) k_lo * kv_row;
+    const float * S0 = a.S + (size_t) (h0 + min(gid, G - 1)) * a.n_ctx + k_lo, * S1 = a.S + (size_t) (h0 + min(gid + 8, G - 1)) * a.n_ctx + k_lo;
+    float (*vr)[AL_KB][AL_VS] = reinterpret_cast<float (*)[AL_KB][AL_VS]>(vring[warp]);
     auto issue = [&](int i, bool v, bool s) {
         if (i < nst) {
-            if (v) {
+            const int jj0 = (i * AL_WARPS + warp) * AL_KB;
+            if (v) {                                              // lane copies 64 bytes: dims 16 tig .. + 15 of key gid; rows past the end are zeroed (0 x garbage could be NaN)
+                const int jj = jj0 + gid;
+                float * dst = &vr[i % AL_KR][gid][16 * tig];
+                if (jj < nk && jj != j_new) {
+                    const float * src = vp + (size_t) jj * kv_row;
 #pragma unroll
-                for (int b = 0; b < AL_B; b++) {
-                    const int jj = warp + AL_WARPS * (AL_B * i + b);
-                    if (jj < nk && jj != j_new) cp_async8(&vr[i % AL_R][b][lane], vp + (size_t) jj * kv_row);
+                    for (int c = 0; c < 4; c++) cp_async16(dst + 4 * c, src + 4 * c);
+                } else if (jj >= nk) {
+#pragma unroll
+                    for (int c = 0; c < 4; c++) *reinterpret_cast<float4 *>(dst + 4 * c) = make_float4(0.f, 0.f, 0.f, 0.f);
                 }
             }
             if (s) {
 #pragma unroll
                 for (int u = 0; u < 2; u++) {
-                    const int b = eb + 2 * u, jj = warp + AL_WARPS * (AL_B * i + b);
-                    if (jj < nk) cp_async4(&sring[warp][i % AL_R][b][eh], Sr + jj);
+                    const int jj = jj0 + 2 * tig + u;
+                    if (jj < nk) { cp_async4(&sring[warp][i % AL_KR][lane][u], S0 + jj); cp_async4(&sring[warp][i % AL_KR][lane][2 + u], S1 + jj); }
                 }
             }
         }
         cp_async_commit();
     };
-    // V rows of EARLIER positions have been in the cache since their own decode steps: the first stages travel while the scores kernel still runs
+    // V rows of EARLIER positions have been in the cache since their own decode steps: the first stage travels while the scores kernel still runs
 #pragma unroll
-    for (int i = 0; i < AL_R - 1; i++) issue(i, true, false);
+    for (int i = 0; i < AL_KR - 1; i++) issue(i, true, false);
     asm volatile("griddepcontrol.wait;" ::: "memory");            // launched programmatically behind the scores kernel: its S / pmax / KV append are complete from here on
     if (nk > 0) {
 #pragma unroll
-    for (int i = 0; i < AL_R - 1; i++) issue(i, false, true);     // their scores, together with the split maxima: one round trip
-    const float2 vnew = j_new >= 0 && j_new < nk ? *reinterpret_cast<const float2 *>(vp + (size_t) j_new * kv_row) : make_float2(0.f, 0.f);
+    for (int i = 0; i < AL_KR - 1; i++) issue(i, false, true);    // their scores, together with the split maxima: one round trip
+    const bool has_new = j_new >= 0 && j_new < nk;
+    const float2 vnew = has_new ? *reinterpret_cast<const float2 *>(a.vc + (size_t) kvh * 64 + 2 * lane + (size_t) (k_lo + j_new) * kv_row) : make_float2(0.f, 0.f);
     if (tid < AL_G) {
         float mx = -INFINITY;
         if (tid < G) for (int s = 0; s < n_used; s++) mx = fmaxf(mx, a.pmax[(size_t) (h0 + tid) * AL_MAX_SPLITS + s]);
         gmax[tid] = mx;
     }
     __syncthreads();
-    const float gm = gmax[eh];
-    double lsum = 0.0;                                             // sum of head eh's e over this lane's keys
-    // O_partial[h][2l..2l+1] = sum over the warp's keys of V[key][2l..2l+1] * e[key][h],  e = table_exp_f16[f16(s - max)] (ggml.c:12427-12440)
-    float2 acc[AL_G];
+    const float gm0 = gmax[gid], gm1 = gmax[gid + 8];
+    double lsum0 = 0.0, lsum1 = 0.0;                               // heads gid, gid + 8: sum of e over this lane's keys
+    // O[16 heads x 64 dims] += E[16 x 8 keys] V[8 x 64] per stage: 8 n-tiles of 8 dims, accumulators c0, c1 = (gid, 8 nt + 2 tig, + 1), c2, c3 = (gid + 8, ..)
+    float acc[8][4];
 #pragma unroll
-    for (int h = 0; h < AL_G; h++) acc[h] = make_float2(0.f, 0.f);
+    for (int nt = 0; nt < 8; nt++) { acc[nt][0] = 0.f; acc[nt][1] = 0.f; acc[nt][2] = 0.f; acc[nt][3] = 0.f; }
     for (int i = 0; i < nst; i++) {
-        issue(i + AL_R - 1, true, true);
-        cp_async_wait<AL_R - 1>();
-        // the stage's 4 x 16 exponentials, two per lane, handed to the whole warp through shared memory (16 shuffles per key before)
-        __syncwarp();                                                         // the previous stage's es reads are done
+        issue(i + AL_KR - 1, true, true);
+        cp_async_wait<AL_KR - 1>();
+        __syncwarp();
+        const int jj0 = (i * AL_WARPS + warp) * AL_KB, st = i % AL_KR;
+        if (has_new && j_new >= jj0 && j_new < jj0 + AL_KB) {     // this position's V row goes into its ring row now
+            *reinterpret_cast<float2 *>(&vr[st][j_new - jj0][2 * lane]) = vnew;
+            __syncwarp();
+        }
+        // e = table_exp_f16[f16(s - max)] (ggml.c:12427-12440), produced directly in A-fragment layout: a0 = (gid; keys 2 tig, + 1), a1 = (gid + 8; ..)
+        float e[4];
 #pragma unroll
         for (int u = 0; u < 2; u++) {
-            const int b = eb + 2 * u, jj = warp + AL_WARPS * (AL_B * i + b);
-            float e = 0.f;
-            if (jj < nk && eh < G) { e = exp_f16lut_l(__fsub_rn(sring[warp][i % AL_R][b][eh], gm)); lsum += (double) e; }
-            es[warp][b][eh] = e;
+            const bool live = jj0 + 2 * tig + u < nk;
+            e[u]     = live && gid < G     ? exp_f16lut_l(__fsub_rn(sring[warp][st][lane][u], gm0)) : 0.f;
+            e[2 + u] = live && gid + 8 < G ? exp_f16lut_l(__fsub_rn(sring[warp][st][lane][2 + u], gm1)) : 0.f;
         }
-        __syncwarp();
+        lsum0 += (double) e[0] + (double) e[1]; lsum1 += (double) e[2] + (double) e[3];
+        const __half2 e0h = __floats2half2_rn(e[0], e[1]), e1h = __floats2half2_rn(e[2], e[3]);       // exact: e is an fp16 value
+        const uint32_t a0 = *reinterpret_cast<const uint32_t *>(&e0h), a1 = *reinterpret_cast<const uint32_t *>(&e1h);
 #pragma unroll
-        for (int b = 0; b < AL_B; b++) {
-            const int jj = warp + AL_WARPS * (AL_B * i + b);
-            if (jj < nk) {                                                    // warp-uniform
-                const float2 vv = jj == j_new ? vnew : vr[i % AL_R][b][lane];
-                const float4 * e4 = reinterpret_cast<const float4 *>(es[warp][b]);
-#pragma unroll
-                for (int c = 0; c < AL_G / 4; c++) {
-                    const float4 e = e4[c];
-                    acc[4 * c].x += vv.x * e.x;     acc[4 * c].y += vv.y * e.x;
-                    acc[4 * c + 1].x += vv.x * e.y; acc[4 * c + 1].y += vv.y * e.y;
-                    acc[4 * c + 2].x += vv.x * e.z; acc[4 * c + 2].y += vv.y * e.z;
-                    acc[4 * c + 3].x += vv.x * e.w; acc[4 * c + 3].y += vv.y * e.w;
-                }
-            }
+        for (int nt = 0; nt < 8; nt++) {                                         // B column gid = dim 8 nt + gid, rows = keys 2 tig, 2 tig + 1
+            uint32_t bh, bl;
+            split_h2(vr[st][2 * tig][8 * nt + gid], vr[st][2 * tig + 1][8 * nt + gid], bh, bl);
+            mma_1688(acc[nt], a0, a1, bh); mma_1688(acc[nt], a0, a1, bl);
         }
+        __syncwarp();                                             // all reads of this stage are done before the next iteration refills it
     }
     cp_async_wait<0>();
-    dsum[warp][eb][eh] = lsum;
-    __syncwarp();                                                              // every lane is done with the ring: it becomes the warp's partial-output block
-    float2 (*oacc)[32] = reinterpret_cast<float2 (*)[32]>(vring[warp]);
+    lsum0 += __shfl_xor_sync(0xffffffffu, lsum0, 1); lsum0 += __shfl_xor_sync(0xffffffffu, lsum0, 2);
+    lsum1 += __shfl_xor_sync(0xffffffffu, lsum1, 1); lsum1 += __shfl_xor_sync(0xffffffffu, lsum1, 2);
+    if (tig == 0) { dsum[warp][0][gid] = lsum0; dsum[warp][0][gid + 8] = lsum1; dsum[warp][1][gid] = 0.0; dsum[warp][1][gid + 8] = 0.0; }
+    __syncwarp();                                                              // every lane is done with the ring: it becomes the warp's partial-output block [head][64]
 #pragma unroll
-    for (int h = 0; h < AL_G; h++) oacc[h][lane] = acc[h];
+    for (int nt = 0; nt < 8; nt++) {
+        vring[warp][gid * 32 + 4 * nt + tig] = make_float2(acc[nt][0], acc[nt][1]);
+        vring[warp][(gid + 8) * 32 + 4 * nt + tig] = make_float2(acc[nt][2], acc[nt][3]);
+    }
     __syncthreads();
     if (n_used > 1) {
         if (tid < G) a.psum[(size_t) (h0 + tid) * AL_MAX_SPLITS + split] = dsum_total(dsum, tid);

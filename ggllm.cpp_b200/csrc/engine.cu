@@ -594,9 +594,12 @@ static void enqueue_decode_fused(b200_falcon * f, int n_past, float theta_scale,
     const MmvEpilogue none = { EPI_NONE, nullptr, nullptr, nullptr, nullptr };
     // ffn_up applies GELU and, chunk by chunk as CTAs finish, quantises its output row for ffn_down (no INIT pass, no prologue work there)
     MmvEpilogue gelu = { EPI_GELU, nullptr, nullptr, &xup, f->q_ctr };
-    // ffn_up reads the LayerNorm's output and wo the attention's: neither reads what the mat-vec in front of it writes (MmvEpilogue::late_wait)
+    // ffn_up reads the LayerNorm's output, which was complete and flushed before qkv's rows started: nothing it reads comes from the kernel in
+    // front of it (MmvEpilogue::late_wait).  wo does NOT get it although it reads nothing of ffn_down's either: its input comes from the
+    // attention kernels of the OTHER stream, and inside the captured graph that join may be a programmatic edge too -- only
+    // griddepcontrol.wait then guarantees that their stores are visible (one wrong eval in ~12 runs of a tiny model with a late wait there).
     MmvEpilogue wo_epi = none;
-    gelu.late_wait = 1; wo_epi.late_wait = 1;
+    gelu.late_wait = 1;
     // debugging aid for timing experiments only (results are wrong when anything is skipped): B200_DBG_SKIP=ln,qkv,attn,up,down,wo
     const char * dbg = getenv("B200_DBG_SKIP");
     auto skip = [&](const char * what) { return dbg && strstr(dbg, what) != nullptr; };

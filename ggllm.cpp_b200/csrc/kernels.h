@@ -23,10 +23,10 @@ struct MmvEpilogue { int kind; const float * r1; const float * r2;         // AD
     // optional (fast kernel, N == 1, M % 256 == 0): the output row is also quantised for the NEXT mat-mul (its INIT pass,
     // ggml.c:11462-11476) by whichever CTA completes a 256-value chunk; qctr = M / 256 zero-initialised, self-resetting counters
     const ActQ * qout; unsigned * qctr;
-    // The kernel in front of this one in the stream produces NOTHING this one reads (ffn_up behind qkv, wo behind ffn_down: their inputs
-    // were complete before that kernel started): with programmatic dependent launch the rows then stream from the moment the CTAs are
-    // resident, and griddepcontrol.wait moves to the END of the kernel, where it only keeps the chain of completions intact (whoever
-    // waits for this grid has thereby waited for the one in front of it)
+    // The kernel in front of this one in the stream produces NOTHING this one reads, and everything it reads was complete AND flushed before
+    // that kernel's main body ran (ffn_up behind qkv: both read the LayerNorm's output): with programmatic dependent launch the rows then
+    // stream from the moment the CTAs are resident, and griddepcontrol.wait moves to the END of the kernel, where it only keeps the chain
+    // of completions intact (whoever waits for this grid has thereby waited for the one in front of it)
     int late_wait; };
 void   launch_mmv(const WPlanes & W, const ActQ & A, float * y, int64_t y_stride, MmvEpilogue epi, cudaStream_t stream);
 void   launch_mmv_f(const WPlanes & W, const float * x, int64_t x_stride, int N, float * y, int64_t y_stride, cudaStream_t stream); // f16/f32 weights
