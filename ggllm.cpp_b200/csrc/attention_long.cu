@@ -4,20 +4,20 @@
 // differs is how the work is laid out, because at thousands of keys these kernels stop being hidden beside ffn_up / ffn_down:
 //   * ONE WAVE: n_splits x n_head_kv x head groups ~ the SM count.  Beside the mat-vec CTAs an SM has registers for exactly one of these
 //     128-thread CTAs, so the 256-CTA grid of attention.cu runs as two waves of latency-bound CTAs
-//   * rows stream through a warp-private cp.async ring (AL_R stages of AL_B rows): a lane reads back exactly the bytes it copied, so no
-//     barrier is involved and AL_R - 1 stages stay in flight per warp without holding registers
-//   * scores: ncu on attention.cu's kernel at 8k keys (profiles/r2_notes.md): 151 instructions per key, one warp per scheduler, issue slot
-//     29 % busy, no memory stall -- a latency-bound instruction stream.  Here a warp step covers AL_B = 4 keys, lane = (key, octet of the
-//     head dimension), the rotated query rows sit in shared memory, and the 16 per-head partials are reduced over the 8 lanes of a key
-//     only (14 shuffles per 4 keys instead of 64): 79 instructions per key
-//   * values: the exponentials of a ring stage (4 keys x 16 heads) are taken two per lane right where the stage is consumed (no separate
-//     pass over a [key][head] array of the whole split) and handed to the warp through 256 bytes of shared memory (four broadcast
-//     LDS.128 per key instead of 16 shuffles); the scores travel through the same ring as the V rows: 97 instructions per key (119 with
-//     shuffles, profiles/r2_attention_long.md)
-// Measured (Falcon-40B Q4_K, tok/s at n_past 8 / 2000 / 8000): attention.cu 210 / 195 / 135, this file 210 / 204 / 160; Falcon-180B
-// geometry (10 layers) at 8000: 314 -> 377.  Falcon-7B (one KV head, five head groups re-reading it) is 8-10 % SLOWER with it at every length, and so are
-// short contexts in general (more shared memory per CTA of the fixed grid): launch_attention picks this path only for n_head_kv > 1 and
-// more than attention_long_threshold() keys; the decode graphs of engine.cu are captured per tier.
+//   * rows stream through a warp-private cp.async ring (AL_KR stages of AL_KB = 8 rows, padded against bank conflicts): only __syncwarp
+//     is involved and the next stage is in flight while one is consumed, without holding registers
+//   * both products run on the TENSOR CORES: the G <= 16 query heads of a KV head are exactly the M = 16 of a warp-level mma.  ncu on
+//     attention.cu's kernels at 8k keys (profiles/r2_notes.md): 151 + 119 instructions per key, one warp per scheduler, issue slots 29 %
+//     busy, no memory stall -- latency-bound instruction streams that also take issue slots from the mat-vec CTAs beside them.  A CUDA-core
+//     rewrite (lane = (key, octet), shared-memory broadcasts) reached 79 + 97; mma.sync m16n8k16 (scores) / m16n8k8 (values) with the fp32
+//     operands split into fp16 hi + lo terms reaches 24 + 39 (profiles/r2_attention_long.md): 13 + 21 us per layer alone at 8000 keys
+//   * values: the exponentials come out directly in A-fragment layout (lane = heads gid, gid + 8 x keys 2 tig, 2 tig + 1), no separate pass,
+//     no [key][head] array, no shuffles; the scores travel through the same ring as the V rows
+// Measured (Falcon-40B Q4_K, tok/s at n_past 8 / 2000 / 8000): attention.cu 210 / 195 / 135, this file 211 / 210 / 192; Falcon-180B
+// Q4_K at 8000 on one GPU (BASELINE config 5): 38.0 -> 53.9 tok/s together with the 256 x 2 mat-vec shape for K = 14848.  Against the
+// oracle the tiny-model evals stay at the 1e-8 * S level.  Falcon-7B (one KV head, five head groups re-reading it) was 8-10 % SLOWER
+// with the one-wave layout at every length (CUDA-core version), and short contexts gain nothing: launch_attention picks this path only
+// for n_head_kv > 1 and more than attention_long_threshold() keys; the decode graphs of engine.cu are captured per tier.
 #include "kernels.h"
 #include "actquant.cuh"
 
@@ -25,11 +25,9 @@ __device__ __forceinline__ float exp_f16lut_l(float v) {      // table_exp_f16[f
     return __half2float(__float2half_rn(expf(__half2float(__float2half_rn(v)))));
 }
 
-#define AL_THREADS 128                   // small CTAs at <= 85 registers: one fits beside ffn_up's two 256-thread CTAs on every SM
+#define AL_THREADS 128                   // small CTAs (<= 104 registers): one fits beside ffn_up's two 256-thread CTAs on every SM
 #define AL_WARPS (AL_THREADS / 32)
 #define AL_MAX_SPLITS 32                 // the scratch holds this many partials per head (attention.cu's layout); the launcher picks n_splits <= it
-#define AL_B 4                           // key rows per warp and ring stage
-#define AL_R 4                           // ring stages per warp
 #define AL_G 16                          // query heads per KV head handled together (n_head / n_head_kv <= 16 per CTA, more in grid.z)
 
 struct AttnLongArgs {
@@ -42,7 +40,6 @@ struct AttnLongArgs {
     int fuse_rope; float theta_scale; float * kc_w; float * vc_w; __half * k16; __half * vt16; int ctx_pad;     // see AttnParams::fuse_rope
 };
 
-__device__ __forceinline__ void cp_async8(void * smem, const void * g) { asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(smem_u32(smem)), "l"(g) : "memory"); }
 __device__ __forceinline__ void cp_async16(void * smem, const void * g) { asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(smem_u32(smem)), "l"(g) : "memory"); }
 __device__ __forceinline__ void cp_async4(void * smem, const void * g) { asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(smem_u32(smem)), "l"(g) : "memory"); }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
@@ -57,8 +54,6 @@ __device__ __forceinline__ void split_range(int T, int ns, int split, int & k_lo
     const int per = split_keys(T, ns);
     k_lo = min(T, split * per); k_hi = min(T, k_lo + per);
 }
-// ring stages warp `warp` needs for its keys jj = warp + AL_WARPS * (AL_B * stage + b) < nk
-__device__ __forceinline__ int warp_stages(int nk, int warp) { return nk > warp ? (nk - warp + AL_WARPS * AL_B - 1) / (AL_WARPS * AL_B) : 0; }
 
 // ---- tensor-core helpers.  The G <= 16 query heads of a KV head are exactly the M = 16 of a warp-level mma: scores = Q[16 x 64] K^T and
 // O += E[16 x keys] V run on the tensor cores (legacy mma.sync, the right size for a 16-row problem), which takes the instruction count
