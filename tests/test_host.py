@@ -148,3 +148,36 @@ def test_bench_line_contract(monkeypatch, capsys):
     assert set(("value", "unit", "cores", "kind", "sample")) <= set(d["cpu_baseline"])
     assert d["higher_is_better"] is True and d["vs_baseline"] is None and d["value"] == 208.0 and d["e2e"]["value"] == 205.0
     assert set(d["configs"]) == {"cfg1", "cfg2", "cfg4", "cfg5"}
+
+
+def test_fp16_split_products_reach_fp32_dot_accuracy():
+    """The arithmetic behind the tensor-core decode attention (attention_long.cu): an fp32 operand is split into fp16 terms hi = f16(x),
+    lo = f16(x - hi); products of fp16 pairs are exact in the fp32 accumulator, and hi*hi + hi*lo + lo*hi differs from the exact product by
+    the dropped lo*lo term (~2^-22).  Emulated here in numpy: a 64-term dot product through the three-term split is as close to the fp64
+    result as a plain fp32 dot product is for query / key magnitudes of 0.3 .. 100; below 0.125 the lo term is an fp16 subnormal and the
+    representation error becomes ABSOLUTE, <= 2^-25 per element -- for a score that feeds exp(s - max) that is as good.  The softmax
+    weights e = f16(exp(f16(x))) are fp16 values already, so that operand of the second product needs no split."""
+    rng = np.random.default_rng(5)
+    for mag in (1e-3, 1e-2, 0.3, 1.0, 30.0, 100.0):
+        q = (mag * rng.standard_normal((4096, 64))).astype(np.float32)
+        k = (mag * rng.standard_normal((4096, 64))).astype(np.float32)
+        def split(x):
+            hi = x.astype(np.float16)
+            lo = (x - hi.astype(np.float32)).astype(np.float16)
+            return hi.astype(np.float32), lo.astype(np.float32)
+        qh, ql = split(q); kh, kl = split(k)
+        # every product of two fp16 values has <= 22 significant bits: exact in fp32; the accumulation is fp32 like the mma's
+        terms = np.concatenate([qh * kh, qh * kl, ql * kh], axis=1)
+        got = terms.sum(axis=1, dtype=np.float32)
+        exact = (q.astype(np.float64) * k.astype(np.float64)).sum(axis=1)
+        plain = (q * k).sum(axis=1, dtype=np.float32)
+        scale = (np.abs(q.astype(np.float64)) * np.abs(k.astype(np.float64))).sum(axis=1)
+        if mag < 0.125:
+            bound = 64 * 2.0 ** -24 * max(float(np.abs(q).max()), float(np.abs(k).max()))      # 64 terms x (2^-25 |k| + 2^-25 |q|)
+            assert np.abs(got - exact).max() <= bound, (mag, float(np.abs(got - exact).max()), bound)
+            continue
+        err_split, err_plain = np.abs(got - exact) / scale, np.abs(plain - exact) / scale
+        assert err_split.max() <= 4e-7, (mag, float(err_split.max()))                   # 64 terms x 2^-24 rounding + 2^-22 dropped term, with margin
+        assert np.median(err_split) <= 4 * np.median(err_plain) + 1e-9, (mag, float(np.median(err_split)), float(np.median(err_plain)))
+    e = np.exp(rng.uniform(-12, 0, 10000).astype(np.float16).astype(np.float32)).astype(np.float16)
+    assert np.array_equal(e.astype(np.float32).astype(np.float16), e)                    # e is representable: the A operand of E V is exact
