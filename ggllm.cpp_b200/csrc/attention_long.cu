@@ -57,10 +57,11 @@ __device__ __forceinline__ void split_range(int T, int ns, int split, int & k_lo
 
 // ---- tensor-core helpers.  The G <= 16 query heads of a KV head are exactly the M = 16 of a warp-level mma: scores = Q[16 x 64] K^T and
 // O += E[16 x keys] V run on the tensor cores (legacy mma.sync, the right size for a 16-row problem), which takes the instruction count
-// per key from 79 + 97 (CUDA cores, above) to ~15 + ~25.  fp32 operands are split into two fp16 terms (hi = fp16(x), lo = fp16(x - hi):
+// per key from 79 + 97 (the CUDA-core version of this file) to 24 + 39.  fp32 operands are split into two fp16 terms (hi = fp16(x), lo = fp16(x - hi):
 // 22 significant bits); products of fp16 pairs are exact in the fp32 accumulator, the dropped lo x lo term is 2^-22 of the product -- the
 // fp32 dot product's own rounding level (below |x| = 0.125 the lo term is an fp16 subnormal: the error is then absolute, <= 2^-25 per
-// element; tests/test_host.py emulates both regimes).  e = table_exp_f16[...] IS an fp16 value: the A operand of the second product is exact.
+// element; tests/test_host.py emulates both regimes; an operand beyond fp16's 65504 would overflow the hi term -- Falcon's rotated q / k
+// rows and v rows are O(1) .. O(100)).  e = table_exp_f16[...] IS an fp16 value: the A operand of the second product is exact.
 __device__ __forceinline__ void split_h2(float x0, float x1, uint32_t & hi, uint32_t & lo) {
     const __half2 h = __floats2half2_rn(x0, x1);
     const float2 hf = __half22float2(h);
