@@ -474,8 +474,8 @@ int attention_long_threshold() {             // read on every call (graph builds
 int launch_attention(const float * qkv, const float * k_cache, const float * v_cache, float * out, int64_t out_stride,
                       const AttnParams & p, float * scratch, cudaStream_t stream) {
     if (p.n_tok <= 0) return 0;
-    // long contexts of grouped-query models: one-wave kernels with cp.async rings (measured crossover, see attention_long.cu)
-    const bool long_ctx = p.n_head_kv > 1 && (p.n_past_dev ? p.long_ctx != 0 : p.n_past + 1 > attention_long_threshold());
+    // long contexts: one-wave tensor-core kernels with cp.async rings (measured crossover, see attention_long.cu)
+    const bool long_ctx = p.n_past_dev ? p.long_ctx != 0 : p.n_past + 1 > attention_long_threshold();
     if (long_ctx && launch_attention_long(qkv, k_cache, v_cache, out, p, scratch, stream)) return 2;
     if (launch_attention_split(qkv, k_cache, v_cache, out, p, scratch, stream)) return 2;
     if (p.fuse_rope) {                                         // fallback kernel: RoPE + append in their own kernel, in place, as before

@@ -1,4 +1,4 @@
-// attention_long.cu -- split-KV decode attention (n_tok == 1, head_dim 64, grouped-query models) for LONG contexts.
+// attention_long.cu -- split-KV decode attention (n_tok == 1, head_dim 64) for LONG contexts.
 //
 // Same contract and scratch layout as the split-KV kernels of attention.cu (see there for the numerics, libfalcon.cpp:2285-2366); what
 // differs is how the work is laid out, because at thousands of keys these kernels stop being hidden beside ffn_up / ffn_down:
@@ -15,9 +15,9 @@
 //     no [key][head] array, no shuffles; the scores travel through the same ring as the V rows
 // Measured (Falcon-40B Q4_K, tok/s at n_past 8 / 2000 / 8000): attention.cu 210 / 195 / 135, this file 211 / 210 / 192; Falcon-180B
 // Q4_K at 8000 on one GPU (BASELINE config 5): 38.0 -> 53.9 tok/s together with the 256 x 2 mat-vec shape for K = 14848.  Against the
-// oracle the tiny-model evals stay at the 1e-8 * S level.  Falcon-7B (one KV head, five head groups re-reading it) was 8-10 % SLOWER
-// with the one-wave layout at every length (CUDA-core version), and short contexts gain nothing: launch_attention picks this path only
-// for n_head_kv > 1 and more than attention_long_threshold() keys; the decode graphs of engine.cu are captured per tier.
+// oracle the tiny-model evals stay at the 1e-8 * S level.  Falcon-7B (one KV head, five head groups re-reading it): 631 / 598 / 308 ->
+// 634 / 607 / 500 tok/s at n_past 1100 / 2000 / 8000.  Short contexts gain nothing (and the CUDA-core one-wave version was slower there):
+// launch_attention picks this path above attention_long_threshold() keys; the decode graphs of engine.cu are captured per tier.
 #include "kernels.h"
 #include "actquant.cuh"
 

@@ -89,7 +89,7 @@ struct AttnParams {
     // decides by itself
     int long_ctx;
 };
-int    attention_long_threshold();          // keys above which grouped-query decode attention switches to attention_long.cu
+int    attention_long_threshold();          // keys above which decode attention switches to attention_long.cu
 // fused: rope(Q), rope(K) -> K cache append, V cache append      (libfalcon.cpp:2229-2281)
 void   launch_rope_kv_append(float * qkv, float * k_cache, float * v_cache, const AttnParams & p, float theta_scale, cudaStream_t stream);
 // out[t][h*head_dim + i] = softmax(scale * Q K^T + causal mask) V   (libfalcon.cpp:2285-2366)

@@ -98,10 +98,10 @@ def test_float_and_mixed_weight_models_prompt_gemm(gpu, hp, wt, overrides):
 
 @pytest.mark.parametrize("hp", [TINY_40B, TINY_7B])
 def test_decode_across_the_long_context_tier(gpu, hp, monkeypatch):
-    """Grouped-query models switch to the one-wave cp.async attention kernels (attention_long.cu) above attention_long_threshold() keys;
-    the decode graphs are captured per tier.  With the threshold moved to 12 keys a tiny model crosses it in the middle of a decode run
-    and of a device-side greedy generation: every eval inside the tolerance contract, generation == host arg-max loop.  (Falcon-7B has
-    one KV head and stays on the short-context kernels: same run, same checks.)"""
+    """Decode attention switches to the one-wave tensor-core kernels (attention_long.cu) above attention_long_threshold() keys; the decode
+    graphs are captured per tier.  With the threshold moved to 12 keys a tiny model crosses it in the middle of a decode run and of a
+    device-side greedy generation: every eval inside the tolerance contract, generation == host arg-max loop (grouped-query and
+    multi-query geometry)."""
     monkeypatch.setenv("B200_ATTN_LONG_FROM", "12")
     long0 = gpu.lib().b200_attention_long_launches()
     tensors = synth_model(hp, po.Q4_K if hp is TINY_40B else po.Q4_0, seed=7)
@@ -119,7 +119,7 @@ def test_decode_across_the_long_context_tier(gpu, hp, monkeypatch):
     f.eval(prompt, 0)                                   # same start state for the device loop
     got = f.generate_greedy(first, len(prompt), 16)
     assert list(got) == want
-    assert (gpu.lib().b200_attention_long_launches() > long0) == (hp["n_head_kv"] > 1)      # the long tier was really taken / really left alone
+    assert gpu.lib().b200_attention_long_launches() > long0                                   # the long tier was really taken
     f.free()
 
 
