@@ -181,3 +181,34 @@ def test_fp16_split_products_reach_fp32_dot_accuracy():
         assert np.median(err_split) <= 4 * np.median(err_plain) + 1e-9, (mag, float(np.median(err_split)), float(np.median(err_plain)))
     e = np.exp(rng.uniform(-12, 0, 10000).astype(np.float16).astype(np.float32)).astype(np.float16)
     assert np.array_equal(e.astype(np.float32).astype(np.float16), e)                    # e is representable: the A operand of E V is exact
+
+
+def test_launch_list_tool_pivots_an_ncu_csv(tmp_path):
+    """tools/launch_list.py (the script behind profiles/r2_bench_launches.csv and r2_traffic.json): one row per launch, the last COMPLETE
+    decode step only, DRAM bytes per mat-vec launch"""
+    import subprocess, csv as _csv, json
+    ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = ["ID", "Process ID", "Process Name", "Host Name", "Kernel Name", "Context", "Stream", "Block Size", "Grid Size", "Device", "CC",
+           "Section Name", "Metric Name", "Metric Unit", "Metric Value"]
+    rows, lid = [hdr], 0
+    def launch(name, ns, rd):
+        nonlocal lid
+        for metric, unit, val in (("gpu__time_duration.sum", "us", ns / 1e3), ("dram__bytes_read.sum", "Mbyte", rd / 1e6), ("dram__bytes_write.sum", "byte", 0)):
+            rows.append([str(lid), "1", "python", "box", name, "1", "14", "(256, 1, 1)", "(296, 1, 1)", "0", "10.0", "Command line profiler metrics", metric, unit, "%.6f" % val])
+        lid += 1
+    for step in range(3):                                   # the third step is cut short by the capture limit
+        launch("dequant_rows_kernel(WPlanes, const int *, int, float *, long)", 5000, 1e4)
+        for i in range(4 if step < 2 else 2):
+            launch("void mmv_fast_kernel<12, 256, 1, 8, 0>(WPlanes, FastX, float *, long, Epi)", 20000, 80e6)
+        launch("attn_dec_scores_kernel(AttnDecArgs)", 6000, 1e5)
+    raw, out, tr = tmp_path / "raw.csv", tmp_path / "out.csv", tmp_path / "traffic.json"
+    with open(raw, "w", newline="") as f:
+        f.write("==PROF== Connected to process 1\n")
+        _csv.writer(f, quoting=_csv.QUOTE_ALL).writerows(rows)
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "launch_list.py"), str(raw), str(out), "--traffic", str(tr)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    body = [l for l in open(out).read().splitlines()[2:] if l]
+    assert len(body) == 6                                    # the second (last complete) step: gather + 4 mat-vecs + scores
+    t = json.load(open(tr))
+    assert t["matvec_launches_per_step"] == 4 and abs(t["dram_bytes_per_matvec_launch"] - 80e6) < 1.0
+    assert "mmv_fast_kernel" in r.stdout and "87.9 %" in r.stdout          # 80 of 91 us
